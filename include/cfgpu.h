@@ -1,0 +1,110 @@
+/* cfgpu.h — C ABI of libcfgpu.so, the B200 (sm_100a) implementation of ContextForge's plugin
+ * hook-chain hot path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   cf_builder_add_pattern + cf_compile
+ *       -> `re.compile(...)` at plugin construction:
+ *          plugins/regex_filter/search_replace.py:67-75,
+ *          plugins/harmful_content_detector/harmful_content_detector.py:70-87,
+ *          plugins/deny_filter/deny.py:43-46
+ *   cf_scan / cf_scan_host
+ *       -> the per-string matcher loops:
+ *          harmful `_scan_text`  plugins/harmful_content_detector/harmful_content_detector.py:92-107
+ *          deny `word in value`  plugins/deny_filter/deny.py:59-60
+ *          regex_filter "does any rule match" (dirty detection for cf_sub_host)
+ *   cf_sub_host
+ *       -> `pattern.sub(replacement, value)` applied rule after rule:
+ *          plugins/regex_filter/search_replace.py:127-130,147-155
+ *   cf_mask_host
+ *       -> `mask_sensitive_json_bytes(payload, max_depth)`:
+ *          crates/request_logging_masking_native_extension/src/lib.rs:346-360
+ *   cf_toon_host
+ *       -> `orjson.loads` + `toon.encode` + "only if smaller" of `_process_content_item`:
+ *          plugins/toon_encoder/toon_encoder.py:277-303, plugins/toon_encoder/toon.py:82-565
+ *
+ * Conventions: every function returns CF_OK (0) or a negative CF_E_* code and never throws.
+ * All buffers are caller-owned.  A cf_ctx belongs to one device; calls on one ctx must be
+ * serialised by the caller (the Python host holds one ctx per process/GPU).
+ *
+ * Packed stream layout (host and device), used by every data entry point:
+ *     stream  = unit_0 0xFF unit_1 0xFF ... unit_{n-1} 0xFF      (UTF-8; 0xFF never occurs in UTF-8)
+ *     offsets = uint64[n+1]; offsets[i] = start of unit_i; offsets[n] = stream length
+ *     unit_i  = stream[offsets[i] .. offsets[i+1]-1)
+ */
+#ifndef CFGPU_H
+#define CFGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CF_OK 0
+#define CF_E_CUDA (-1)        /* CUDA runtime/driver error; see cf_last_error */
+#define CF_E_BADARG (-2)
+#define CF_E_UNSUPPORTED (-3) /* valid pattern the engine cannot express (caller must fail loudly) */
+#define CF_E_TOO_LARGE (-4)   /* automaton/state explosion or table limits */
+#define CF_E_CAPACITY (-5)    /* caller-provided output buffer too small; required size reported */
+#define CF_E_NOGPU (-6)       /* no usable CUDA device */
+#define CF_E_NOMEM (-7)
+
+#define CF_PAT_SEARCH 0u   /* existence only (harmful / deny) */
+#define CF_PAT_ORDERED 1u  /* regex_filter rule: also build the leftmost-first automaton */
+
+typedef struct cf_builder cf_builder;
+typedef struct cf_ctx cf_ctx;
+typedef struct cf_prog cf_prog;
+typedef struct cf_batch cf_batch;
+
+/* ---------------- program construction (host only; usable without a GPU) ---------------- */
+int cf_builder_new(cf_builder** out);
+void cf_builder_free(cf_builder* b);
+const char* cf_builder_last_error(cf_builder* b);
+/* code points that are \w (sorted, disjoint inclusive ranges: lo0 hi0 lo1 hi1 ...) */
+int cf_builder_set_word_set(cf_builder* b, const uint32_t* ranges, uint32_t nranges);
+/* ast: serialized pattern (see csrc/re_backend.h); returns the pattern's bit index */
+int cf_builder_add_pattern(cf_builder* b, const uint32_t* ast, uint32_t nwords, uint32_t flags,
+                           uint32_t* out_index);
+/* literal replacement bytes (UTF-8) for a CF_PAT_ORDERED pattern */
+int cf_builder_set_replacement(cf_builder* b, uint32_t pattern_index, const uint8_t* repl, uint32_t len);
+/* run the host part of compilation now (idempotent); reports table sizes */
+typedef struct cf_compile_stats {
+  uint32_t n_patterns, words_per_bitmap, n_classes, n_states, n_accsets, n_ordered;
+  uint32_t trans_bytes, reserved;
+} cf_compile_stats;
+int cf_builder_compile_host(cf_builder* b, cf_compile_stats* out);
+
+/* ---------------- device context / program ---------------- */
+int cf_init(int device_ordinal, cf_ctx** out);
+void cf_shutdown(cf_ctx* ctx);
+const char* cf_last_error(cf_ctx* ctx);
+int cf_compile(cf_ctx* ctx, cf_builder* b, cf_prog** out); /* uploads tables to HBM */
+void cf_free_prog(cf_prog* p);
+uint32_t cf_prog_words(const cf_prog* p);    /* u64 words per verdict bitmap (W) */
+uint32_t cf_prog_patterns(const cf_prog* p);
+
+/* ---------------- batches (device-resident packed streams) ---------------- */
+int cf_batch_create(cf_ctx* ctx, uint64_t max_stream_bytes, uint32_t max_units, cf_batch** out);
+void cf_batch_free(cf_batch* b);
+/* async H2D of a packed stream on `cuda_stream` (cudaStream_t, may be NULL) */
+int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
+                    const uint64_t* offsets, uint32_t n_units, void* cuda_stream);
+uint32_t cf_batch_units(const cf_batch* b);
+uint64_t cf_batch_bytes(const cf_batch* b);
+
+/* ---------------- stage 1: multi-pattern scan ---------------- */
+/* device-resident: d_bitmaps = device pointer to n_units*W uint64 (may be torch-owned memory) */
+int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cuda_stream);
+/* host buffers: upload + scan + download, synchronous; h_bitmaps = n_units*W uint64 */
+int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
+                 const uint64_t* offsets, uint32_t n_units, uint64_t* h_bitmaps);
+/* number of kernels launched by this ctx so far (for bench.py's gpu_launches) */
+uint64_t cf_kernel_launches(const cf_ctx* ctx);
+
+/* last scan's device-side counters: [0]=prefilter candidates, [1]=DFA verify steps */
+int cf_scan_counters(cf_ctx* ctx, uint64_t out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFGPU_H */

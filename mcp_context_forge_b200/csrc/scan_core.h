@@ -1,0 +1,137 @@
+// scan_core.h — data layout + the per-candidate verification routine shared by the CUDA scan
+// kernel (cfgpu.cu) and the host-side table simulator used only by the CPU unit tests
+// (host_sim.cpp).  Everything here is plain C++ that compiles for host and device.
+//
+// Reference semantics being implemented (all relative to /root/reference):
+//   * harmful_content_detector: `pat.search(text)` for each IGNORECASE pattern
+//       plugins/harmful_content_detector/harmful_content_detector.py:92-107
+//   * deny_filter: `word in value`                      plugins/deny_filter/deny.py:59-60
+//   * regex_filter: `pattern.sub(replacement, value)`   plugins/regex_filter/search_replace.py:127-130
+// A "unit" is one Python `str` handed to those calls, UTF-8 encoded.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define CF_HD __host__ __device__ __forceinline__
+#else
+#define CF_HD inline
+#endif
+
+namespace cf {
+
+// ---------------------------------------------------------------------------------------------
+// Packed stream layout (HBM and host):
+//   stream = unit_0 0xFF unit_1 0xFF ... unit_{n-1} 0xFF          (0xFF never occurs in UTF-8)
+//   offsets[i] = byte offset of unit_i, offsets[n] = total length including terminators
+//   unit_i = stream[offsets[i] .. offsets[i+1]-1)   (the byte at offsets[i+1]-1 is its 0xFF)
+// On the device the stream is preceded by CF_FRONT_PAD bytes of 0xFF and followed by 0xFF up to a
+// multiple of the scan tile plus one extra tile, so tile loads never need bounds checks.
+// ---------------------------------------------------------------------------------------------
+static const uint8_t  TERM      = 0xFF;
+static const uint32_t FRONT_PAD = 256;
+
+// previous-character contexts (needed by \b, \B, ^, \A)
+enum : uint32_t { P_START = 0, P_WORD = 1, P_NL = 2, P_OTHER = 3 };
+
+static const uint32_t DEAD = 0;         // DFA state 0 is the dead state
+static const uint32_t ACC_SHIFT = 16;   // transition entry = next_state | acc_index << 16
+
+// Tables for one anchored DFA over code-point classes.
+struct DfaTables {
+  const uint16_t* ascii_cls;    // [128] class of each ASCII code point
+  const uint32_t* range_start;  // [nranges] first code point of each non-ASCII range (sorted, [0]=0x80)
+  const uint16_t* range_cls;    // [nranges] class of that range
+  const uint8_t*  cls_ctx;      // [ncls] P_WORD / P_NL / P_OTHER for a char of this class
+  const uint32_t* trans;        // [nstates * ncols]; ncols = ncls + 1, column ncls = end-of-text
+  const uint64_t* accsets;      // [naccs * W] pattern bitmaps; acc index 0 = empty set
+  uint32_t nranges;
+  uint32_t ncols;
+  uint32_t W;                   // u64 words per verdict bitmap
+  uint32_t start_state[4];      // indexed by previous-character context
+};
+
+// Decode one UTF-8 scalar (generalised: surrogates ED A0..BF xx are accepted, Python's
+// 'surrogatepass').  `p < end` is required.  Never reads at or beyond `end`.
+CF_HD uint32_t utf8_decode(const uint8_t* s, uint64_t p, uint64_t end, uint32_t* len) {
+  uint32_t b0 = s[p];
+  if (b0 < 0x80) { *len = 1; return b0; }
+  uint32_t need = (b0 >= 0xF0) ? 4u : (b0 >= 0xE0) ? 3u : (b0 >= 0xC0) ? 2u : 1u;
+  if (need == 1 || p + need > end) { *len = 1; return 0xFFFD; }  // stray continuation / truncated
+  uint32_t cp = b0 & (0xFFu >> (need + 1));
+  for (uint32_t k = 1; k < need; ++k) cp = (cp << 6) | (s[p + k] & 0x3Fu);
+  *len = need;
+  return cp;
+}
+
+CF_HD uint32_t classify(const DfaTables& t, uint32_t cp) {
+  if (cp < 0x80) return t.ascii_cls[cp];
+  uint32_t lo = 0, hi = t.nranges;  // last range with start <= cp
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (t.range_start[mid] <= cp) lo = mid; else hi = mid;
+  }
+  return t.range_cls[lo];
+}
+
+// Context of the character that ends right before byte position p (p > ustart).
+CF_HD uint32_t prev_context(const DfaTables& t, const uint8_t* s, uint64_t ustart, uint64_t p) {
+  uint64_t q = p - 1;
+  while (q > ustart && (s[q] & 0xC0) == 0x80 && p - q < 4) --q;
+  uint32_t len;
+  uint32_t cp = utf8_decode(s, q, p, &len);
+  return t.cls_ctx[classify(t, cp)];
+}
+
+// Run the anchored DFA from byte position p of the unit [ustart, uend); OR the bitmaps of all
+// patterns that match starting exactly at p (any end) into bits[0..W).  Returns the number of
+// DFA steps (for statistics).  Search semantics: existence only.
+CF_HD uint32_t verify_search(const DfaTables& t, const uint8_t* s, uint64_t ustart, uint64_t uend,
+                             uint64_t p, uint64_t* bits) {
+  uint32_t ctx = (p == ustart) ? (uint32_t)P_START : prev_context(t, s, ustart, p);
+  uint32_t S = t.start_state[ctx];
+  uint64_t q = p;
+  uint32_t steps = 0;
+  while (S != DEAD) {
+    uint32_t col, len = 0;
+    if (q >= uend) col = t.ncols - 1;
+    else col = classify(t, utf8_decode(s, q, uend, &len));
+    uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
+    uint32_t a = e >> ACC_SHIFT;
+    if (a) for (uint32_t w = 0; w < t.W; ++w) bits[w] |= t.accsets[(uint64_t)a * t.W + w];
+    S = e & 0xFFFFu;
+    ++steps;
+    if (q >= uend) break;
+    q += len;
+  }
+  return steps;
+}
+
+// Leftmost-first match of ONE ordered (priority) DFA anchored at p.  Transition entries carry
+// bit 16 = "a match ends before this character".  Returns the match end (byte offset) or
+// UINT64_MAX when nothing matches at p.  This is Python's backtracking preference order
+// (plugins/regex_filter/search_replace.py:130 -> re.Pattern.sub).
+CF_HD uint64_t match_first(const DfaTables& t, const uint8_t* s, uint64_t ustart, uint64_t uend,
+                           uint64_t p) {
+  uint32_t ctx = (p == ustart) ? (uint32_t)P_START : prev_context(t, s, ustart, p);
+  uint32_t S = t.start_state[ctx];
+  uint64_t q = p, last = ~0ull;
+  while (S != DEAD) {
+    uint32_t col, len = 0;
+    if (q >= uend) col = t.ncols - 1;
+    else col = classify(t, utf8_decode(s, q, uend, &len));
+    uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
+    if (e >> ACC_SHIFT) last = q;
+    S = e & 0xFFFFu;
+    if (q >= uend) break;
+    q += len;
+  }
+  return last;
+}
+
+// Prefilter: E[b] = N<<24 | A<<16 | B<<8 | C, eight pattern buckets per field.
+//   acc' = ((acc >> 8) | 0xFF000000) & E[b]
+// After feeding byte p, (acc & 0xFF) != 0  <=>  some bucket admits a match starting at p-2
+// (previous byte admissible, and the first three bytes admissible).  No false negatives.
+CF_HD uint32_t filter_step(uint32_t acc, uint32_t e) { return ((acc >> 8) | 0xFF000000u) & e; }
+
+}  // namespace cf

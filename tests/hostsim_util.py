@@ -1,0 +1,110 @@
+"""ctypes access to tests/hostsim/libcfhostsim.so (TEST-ONLY CPU simulation of the scan tables)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "tests", "hostsim", "libcfhostsim.so")
+SRCS = [
+    os.path.join(ROOT, "tests", "hostsim", "host_sim.cpp"),
+    os.path.join(ROOT, "mcp_context_forge_b200", "csrc", "cf_host.cpp"),
+    os.path.join(ROOT, "mcp_context_forge_b200", "csrc", "re_backend.cpp"),
+]
+
+
+def build(force=False):
+    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return SO
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", SO] + SRCS)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.cf_builder_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+class HostProgram:
+    """Builder wrapper mirroring mcp_context_forge_b200.engine.Program but running on the CPU simulator."""
+
+    def __init__(self):
+        from mcp_context_forge_b200 import regex_frontend as fe
+
+        self.fe = fe
+        self.L = lib()
+        self.b = ctypes.c_void_p()
+        assert self.L.cf_builder_new(ctypes.byref(self.b)) == 0
+        ws = np.array(fe.word_set(), dtype=np.uint32).reshape(-1)
+        assert self.L.cf_builder_set_word_set(self.b, ws.ctypes.data_as(ctypes.c_void_p), len(ws) // 2) == 0
+        self.n = 0
+
+    def add_ast(self, ast, ordered=False, repl=None):
+        a = np.array(ast, dtype=np.uint32)
+        idx = ctypes.c_uint32()
+        rc = self.L.cf_builder_add_pattern(self.b, a.ctypes.data_as(ctypes.c_void_p), len(a), 1 if ordered else 0, ctypes.byref(idx))
+        assert rc == 0, self.err()
+        if ordered:
+            r = (repl or "").encode("utf-8", "surrogatepass")
+            assert self.L.cf_builder_set_replacement(self.b, idx, r, len(r)) == 0
+        self.n += 1
+        return idx.value
+
+    def add(self, pattern, flags=0, ordered=False, repl=None):
+        return self.add_ast(self.fe.compile_ast(pattern, flags, "sub" if ordered else "search"), ordered, repl)
+
+    def err(self):
+        return self.L.cf_builder_last_error(self.b).decode()
+
+    def compile(self):
+        stats = (ctypes.c_uint32 * 8)()
+        rc = self.L.cf_builder_compile_host(self.b, stats)
+        if rc:
+            raise RuntimeError(f"compile rc={rc}: {self.err()}")
+        return list(stats)
+
+    def scan(self, units):
+        """units: list[str] -> list[int] bitmaps (python ints), stats"""
+        enc = [u.encode("utf-8", "surrogatepass") for u in units]
+        stream = b"".join(e + b"\xff" for e in enc)
+        offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+        np.cumsum([len(e) + 1 for e in enc], out=offs[1:])
+        W = (self.n + 63) // 64
+        bm = np.zeros(len(enc) * W, dtype=np.uint64)
+        st = np.zeros(2, dtype=np.uint64)
+        rc = self.L.cfh_scan(self.b, stream, ctypes.c_uint64(len(stream)), offs.ctypes.data_as(ctypes.c_void_p), len(enc),
+                             bm.ctypes.data_as(ctypes.c_void_p), st.ctypes.data_as(ctypes.c_void_p))
+        if rc:
+            raise RuntimeError(f"scan rc={rc}: {self.err()}")
+        out = []
+        for i in range(len(enc)):
+            v = 0
+            for w in range(W):
+                v |= int(bm[i * W + w]) << (64 * w)
+            out.append(v)
+        return out, [int(x) for x in st]
+
+    def sub(self, ordered_index, text):
+        e = text.encode("utf-8", "surrogatepass")
+        cap = len(e) * 8 + 1024
+        buf = ctypes.create_string_buffer(cap)
+        olen = ctypes.c_uint64()
+        nm = ctypes.c_uint64()
+        rc = self.L.cfh_sub(self.b, ordered_index, e, ctypes.c_uint64(len(e)), buf, ctypes.c_uint64(cap), ctypes.byref(olen), ctypes.byref(nm))
+        if rc:
+            raise RuntimeError(f"sub rc={rc}: {self.err()}")
+        return buf.raw[: olen.value].decode("utf-8", "surrogatepass"), nm.value
+
+    def __del__(self):
+        try:
+            self.L.cf_builder_free(self.b)
+        except Exception:
+            pass

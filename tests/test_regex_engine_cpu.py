@@ -1,0 +1,142 @@
+"""CPU validation of the regex front-end + C++ back-end tables (prefilter, search DFA, ordered
+DFA) against CPython `re`, through the TEST-ONLY host simulator (tests/hostsim).  The CUDA kernels
+run the very same tables and the same scan_core.h routines; their parity is tested in
+test_scan_gpu.py."""
+import random
+import re
+
+import pytest
+
+from hostsim_util import HostProgram
+
+DEFAULT_LEXICONS = {  # /root/reference/plugins/harmful_content_detector/harmful_content_detector.py:36-52
+    "self_harm": [r"\bkill myself\b", r"\bsuicide\b", r"\bself-harm\b", r"\bwant to die\b"],
+    "violence": [r"\bkill (?:him|her|them|someone)\b", r"\bshoot (?:him|her|them|someone)\b", r"\bstab (?:him|her|them|someone)\b"],
+    "hate": [r"\b(?:kill|eradicate) (?:[a-z]+) people\b", r"\b(?:racial slur|hate speech)\b"],
+}
+HARMFUL = [p for v in DEFAULT_LEXICONS.values() for p in v]
+
+WORDS = ["kill", "myself", "suicide", "self-harm", "want", "to", "die", "him", "her", "them", "someone", "shoot", "stab",
+         "eradicate", "people", "racial", "slur", "hate", "speech", "crap", "crud", "innovative", "the", "a", "of", "x",
+         "Kill", "KILL", "ſuicide", "Kill", "é", "ß", "naïve", "日本語", "😀", "İ", "ı", "ͅ", "µ", "μ", "١٢", "12", "0",
+         "_", "-", ".", ",", ":", "\n", "\t", " ", " ", "\x1c", "ǅ", "ǆ", "ᾳ", "Σ", "ς", "σ", "\ud800", "\U00010400", "\U00010428"]
+SEPS = [" ", " ", " ", "", "  ", "\n", "-", "_", ".", "é", "1"]
+
+
+def rand_text(rng, n):
+    out = []
+    for _ in range(n):
+        out.append(rng.choice(WORDS))
+        out.append(rng.choice(SEPS))
+    return "".join(out)
+
+
+def expected_bits(compiled, s):
+    v = 0
+    for i, c in enumerate(compiled):
+        if c.search(s):
+            v |= 1 << i
+    return v
+
+
+def test_default_lexicon_curated():
+    hp = HostProgram()
+    for p in HARMFUL:
+        hp.add(p, re.I)
+    comp = [re.compile(p, re.I) for p in HARMFUL]
+    cases = ["I want to die", "kill myself", "ſuicide", "Kill him now", "ésuicide", "suicide_", "suicide١", "suicide", "x suicide.",
+             "kill  him", "kill him", "Kill all people", "kill ſome people", "eradicate é people", "hate speech!", "", "self-harm",
+             "selfharm", "shoot someonex", "stab Them", "WANT TO DIE", "killmyself", "kill myselfé", "suicide\n", "\nsuicide"]
+    got, _ = hp.scan(cases)
+    for s, g in zip(cases, got):
+        assert g == expected_bits(comp, s), repr(s)
+
+
+def test_default_lexicon_fuzz():
+    rng = random.Random(1)
+    hp = HostProgram()
+    for p in HARMFUL:
+        hp.add(p, re.I)
+    comp = [re.compile(p, re.I) for p in HARMFUL]
+    units = [rand_text(rng, rng.randint(0, 40)) for _ in range(3000)]
+    got, stats = hp.scan(units)
+    bad = [(u, g, expected_bits(comp, u)) for u, g in zip(units, got) if g != expected_bits(comp, u)]
+    assert not bad, bad[:3]
+    assert any(got)
+
+
+FEATURE_PATTERNS = [
+    (r"crap", 0), (r"cr[au]p+", 0), (r"\bkill\b", re.I), (r"\Bill", re.I), (r"^kill", 0), (r"^kill", re.M), (r"die$", 0), (r"die$", re.M),
+    (r"\Akill", 0), (r"die\Z", 0), (r"k.ll", 0), (r"k.ll", re.S), (r"\d+", 0), (r"\w+-\w+", 0), (r"\s{2,}", 0), (r"[^a-z\s]+", re.I),
+    (r"(?i)STRASSE|straße", 0), (r"[a-zA-Z]{5,7}\b", 0), (r"a|ab|abc", 0), (r"(?:ab|a)(?:bc|c)?x", 0), (r"x*?y", 0), (r"h[ae]te? sp", 0),
+    (r"\bto\b.*\bdie\b", 0), (r"s(?i:UI)cide", 0), (r"[à-ÿ]+", re.I), (r"[kK]ill", 0), (r"ı|İ", re.I), (r"[^\W\d_]+", 0),
+    (r"(?a)\w+\d", 0), (r"µ", re.I), (r"ͅ", re.I), (r"ǆ", re.I), (r"σ+", re.I), (r"[\U00010400-\U00010410]", re.I), (r"\.", 0),
+    (r"", 0), (r"\b", 0), (r"\B", 0), (r"x?", 0), (r"(want|need) to (die|live)", 0), (r"[-_.]{2}", 0), (r"\x1c", 0), (r"\ud800", 0),
+]
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_feature_patterns_search_fuzz(chunk):
+    rng = random.Random(100 + chunk)
+    pats = FEATURE_PATTERNS[chunk::4]
+    hp = HostProgram()
+    for p, f in pats:
+        hp.add(p, f)
+    comp = [re.compile(p, f) for p, f in pats]
+    units = [rand_text(rng, rng.randint(0, 25)) for _ in range(1500)] + ["", "\n", "a", "é"]
+    got, _ = hp.scan(units)
+    for u, g in zip(units, got):
+        exp = expected_bits(comp, u)
+        assert g == exp, (u, [pats[i] for i in range(len(pats)) if (g ^ exp) >> i & 1])
+
+
+def test_many_patterns_multiword_bitmap():
+    rng = random.Random(7)
+    vocab = ["w%03d" % i for i in range(200)]
+    hp = HostProgram()
+    for w in vocab:
+        hp.add_ast(hp.fe.literal_ast(w))
+    stats = hp.compile()
+    assert stats[1] == 4  # 200 patterns -> 4 u64 words
+    units = [" ".join(rng.choice(vocab + ["zzz", "w", "w0"]) for _ in range(rng.randint(0, 12))) for _ in range(300)]
+    got, _ = hp.scan(units)
+    for u, g in zip(units, got):
+        exp = sum(1 << i for i, w in enumerate(vocab) if w in u)
+        assert g == exp
+
+
+SUB_RULES = [
+    (r"crap", 0, "crud"), (r"crud", 0, "yikes"), (r"cr[au]p+", 0, "X"), (r"\bkill\b", re.I, "[k]"), (r"a|ab|abc", 0, "<>"),
+    (r"(?:ab|a)(?:bc|c)?x", 0, ""), (r"x+?", 0, "y"), (r"\d+", 0, "#"), (r"\w+-\w+", 0, "é"), (r"[^a-z\s]+", re.I, "·"),
+    (r"k.l+", re.S, "日本"), (r"s(?i:UI)cide", 0, "ſ"), (r"to (?:die|live)\b", 0, "—"), (r"\s{2,}", 0, " "), (r"e\Z", 0, "E"),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(SUB_RULES)))
+def test_sub_leftmost_first_fuzz(idx):
+    pat, flags, repl = SUB_RULES[idx]
+    rng = random.Random(200 + idx)
+    hp = HostProgram()
+    hp.add(pat, flags, ordered=True, repl=repl)
+    c = re.compile(pat, flags)
+    units = [rand_text(rng, rng.randint(0, 25)) for _ in range(800)] + ["", "crapcrap", "abcx abx acx ax", "xxxx"]
+    for u in units:
+        got, n = hp.sub(0, u)
+        exp, en = c.subn(repl.replace("\\", "\\\\"), u)
+        assert got == exp and n == en, (u, got, exp)
+
+
+def test_unsupported_and_invalid():
+    from mcp_context_forge_b200.regex_frontend import UnsupportedPattern, compile_ast
+
+    for bad in [r"(a)\1", r"(?=a)b", r"(?<!a)b", r"(?>a)b", r"a*+", r"(a)?(?(1)b|c)"]:
+        with pytest.raises(UnsupportedPattern):
+            compile_ast(bad)
+    with pytest.raises(re.error):
+        compile_ast(r"(unclosed")
+    with pytest.raises(UnsupportedPattern):
+        compile_ast(r"a$b")
+    hp = HostProgram()
+    hp.add(r"x*", 0, ordered=True, repl="-")
+    with pytest.raises(RuntimeError):
+        hp.compile()  # empty-matching substitution rule -> CF_E_UNSUPPORTED
