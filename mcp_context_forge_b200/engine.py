@@ -1,0 +1,204 @@
+"""Host-side engine objects over the C ABI (include/cfgpu.h): Context, Program, Batch.
+
+These are thin: packing of Python strings into the packed-stream layout, pattern front-end calls,
+and error translation.  All data-path work happens in libcfgpu.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from ctypes import byref, c_uint32, c_uint64, c_void_p
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _native as N
+from . import regex_frontend as fe
+
+TERM = b"\xff"
+
+
+def encode_unit(u: Union[str, bytes]) -> bytes:
+    """UTF-8 with 'surrogatepass' so every Python str (even with lone surrogates) has a byte form
+    whose decoding reproduces the same code points the reference's `re` sees."""
+    return u if isinstance(u, bytes) else u.encode("utf-8", "surrogatepass")
+
+
+def pack_units(units: Sequence[Union[str, bytes]]) -> Tuple[bytes, np.ndarray]:
+    """Pack units into the stream layout of include/cfgpu.h: unit 0xFF unit 0xFF ..., uint64 offsets."""
+    enc = [encode_unit(u) for u in units]
+    stream = TERM.join(enc) + TERM if enc else b""
+    offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+    if enc:
+        np.cumsum(np.fromiter((len(e) + 1 for e in enc), dtype=np.uint64, count=len(enc)), out=offs[1:])
+    return stream, offs
+
+
+class Context:
+    """One per (process, device).  Not thread-safe: calls are serialised with a lock."""
+
+    _instances: dict = {}
+    _ilock = threading.Lock()
+
+    def __init__(self, device: int = 0):
+        self.lib = N.load()
+        self.h = c_void_p()
+        rc = self.lib.cf_init(device, byref(self.h))
+        if rc != N.CF_OK:
+            msg = self.lib.cf_last_error(self.h).decode() if self.h else "no CUDA device / driver"
+            raise N.CfError(rc, f"cf_init(device={device}) failed: {msg}")
+        self.device = device
+        self.lock = threading.RLock()
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        with cls._ilock:
+            ctx = cls._instances.get(device)
+            if ctx is None:
+                ctx = cls._instances[device] = Context(device)
+            return ctx
+
+    def check(self, rc: int, what: str) -> None:
+        if rc != N.CF_OK:
+            raise N.CfError(rc, f"{what}: {self.lib.cf_last_error(self.h).decode()}")
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.cf_kernel_launches(self.h))
+
+    def scan_counters(self) -> Tuple[int, int]:
+        out = (c_uint64 * 2)()
+        self.check(self.lib.cf_scan_counters(self.h, out), "cf_scan_counters")
+        return int(out[0]), int(out[1])
+
+
+class Program:
+    """A set of patterns compiled for the GPU.  Pattern i owns bit i of every verdict bitmap."""
+
+    def __init__(self):
+        self.lib = N.load()
+        self.b = c_void_p()
+        rc = self.lib.cf_builder_new(byref(self.b))
+        if rc != N.CF_OK:
+            raise N.CfError(rc, "cf_builder_new")
+        ws = np.asarray(fe.word_set(), dtype=np.uint32).reshape(-1)
+        self._check_b(self.lib.cf_builder_set_word_set(self.b, ws.ctypes.data, len(ws) // 2), "word set")
+        self.n_patterns = 0
+        self.n_ordered = 0
+        self.h: Optional[c_void_p] = None
+        self.ctx: Optional[Context] = None
+
+    def _check_b(self, rc: int, what: str) -> None:
+        if rc != N.CF_OK:
+            raise N.CfError(rc, f"{what}: {self.lib.cf_builder_last_error(self.b).decode()}")
+
+    def _add(self, ast: List[int], flags: int) -> int:
+        a = np.asarray(ast, dtype=np.uint32)
+        idx = c_uint32()
+        self._check_b(self.lib.cf_builder_add_pattern(self.b, a.ctypes.data, len(a), flags, byref(idx)), "add_pattern")
+        self.n_patterns += 1
+        return idx.value
+
+    def add_search(self, pattern: str, flags: int = 0) -> int:
+        """`re.compile(pattern, flags).search(unit)` existence bit."""
+        return self._add(fe.compile_ast(pattern, flags, "search"), N.CF_PAT_SEARCH)
+
+    def add_literal(self, word: str) -> int:
+        """`word in unit` existence bit (deny_filter)."""
+        return self._add(fe.literal_ast(word), N.CF_PAT_SEARCH)
+
+    def add_sub(self, pattern: str, flags: int, replacement: str) -> int:
+        """One regex_filter rule: `re.compile(pattern, flags).sub(replacement, unit)` with a literal
+        replacement (template already expanded by the caller)."""
+        idx = self._add(fe.compile_ast(pattern, flags, "sub"), N.CF_PAT_ORDERED)
+        r = encode_unit(replacement)
+        self._check_b(self.lib.cf_builder_set_replacement(self.b, idx, r, len(r)), "set_replacement")
+        self.n_ordered += 1
+        return idx
+
+    def compile_host(self) -> N.CompileStats:
+        st = N.CompileStats()
+        self._check_b(self.lib.cf_builder_compile_host(self.b, byref(st)), "compile")
+        return st
+
+    def compile(self, ctx: Context) -> "Program":
+        self.compile_host()
+        h = c_void_p()
+        with ctx.lock:
+            ctx.check(self.lib.cf_compile(ctx.h, self.b, byref(h)), "cf_compile")
+        self.h, self.ctx = h, ctx
+        return self
+
+    @property
+    def words(self) -> int:
+        return (self.n_patterns + 63) // 64 or 1
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.cf_free_prog(self.h)
+            self.lib.cf_builder_free(self.b)
+        except Exception:
+            pass
+
+
+class Batch:
+    """Device-resident packed stream (grown on demand by the caller creating a bigger one)."""
+
+    def __init__(self, ctx: Context, max_bytes: int, max_units: int):
+        self.ctx = ctx
+        self.h = c_void_p()
+        with ctx.lock:
+            ctx.check(ctx.lib.cf_batch_create(ctx.h, max_bytes, max_units, byref(self.h)), "cf_batch_create")
+        self.max_bytes, self.max_units = max_bytes, max_units
+
+    def upload(self, stream, offsets: np.ndarray, cuda_stream: int = 0) -> None:
+        n = len(offsets) - 1
+        sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+        nbytes = int(offsets[-1])
+        with self.ctx.lock:
+            self.ctx.check(self.ctx.lib.cf_batch_upload(self.ctx.h, self.h, sp, nbytes, offsets.ctypes.data, n, cuda_stream), "cf_batch_upload")
+
+    def __del__(self):
+        try:
+            self.ctx.lib.cf_batch_free(self.h)
+        except Exception:
+            pass
+
+
+def bitmaps_to_ints(bm: np.ndarray, n: int, W: int) -> List[int]:
+    if W == 1:
+        return [int(x) for x in bm[:n]]
+    out = []
+    for i in range(n):
+        v = 0
+        for w in range(W):
+            v |= int(bm[i * W + w]) << (64 * w)
+        out.append(v)
+    return out
+
+
+def scan_host(prog: Program, batch: Batch, stream, offsets: np.ndarray) -> np.ndarray:
+    """End-to-end scan through the C ABI with host buffers (H2D + kernels + D2H, synchronous).
+    Returns a uint64 array of n_units * W bitmap words."""
+    ctx = batch.ctx
+    n = len(offsets) - 1
+    W = prog.words
+    out = np.empty(n * W, dtype=np.uint64)
+    sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+    with ctx.lock:
+        ctx.check(ctx.lib.cf_scan_host(ctx.h, prog.h, batch.h, sp, int(offsets[-1]), offsets.ctypes.data, n, out.ctypes.data), "cf_scan_host")
+    return out
+
+
+def scan_units(prog: Program, units: Sequence[Union[str, bytes]], ctx: Optional[Context] = None) -> List[int]:
+    """Convenience: pack, scan on the GPU, return one Python int bitmap per unit."""
+    ctx = ctx or prog.ctx or Context.get()
+    if prog.h is None:
+        prog.compile(ctx)
+    if not units:
+        return []
+    stream, offs = pack_units(units)
+    batch = Batch(ctx, len(stream), len(units))
+    bm = scan_host(prog, batch, stream, offs)
+    return bitmaps_to_ints(bm, len(units), prog.words)
