@@ -101,6 +101,11 @@ int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, ui
 /* number of kernels launched by this ctx so far (for bench.py's gpu_launches) */
 uint64_t cf_kernel_launches(const cf_ctx* ctx);
 
+/* per-launch CUDA-event timing of the dominant kernel of each stage (scan_kernel for cf_scan),
+ * recorded on the launching stream; used by bench.py for roofline.achieved */
+int cf_profile_begin(cf_ctx* ctx, uint32_t max_launches); /* 0 disables */
+int cf_profile_collect(cf_ctx* ctx, double* total_ms, uint32_t* n_launches);
+
 /* last scan's device-side counters: [0]=prefilter candidates, [1]=DFA verify steps */
 int cf_scan_counters(cf_ctx* ctx, uint64_t out[2]);
 

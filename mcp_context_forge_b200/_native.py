@@ -49,6 +49,8 @@ _SIGS = {
     "cf_scan_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "cf_kernel_launches": (c_uint64, [c_void_p]),
     "cf_scan_counters": (c_int, [c_void_p, c_void_p]),
+    "cf_profile_begin": (c_int, [c_void_p, c_uint32]),
+    "cf_profile_collect": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint32)]),
 }
 
 _lib = None

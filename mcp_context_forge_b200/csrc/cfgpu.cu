@@ -8,8 +8,10 @@
 //                    LDS + 4 integer ops shift-AND prefilter, rare candidates verified by an
 //                    anchored class DFA (scan_core.h) cooperatively within the warp.
 // This is HBM-bound byte work: no tensor cores by design.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -21,19 +23,35 @@
 // ------------------------------------------------------------------------------------------------
 // host-side objects
 // ------------------------------------------------------------------------------------------------
+static const uint32_t LANE_BYTES = 64;
+static const uint32_t WARP_BYTES = 32 * LANE_BYTES;          // 2 KiB per warp per tile
+static const uint32_t MAX_WARPS = 24;   // padding granularity (>= every variant)
+static const uint32_t MAX_TILE = MAX_WARPS * WARP_BYTES;     // buffers are padded for the largest tile
+static const uint32_t STAGES = 3;
+
 struct cf_ctx {
   int device = 0;
   int sm_count = 0;
   std::string err;
   uint64_t launches = 0;
-  uint64_t* d_counters = nullptr;   // [2] candidates, verify steps
-  uint32_t* d_tile_unit = nullptr;  // per-tile first unit index (grown on demand)
-  uint64_t tile_unit_cap = 0;
+  uint64_t* d_qstate = nullptr;     // two {candidates appended, verify steps} pairs, used alternately
+  uint32_t qphase = 0;
+  uint64_t* d_queue = nullptr;      // candidate start positions
+  uint32_t qcap = 1u << 20;
+  // optional per-launch timing of the dominant kernel (bench.py roofline): event pairs
+  std::vector<cudaEvent_t> prof_ev;
+  uint32_t prof_used = 0;
+  bool prof_on = false;
+  // scan kernel configuration (CF_SCAN_WARPS / CF_SCAN_ACC override the defaults; experiments)
+  uint32_t scan_warps = 16;
+  uint32_t scan_acc = 0;
+  uint32_t tile() const { return scan_warps * WARP_BYTES; }
 };
 
 struct DevDfa {
   cf::DfaTables t;
   std::vector<void*> allocs;
+  uint64_t trans_bytes = 0, acc_bytes = 0, stage_bytes = 0;   // sizes for staging in shared memory
 };
 
 struct cf_prog {
@@ -55,17 +73,15 @@ struct cf_batch {
   cf_ctx* ctx = nullptr;
   uint8_t* d_buf = nullptr;        // FRONT_PAD + stream + tail pad
   uint64_t* d_offsets = nullptr;
+  uint32_t* d_coarse = nullptr;    // unit index at every 4 KiB of stream (built on upload)
+  std::vector<uint32_t> h_coarse;
   uint64_t cap_bytes = 0;
   uint32_t cap_units = 0;
   uint64_t nbytes = 0;
   uint32_t n = 0;
+  CUtensorMap tmap;                // 2-D view of d_buf: rows of 128 B, box = one scan tile, SWIZZLE_128B
 };
 
-static const uint32_t SCAN_WARPS = 8;
-static const uint32_t LANE_BYTES = 64;
-static const uint32_t TILE = SCAN_WARPS * 32 * LANE_BYTES;   // 16 KiB
-static const uint32_t HALO = 16;
-static const uint32_t STAGES = 3;
 
 #define CF_CUDA(ctx, call)                                                                  \
   do {                                                                                      \
@@ -114,118 +130,227 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// prep kernel: bitmaps := always-bits; tile_unit[i] := index of the unit containing byte i*TILE
-// ------------------------------------------------------------------------------------------------
-__global__ void prep_kernel(uint64_t* __restrict__ bitmaps, const uint64_t* __restrict__ always, uint32_t W,
-                            uint32_t n_units, const uint64_t* __restrict__ offsets,
-                            uint32_t* __restrict__ tile_unit, uint64_t ntiles, uint64_t* __restrict__ counters) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { counters[0] = 0; counters[1] = 0; }
-  uint64_t nb = (uint64_t)n_units * W;
-  if (i < nb) bitmaps[i] = always ? always[i % W] : 0ull;
-  if (i <= ntiles) {
-    uint64_t pos = i * TILE;
-    uint32_t lo = 0, hi = n_units;   // largest u with offsets[u] <= pos (offsets[0] == 0)
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (offsets[mid] <= pos) lo = mid; else hi = mid;
-    }
-    tile_unit[i] = lo;
-  }
+// 2-D tiled TMA load (rows of 128 bytes, SWIZZLE_128B): one instruction per tile
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
-// scan kernel
+// scan pipeline: fill (only when some pattern matches every unit) -> scan_kernel -> verify_kernel
 // ------------------------------------------------------------------------------------------------
+__global__ void fill_bitmaps_kernel(uint64_t* __restrict__ bitmaps, const uint64_t* __restrict__ always,
+                                    uint32_t W, uint64_t total) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) bitmaps[i] = always[i % W];
+}
+
 struct ScanParams {
   const uint8_t* stream;     // device pointer to stream byte 0 (FRONT_PAD bytes of 0xFF precede it)
   uint64_t nbytes;           // stream length including terminators
   uint64_t ntiles;
   const uint64_t* offsets;
-  const uint32_t* tile_unit;
+  const uint32_t* coarse;    // coarse[k] = unit containing stream byte k << COARSE_SHIFT
   uint32_t n_units;
   const uint32_t* E;
   cf::DfaTables dfa;
   unsigned long long* bitmaps;
-  unsigned long long* counters;
+  unsigned long long* queue;      // candidate start positions; CTA c owns [c*qcap_cta, (c+1)*qcap_cta)
+  unsigned long long* qstate;     // [0] = candidates found, [1] = DFA steps (statistics, this scan)
+  unsigned long long* qstate_next; // the pair the NEXT scan will use; CTA 0 zeroes it
+  uint32_t qcap_cta;
+  uint32_t dfa_bytes;             // bytes needed to stage the DFA tables in shared memory (0 = too big)
+  uint32_t dfa_trans_bytes, dfa_acc_bytes;
+  uint32_t dbg;                   // experiments: 1 = skip verification, 2 = no smem staging
 };
 
-struct ScanSmem {
-  alignas(128) uint8_t tile[STAGES][TILE + HALO];
-  uint32_t E[256];
+// Verify one candidate start: run the anchored class DFA from `start` until it dies or reaches the
+// unit's 0xFF terminator; unit boundaries come from the terminators themselves.  The unit INDEX is
+// only needed when something matched: one probe of the 4 KiB-granular coarse index + a short walk.
+static const uint32_t COARSE_SHIFT = 12;
+__device__ __forceinline__ uint32_t unit_of(const ScanParams& P, uint64_t pos) {
+  uint32_t u = P.coarse[pos >> COARSE_SHIFT];
+  while (P.offsets[u + 1] <= pos) ++u;
+  return u;
+}
+
+__device__ __noinline__ void verify_candidate(const ScanParams& P, const cf::DfaTables& t, uint64_t start, uint32_t& steps) {
+  if (start >= P.nbytes) return;                       // pad region
+  const uint8_t* __restrict__ s = P.stream;
+  const uint32_t b0 = s[start];
+  if ((b0 & 0xC0) == 0x80) return;                     // not a character boundary
+  uint32_t ctx;
+  if (s[start - 1] == cf::TERM) ctx = cf::P_START;     // FRONT_PAD makes s[-1] valid for unit 0
+  else ctx = cf::prev_context(t, s, start - 4, start); // backward scan stops at any non-continuation byte
+  uint32_t S = t.start_state[ctx];
+  uint64_t q = start;
+  const bool small = t.W <= 2;
+  unsigned long long bits0 = 0, bits1 = 0;
+  uint32_t unit = 0xFFFFFFFFu;
+  while (S != cf::DEAD) {
+    uint32_t col, len = 0;
+    const bool eot = s[q] == cf::TERM;
+    if (eot) col = t.ncols - 1;
+    else col = cf::classify(t, cf::utf8_decode(s, q, q + 4, &len));
+    uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
+    uint32_t a = e >> cf::ACC_SHIFT;
+    if (a) {
+      if (small) {
+        bits0 |= t.accsets[(uint64_t)a * t.W];
+        if (t.W == 2) bits1 |= t.accsets[(uint64_t)a * 2 + 1];
+      } else {
+        if (unit == 0xFFFFFFFFu) unit = unit_of(P, start);
+        for (uint32_t w = 0; w < t.W; ++w) {
+          unsigned long long v = t.accsets[(uint64_t)a * t.W + w];
+          if (v) atomicOr(&P.bitmaps[(uint64_t)unit * t.W + w], v);
+        }
+      }
+    }
+    S = e & 0xFFFFu;
+    ++steps;
+    if (eot) break;
+    q += len;
+  }
+  if (bits0 | bits1) {
+    unit = unit_of(P, start);
+    if (bits0) atomicOr(&P.bitmaps[(uint64_t)unit * t.W], bits0);
+    if (bits1) atomicOr(&P.bitmaps[(uint64_t)unit * t.W + 1], bits1);
+  }
+}
+
+static const uint32_t WQ = 32;   // per-warp candidate staging slots in shared memory
+
+template <uint32_t WARPS>
+struct ScanSmemT {
+  // Lane-private-bank prefilter table: the entry for byte value b as seen by lane l lives at byte
+  // offset b*256 + l*4, i.e. always in bank l -> every lookup is conflict-free for any input, and the
+  // offset (b << 8 | l << 2) is produced by ONE PRMT from the data word and a lane constant.
+  alignas(1024) uint32_t tbl[256 * 64];
+  // tile rows are 128 B, stored with the TMA 128-byte swizzle: 16-byte chunk c of row r sits at
+  // chunk c ^ (r & 7) -> a lane reading its own 64 contiguous bytes is bank-conflict free
+  alignas(1024) uint8_t tile[STAGES][WARPS * WARP_BYTES];
+  alignas(8) unsigned long long wq[WARPS][WQ];
+  uint32_t wq_n[WARPS];
+  uint32_t cq_n;                   // candidates in this CTA's global queue segment
   alignas(8) uint64_t full[STAGES];
   alignas(8) uint64_t empty[STAGES];
 };
 
-__device__ __forceinline__ void verify_candidate(const ScanParams& P, uint64_t start, uint32_t& steps) {
-  if (start >= P.nbytes) return;                       // pad region
-  const uint8_t* s = P.stream;
-  if ((s[start] & 0xC0) == 0x80) return;               // not a character boundary
-  uint64_t tix = start / TILE;
-  uint32_t lo = P.tile_unit[tix], hi = P.tile_unit[tix + 1] + 1;   // unit in [lo, hi)
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (P.offsets[mid] <= start) lo = mid; else hi = mid;
-  }
-  uint64_t ustart = P.offsets[lo], uend = P.offsets[lo + 1] - 1;
-  const cf::DfaTables& t = P.dfa;
-  uint32_t ctx = (start == ustart) ? (uint32_t)cf::P_START : cf::prev_context(t, s, ustart, start);
-  uint32_t S = t.start_state[ctx];
-  uint64_t q = start;
-  while (S != cf::DEAD) {
-    uint32_t col, len = 0;
-    if (q >= uend) col = t.ncols - 1;
-    else col = cf::classify(t, cf::utf8_decode(s, q, uend, &len));
-    uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
-    uint32_t a = e >> cf::ACC_SHIFT;
-    if (a)
-      for (uint32_t w = 0; w < t.W; ++w) {
-        unsigned long long v = t.accsets[(uint64_t)a * t.W + w];
-        if (v) atomicOr(&P.bitmaps[(uint64_t)lo * t.W + w], v);
-      }
-    S = e & 0xFFFFu;
-    ++steps;
-    if (q >= uend) break;
-    q += len;
-  }
+// append one candidate (called by the few lanes that found one; divergent context)
+template <uint32_t WARPS>
+__device__ __noinline__ void push_candidate(ScanSmemT<WARPS>& sm, const ScanParams& P, uint32_t warp, uint64_t pos) {
+  uint32_t slot = atomicAdd(&sm.wq_n[warp], 1u);
+  if (slot < WQ) { sm.wq[warp][slot] = pos; return; }
+  // staging full (pathologically dense candidates): go straight to the CTA queue
+  uint32_t g = atomicAdd(&sm.cq_n, 1u);
+  if (g < P.qcap_cta) P.queue[(uint64_t)blockIdx.x * P.qcap_cta + g] = pos;
+  else { uint32_t st = 0; verify_candidate(P, P.dfa, pos, st); }   // queue full: verify in place
 }
 
-#define FEED(word, k)                                                        \
-  {                                                                          \
-    uint32_t b_ = __byte_perm((word), 0, 0x4440 + (k));                      \
-    acc = ((acc >> 8) | 0xFF000000u) & sE[b_];                               \
-    hit |= acc;                                                              \
+// warp-cooperative flush of the staging slots into the CTA's queue segment
+template <uint32_t WARPS>
+__device__ __forceinline__ void flush_candidates(ScanSmemT<WARPS>& sm, const ScanParams& P, uint32_t warp, uint32_t lane) {
+  uint32_t n = sm.wq_n[warp];
+  if (n > WQ) n = WQ;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&sm.cq_n, n);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (lane < n) {
+    unsigned long long pos = sm.wq[warp][lane];
+    if (base + lane < P.qcap_cta) P.queue[(uint64_t)blockIdx.x * P.qcap_cta + base + lane] = pos;
+    else { uint32_t st = 0; verify_candidate(P, P.dfa, pos, st); }
   }
-#define FEED4(word) FEED(word, 0) FEED(word, 1) FEED(word, 2) FEED(word, 3)
-#define FEED16(v) FEED4((v).x) FEED4((v).y) FEED4((v).z) FEED4((v).w)
+  __syncwarp();
+  if (lane == 0) sm.wq_n[warp] = 0;
+  __syncwarp();
+}
 
-__global__ void __launch_bounds__(SCAN_WARPS * 32, 3) scan_kernel(const ScanParams P) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmem& sm = *reinterpret_cast<ScanSmem*>(smem_raw);
+template <uint32_t ACC>
+__device__ __forceinline__ uint32_t acc_shift(uint32_t acc) {
+  if (ACC == 1) {   // (acc >> 6) + 0x3F000000 as IMAD.HI on the FMA pipe instead of the ALU pipe
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, 0x4000000, 0x3F000000;" : "=r"(r) : "r"(acc));
+    return r;
+  }
+  return (acc >> 6) | 0x3F000000u;
+}
+
+#define FEED(word, k, H)                                                                      \
+  {                                                                                           \
+    const uint32_t a_ = __byte_perm((word), lane4, 0x5504 | ((k) << 4)); /* b<<8 | lane<<2 */ \
+    acc = acc_shift<ACC>(acc) & *reinterpret_cast<const uint32_t*>(tblb + a_);                \
+    H |= acc;                                                                                 \
+  }
+#define FEED4(word, H) FEED(word, 0, H) FEED(word, 1, H) FEED(word, 2, H) FEED(word, 3, H)
+#define FEED16(v, H) FEED4((v).x, H) FEED4((v).y, H) FEED4((v).z, H) FEED4((v).w, H)
+
+// rare path, lane-local: re-run one 16-byte group with position tracking (data still in registers)
+#define REFEED(word, k, bit)                                                                  \
+  {                                                                                           \
+    const uint32_t a_ = __byte_perm((word), lane4, 0x5504 | ((k) << 4));                      \
+    acc = ((acc >> 6) | 0x3F000000u) & *reinterpret_cast<const uint32_t*>(tblb + a_);         \
+    m |= ((acc & 0x3Fu) ? 1u : 0u) << (bit);                                                  \
+  }
+#define REFEED4(word, b0) REFEED(word, 0, (b0)) REFEED(word, 1, (b0) + 1) REFEED(word, 2, (b0) + 2) REFEED(word, 3, (b0) + 3)
+#define REGROUP(prevword, v, gpos)                                                            \
+  {                                                                                           \
+    uint32_t acc = 0, dummy = 0, m = 0;                                                       \
+    FEED4(prevword, dummy)                                                                    \
+    (void)dummy;                                                                              \
+    REFEED4((v).x, 0) REFEED4((v).y, 4) REFEED4((v).z, 8) REFEED4((v).w, 12)                  \
+    while (m) {                                                                               \
+      const uint32_t k_ = __ffs(m) - 1;                                                       \
+      m &= m - 1;                                                                             \
+      push_candidate<WARPS>(sm, P, warp, (gpos) + k_ - 3);                                    \
+    }                                                                                         \
+  }
+
+template <uint32_t WARPS, uint32_t ACC>
+__global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_constant__ ScanParams P,
+                                                               const __grid_constant__ CUtensorMap tmap) {
+  constexpr uint32_t TILE = WARPS * WARP_BYTES;
+  constexpr int32_t TROWS = TILE / 128;
+  constexpr int32_t ROW0 = cf::FRONT_PAD / 128;   // stream byte 0 is row FRONT_PAD/128 of the buffer
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  ScanSmemT<WARPS>& sm = *reinterpret_cast<ScanSmemT<WARPS>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t* __restrict__ sE = sm.E;
+  const uint32_t lane4 = lane << 2;
+  const uint8_t* __restrict__ tblb = reinterpret_cast<const uint8_t*>(sm.tbl);
 
-  sm.E[tid] = P.E[tid];   // blockDim == 256
+  for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) sm.tbl[(i >> 5) * 64 + (i & 31)] = P.E[i >> 5];
+  if (tid < WARPS) sm.wq_n[tid] = 0;
+  if (tid == 0) { sm.cq_n = 0; if (blockIdx.x == 0) { P.qstate_next[0] = 0; P.qstate_next[1] = 0; } }
   if (tid == 0) {
-    for (uint32_t s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], SCAN_WARPS); }
+    for (uint32_t s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const uint64_t first = blockIdx.x, stride = gridDim.x;
-  // prologue: fill STAGES-1 slots
-  if (tid == 0) {
+  if (tid == 0) {   // prologue: fill STAGES-1 slots
     for (uint32_t j = 0; j < STAGES - 1; ++j) {
       uint64_t tj = first + (uint64_t)j * stride;
       if (tj < P.ntiles) {
-        mbar_expect_tx(&sm.full[j], TILE + HALO);
-        tma_load_1d(sm.tile[j], P.stream + tj * TILE - HALO, TILE + HALO, &sm.full[j]);
+        mbar_expect_tx(&sm.full[j], TILE);
+        tma_load_2d(sm.tile[j], &tmap, 0, ROW0 + (int32_t)tj * TROWS, &sm.full[j]);
       }
     }
   }
 
-  uint32_t cand_total = 0, step_total = 0;
+  // per-lane swizzled offsets of its four 16-byte slots and of the word holding its look-back bytes
+  const uint32_t g = warp * 32 + lane, row = g >> 1, xr = row & 7, half4 = (g & 1) * 4;
+  const uint32_t o0 = row * 128 + (((half4 + 0) ^ xr) << 4), o1 = row * 128 + (((half4 + 1) ^ xr) << 4);
+  const uint32_t o2 = row * 128 + (((half4 + 2) ^ xr) << 4), o3 = row * 128 + (((half4 + 3) ^ xr) << 4);
+  const uint32_t gp = g ? g - 1 : 0, rowp = gp >> 1;
+  const uint32_t ob = rowp * 128 + (((((gp & 1) * 4) + 3) ^ (rowp & 7)) << 4) + 12;
+  // lane 0 of the CTA takes its look-back word (last 4 bytes of the previous tile) from HBM/L2,
+  // fetched one iteration ahead
+  uint32_t back_next = 0;
+  if (tid == 0 && first < P.ntiles) back_next = *reinterpret_cast<const uint32_t*>(P.stream + first * TILE - 4);
+
   uint32_t it = 0;
   for (uint64_t t = first; t < P.ntiles; t += stride, ++it) {
     const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1;
@@ -235,60 +360,92 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 3) scan_kernel(const ScanPara
       if (tj < P.ntiles) {
         uint32_t sj = j % STAGES;
         if (j >= STAGES) mbar_wait(&sm.empty[sj], ((j / STAGES) - 1) & 1);
-        mbar_expect_tx(&sm.full[sj], TILE + HALO);
-        tma_load_1d(sm.tile[sj], P.stream + tj * TILE - HALO, TILE + HALO, &sm.full[sj]);
+        mbar_expect_tx(&sm.full[sj], TILE);
+        tma_load_2d(sm.tile[sj], &tmap, 0, ROW0 + (int32_t)tj * TROWS, &sm.full[sj]);
       }
     }
+    uint32_t back = back_next;
+    if (tid == 0 && t + stride < P.ntiles) back_next = *reinterpret_cast<const uint32_t*>(P.stream + (t + stride) * TILE - 4);
     mbar_wait(&sm.full[slot], phase);
 
-    // this lane's 64 bytes (+ the word holding its 3 look-back bytes)
-    const uint32_t chunk = (warp * 32 + lane) * LANE_BYTES;          // tile-relative
-    const uint8_t* base = sm.tile[slot] + HALO + chunk;
-    const uint32_t back = *reinterpret_cast<const uint32_t*>(base - 4);
-    const uint4 v0 = *reinterpret_cast<const uint4*>(base);
-    const uint4 v1 = *reinterpret_cast<const uint4*>(base + 16);
-    const uint4 v2 = *reinterpret_cast<const uint4*>(base + 32);
-    const uint4 v3 = *reinterpret_cast<const uint4*>(base + 48);
+    // this lane's 64 bytes (+ the word holding its 4 look-back bytes)
+    const uint32_t chunk = g * LANE_BYTES;          // tile-relative
+    const uint8_t* base = sm.tile[slot];
+    if (g) back = *reinterpret_cast<const uint32_t*>(base + ob);
+    const uint4 v0 = *reinterpret_cast<const uint4*>(base + o0);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(base + o1);
+    const uint4 v2 = *reinterpret_cast<const uint4*>(base + o2);
+    const uint4 v3 = *reinterpret_cast<const uint4*>(base + o3);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[slot]);   // slot may be refilled: data is in registers
 
-    uint32_t acc = 0, hit = 0;
-    FEED(back, 1) FEED(back, 2) FEED(back, 3)
-    hit = 0;   // look-back windows belong to the previous lane
-    FEED16(v0) FEED16(v1) FEED16(v2) FEED16(v3)
+    uint32_t acc = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    FEED4(back, h0)
+    h0 = 0;   // windows ending in the look-back bytes belong to the previous lane
+    FEED16(v0, h0) FEED16(v1, h1) FEED16(v2, h2) FEED16(v3, h3)
 
-    // rare path: some lane saw an admissible 4-byte window
-    uint32_t any = __ballot_sync(0xFFFFFFFFu, (hit & 0xFFu) != 0);
-    while (any) {
-      const uint32_t src = __ffs(any) - 1;
-      any &= any - 1;
-      // the whole warp re-filters the 64 bytes of lane `src`, two feed positions per lane
-      const uint64_t cbase = t * TILE + (uint64_t)(warp * 32 + src) * LANE_BYTES;
-      const uint8_t* g = P.stream + cbase + 2 * lane;
-      uint32_t a2 = 0;
-      a2 = cf::filter_step(a2, sE[g[-3]]);
-      a2 = cf::filter_step(a2, sE[g[-2]]);
-      a2 = cf::filter_step(a2, sE[g[-1]]);
-      a2 = cf::filter_step(a2, sE[g[0]]);
-      const bool c0 = (a2 & 0xFF) != 0;               // start = cbase + 2*lane - 2
-      a2 = cf::filter_step(a2, sE[g[1]]);
-      const bool c1 = (a2 & 0xFF) != 0;               // start = cbase + 2*lane - 1
-      uint32_t steps = 0;
-      if (c0) { verify_candidate(P, cbase + 2 * lane - 2, steps); ++cand_total; }
-      if (c1) { verify_candidate(P, cbase + 2 * lane - 1, steps); ++cand_total; }
-      step_total += steps;
+    // rare path: an admissible 5-byte window ended in one of this lane's 16-byte groups
+    const bool anyhit = ((h0 | h1 | h2 | h3) & 0x3Fu) != 0;
+    if (__any_sync(0xFFFFFFFFu, anyhit)) {
+      if (anyhit) {
+        const uint64_t cpos = t * TILE + chunk;   // stream offset of this lane's first byte
+        if (h0 & 0x3Fu) REGROUP(back, v0, cpos)
+        if (h1 & 0x3Fu) REGROUP(v0.w, v1, cpos + 16)
+        if (h2 & 0x3Fu) REGROUP(v1.w, v2, cpos + 32)
+        if (h3 & 0x3Fu) REGROUP(v2.w, v3, cpos + 48)
+      }
       __syncwarp();
+      if (sm.wq_n[warp] >= WQ / 2) flush_candidates<WARPS>(sm, P, warp, lane);
     }
   }
-  // statistics (one atomic per warp)
-  for (int o = 16; o; o >>= 1) {
-    cand_total += __shfl_xor_sync(0xFFFFFFFFu, cand_total, o);
-    step_total += __shfl_xor_sync(0xFFFFFFFFu, step_total, o);
+  __syncwarp();
+  if (sm.wq_n[warp]) flush_candidates<WARPS>(sm, P, warp, lane);
+  __syncthreads();   // every tile this CTA requested has been consumed; the tile buffers are free
+
+  // ---- tail: verify this CTA's candidates, DFA tables staged in the (now idle) tile buffers
+  const uint32_t ncand = sm.cq_n;
+  if (ncand == 0) return;
+  const uint32_t nq = ncand < P.qcap_cta ? ncand : P.qcap_cta;
+  cf::DfaTables T = P.dfa;
+  if (P.dfa_bytes && P.dfa_bytes <= sizeof(sm.tile) && !(P.dbg & 2)) {
+    uint8_t* dst = &sm.tile[0][0];
+    uint32_t off = 0;
+    auto stage = [&](const void* src, uint32_t bytes) -> const void* {
+      const uint32_t words = (bytes + 3) / 4;
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + off);
+      for (uint32_t i = tid; i < words; i += WARPS * 32) d32[i] = s32[i];
+      const void* r = dst + off;
+      off += (words * 4 + 15) & ~15u;
+      return r;
+    };
+    T.ascii_cls = (const uint16_t*)stage(P.dfa.ascii_cls, 128 * 2);
+    T.range_start = (const uint32_t*)stage(P.dfa.range_start, P.dfa.nranges * 4);
+    T.range_cls = (const uint16_t*)stage(P.dfa.range_cls, P.dfa.nranges * 2);
+    T.cls_ctx = (const uint8_t*)stage(P.dfa.cls_ctx, P.dfa.ncols - 1);
+    T.trans = (const uint32_t*)stage(P.dfa.trans, P.dfa_trans_bytes);
+    T.accsets = (const uint64_t*)stage(P.dfa.accsets, P.dfa_acc_bytes);
+    __syncthreads();
   }
-  if (lane == 0 && (cand_total | step_total)) {
-    atomicAdd(&P.counters[0], (unsigned long long)cand_total);
-    atomicAdd(&P.counters[1], (unsigned long long)step_total);
-  }
+  uint32_t steps = 0;
+  const unsigned long long* q = P.queue + (uint64_t)blockIdx.x * P.qcap_cta;
+  if (!(P.dbg & 1))
+    for (uint32_t i = lane * WARPS + warp; i < nq; i += WARPS * 32)   // spread over warps: less divergence
+      verify_candidate(P, T, q[i], steps);
+  for (int o = 16; o; o >>= 1) steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
+  if (lane == 0 && steps) atomicAdd(&P.qstate[1], (unsigned long long)steps);
+  if (tid == 0) atomicAdd(&P.qstate[0], (unsigned long long)ncand);
+}
+
+typedef void (*scan_fn_t)(const ScanParams, const CUtensorMap);
+struct ScanVariant { scan_fn_t fn; uint32_t warps, acc; size_t smem; };
+static const ScanVariant SCAN_VARIANTS[] = {
+    {scan_kernel<8, 0>, 8, 0, sizeof(ScanSmemT<8>)},    {scan_kernel<8, 1>, 8, 1, sizeof(ScanSmemT<8>)},
+    {scan_kernel<16, 0>, 16, 0, sizeof(ScanSmemT<16>)}, {scan_kernel<16, 1>, 16, 1, sizeof(ScanSmemT<16>)},
+};
+static const ScanVariant* scan_variant(uint32_t warps, uint32_t acc) {
+  for (const auto& v : SCAN_VARIANTS) if (v.warps == warps && v.acc == acc) return &v;
+  return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,6 +470,11 @@ static int upload_dfa(cf_ctx* ctx, const cfre::DfaOut& d, DevDfa& o) {
   if ((rc = upload(ctx, d.cls_ctx, &o.t.cls_ctx, o.allocs))) return rc;
   if ((rc = upload(ctx, d.trans, &o.t.trans, o.allocs))) return rc;
   if ((rc = upload(ctx, d.accsets, &o.t.accsets, o.allocs))) return rc;
+  o.trans_bytes = d.trans.size() * 4;
+  o.acc_bytes = d.accsets.size() * 8;
+  auto r16 = [](uint64_t b) { return (b + 15) & ~15ull; };
+  o.stage_bytes = r16(256) + r16(d.range_start.size() * 4) + r16(d.range_cls.size() * 2) + r16(d.ncols) +
+                  r16(o.trans_bytes) + r16(o.acc_bytes) + 64;
   o.t.nranges = (uint32_t)d.range_start.size();
   o.t.ncols = d.ncols;
   o.t.W = d.W;
@@ -335,17 +497,22 @@ int cf_init(int device_ordinal, cf_ctx** out) {
   CF_CUDA(ctx, cudaGetDeviceProperties(&prop, device_ordinal));
   ctx->sm_count = prop.multiProcessorCount;
   if (prop.major < 10) { ctx->err = "libcfgpu.so is built for sm_100a (Blackwell) only"; return CF_E_NOGPU; }
-  CF_CUDA(ctx, cudaMalloc(&ctx->d_counters, 2 * sizeof(uint64_t)));
-  CF_CUDA(ctx, cudaMemset(ctx->d_counters, 0, 2 * sizeof(uint64_t)));
-  CF_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+  CF_CUDA(ctx, cudaMalloc(&ctx->d_qstate, 4 * sizeof(uint64_t)));
+  CF_CUDA(ctx, cudaMemset(ctx->d_qstate, 0, 4 * sizeof(uint64_t)));
+  CF_CUDA(ctx, cudaMalloc(&ctx->d_queue, (size_t)ctx->qcap * sizeof(uint64_t)));
+  if (const char* e = getenv("CF_SCAN_WARPS")) ctx->scan_warps = (uint32_t)atoi(e);
+  if (const char* e = getenv("CF_SCAN_ACC")) ctx->scan_acc = (uint32_t)atoi(e);
+  if (!scan_variant(ctx->scan_warps, ctx->scan_acc)) { ctx->err = "CF_SCAN_WARPS must be 8 or 16 and CF_SCAN_ACC 0 or 1"; return CF_E_BADARG; }
+  for (const auto& v : SCAN_VARIANTS)
+    CF_CUDA(ctx, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
   return CF_OK;
 }
 
 void cf_shutdown(cf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_counters);
-  cudaFree(ctx->d_tile_unit);
+  cudaFree(ctx->d_qstate);
+  cudaFree(ctx->d_queue);
   delete ctx;
 }
 
@@ -410,7 +577,7 @@ void cf_free_prog(cf_prog* p) {
 uint32_t cf_prog_words(const cf_prog* p) { return p ? p->W : 0; }
 uint32_t cf_prog_patterns(const cf_prog* p) { return p ? p->npat : 0; }
 
-static uint64_t ntiles_for(uint64_t nbytes) { return (nbytes + 2 + TILE - 1) / TILE; }
+static uint64_t ntiles_for(uint64_t nbytes, uint32_t tile) { return (nbytes + 2 + tile - 1) / tile; }
 
 int cf_batch_create(cf_ctx* ctx, uint64_t max_stream_bytes, uint32_t max_units, cf_batch** out) {
   if (!ctx || !out) return CF_E_BADARG;
@@ -421,10 +588,27 @@ int cf_batch_create(cf_ctx* ctx, uint64_t max_stream_bytes, uint32_t max_units, 
   *out = b;
   b->cap_bytes = max_stream_bytes;
   b->cap_units = max_units;
-  uint64_t total = cf::FRONT_PAD + (ntiles_for(max_stream_bytes) + 1) * TILE;
+  uint64_t total = cf::FRONT_PAD + (ntiles_for(max_stream_bytes, MAX_TILE) + 1) * (uint64_t)MAX_TILE;
   CF_CUDA(ctx, cudaMalloc(&b->d_buf, total));
   CF_CUDA(ctx, cudaMemset(b->d_buf, 0xFF, total));
   CF_CUDA(ctx, cudaMalloc(&b->d_offsets, ((uint64_t)max_units + 1) * 8));
+  CF_CUDA(ctx, cudaMalloc(&b->d_coarse, ((max_stream_bytes >> COARSE_SHIFT) + 2) * 4));
+  // tensor map for the scan kernel's tile loads
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CF_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) { ctx->err = "cuTensorMapEncodeTiled unavailable"; return CF_E_CUDA; }
+  cuuint64_t gdim[2] = {128, total / 128};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {128, ctx->tile() / 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = ((encode_fn)fn)(&b->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b->d_buf, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)cr); return CF_E_CUDA; }
   return CF_OK;
 }
 
@@ -433,6 +617,7 @@ void cf_batch_free(cf_batch* b) {
   cudaSetDevice(b->ctx->device);
   cudaFree(b->d_buf);
   cudaFree(b->d_offsets);
+  cudaFree(b->d_coarse);
   delete b;
 }
 
@@ -448,9 +633,20 @@ int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t st
   uint8_t* d_stream = b->d_buf + cf::FRONT_PAD;
   CF_CUDA(ctx, cudaMemcpyAsync(d_stream, stream, stream_bytes, cudaMemcpyHostToDevice, st));
   // re-arm the tail padding that a previous, longer upload may have overwritten
-  uint64_t end = (ntiles_for(b->nbytes > stream_bytes ? b->nbytes : stream_bytes) + 1) * TILE;
+  uint64_t end = (ntiles_for(b->nbytes > stream_bytes ? b->nbytes : stream_bytes, MAX_TILE) + 1) * (uint64_t)MAX_TILE;
   CF_CUDA(ctx, cudaMemsetAsync(d_stream + stream_bytes, 0xFF, end - stream_bytes, st));
   CF_CUDA(ctx, cudaMemcpyAsync(b->d_offsets, offsets, ((uint64_t)n_units + 1) * 8, cudaMemcpyHostToDevice, st));
+  {  // coarse unit index (host sweep over offsets; tiny next to the stream copy)
+    const uint64_t nc = (stream_bytes >> COARSE_SHIFT) + 1;
+    b->h_coarse.resize(nc);
+    uint32_t u = 0;
+    for (uint64_t k = 0; k < nc; ++k) {
+      const uint64_t pos = k << COARSE_SHIFT;
+      while (u + 1 < n_units && offsets[u + 1] <= pos) ++u;
+      b->h_coarse[k] = u;
+    }
+    CF_CUDA(ctx, cudaMemcpyAsync(b->d_coarse, b->h_coarse.data(), nc * 4, cudaMemcpyHostToDevice, st));
+  }
   b->nbytes = stream_bytes;
   b->n = n_units;
   return CF_OK;
@@ -459,37 +655,43 @@ int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t st
 int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cuda_stream) {
   if (!ctx || !p || !b || !d_bitmaps || !b->n) return CF_E_BADARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  uint64_t ntiles = ntiles_for(b->nbytes);
-  if (ntiles + 2 > ctx->tile_unit_cap) {
-    CF_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaFree(ctx->d_tile_unit);
-    ctx->d_tile_unit = nullptr;
-    ctx->tile_unit_cap = (ntiles + 2) * 2;
-    CF_CUDA(ctx, cudaMalloc(&ctx->d_tile_unit, ctx->tile_unit_cap * 4));
+  const uint32_t tile = ctx->tile();
+  const uint64_t ntiles = ntiles_for(b->nbytes, tile);
+  const uint64_t total = (uint64_t)b->n * p->W;
+  if (p->any_always) {
+    fill_bitmaps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_bitmaps, p->d_always, p->W, total);
+    ctx->launches++;
+    CF_CUDA(ctx, cudaGetLastError());
+  } else {
+    CF_CUDA(ctx, cudaMemsetAsync(d_bitmaps, 0, total * 8, st));
   }
-  uint64_t work = (uint64_t)b->n * p->W;
-  if (ntiles + 1 > work) work = ntiles + 1;
-  uint32_t pb = 256;
-  prep_kernel<<<(unsigned)((work + pb - 1) / pb), pb, 0, st>>>(d_bitmaps, p->any_always ? p->d_always : nullptr, p->W,
-                                                               b->n, b->d_offsets, ctx->d_tile_unit, ntiles,
-                                                               ctx->d_counters);
-  ctx->launches++;
-  CF_CUDA(ctx, cudaGetLastError());
   if (p->search_empty) return CF_OK;
   ScanParams P;
   P.stream = b->d_buf + cf::FRONT_PAD;
   P.nbytes = b->nbytes;
   P.ntiles = ntiles;
   P.offsets = b->d_offsets;
-  P.tile_unit = ctx->d_tile_unit;
+  P.coarse = b->d_coarse;
   P.n_units = b->n;
   P.E = p->d_E;
   P.dfa = p->search.t;
   P.bitmaps = (unsigned long long*)d_bitmaps;
-  P.counters = (unsigned long long*)ctx->d_counters;
-  uint64_t grid = (uint64_t)ctx->sm_count * 3;
+  P.queue = (unsigned long long*)ctx->d_queue;
+  P.qstate = (unsigned long long*)ctx->d_qstate + 2 * ctx->qphase;
+  P.qstate_next = (unsigned long long*)ctx->d_qstate + 2 * (ctx->qphase ^ 1);
+  ctx->qphase ^= 1;
+  P.qcap_cta = ctx->qcap / (uint32_t)ctx->sm_count;
+  P.dfa_bytes = p->search.stage_bytes < (1u << 30) ? (uint32_t)p->search.stage_bytes : 0;
+  P.dfa_trans_bytes = (uint32_t)p->search.trans_bytes;
+  P.dfa_acc_bytes = (uint32_t)p->search.acc_bytes;
+  P.dbg = getenv("CF_DBG") ? (uint32_t)atoi(getenv("CF_DBG")) : 0;
+  const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_acc);
+  uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM
   if (grid > ntiles) grid = ntiles;
-  scan_kernel<<<(unsigned)grid, SCAN_WARPS * 32, sizeof(ScanSmem), st>>>(P);
+  const bool prof = ctx->prof_on && (size_t)ctx->prof_used + 2 <= ctx->prof_ev.size();
+  if (prof) cudaEventRecord(ctx->prof_ev[ctx->prof_used], st);
+  sv->fn<<<(unsigned)grid, sv->warps * 32, sv->smem, st>>>(P, b->tmap);
+  if (prof) { cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], st); ctx->prof_used += 2; }
   ctx->launches++;
   CF_CUDA(ctx, cudaGetLastError());
   return CF_OK;
@@ -513,9 +715,40 @@ int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, ui
   return rc;
 }
 
+int cf_profile_begin(cf_ctx* ctx, uint32_t max_launches) {
+  if (!ctx) return CF_E_BADARG;
+  for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  ctx->prof_ev.clear();
+  ctx->prof_used = 0;
+  ctx->prof_on = max_launches > 0;
+  for (uint32_t i = 0; i < 2 * max_launches; ++i) {
+    cudaEvent_t e;
+    CF_CUDA(ctx, cudaEventCreate(&e));
+    ctx->prof_ev.push_back(e);
+  }
+  return CF_OK;
+}
+
+int cf_profile_collect(cf_ctx* ctx, double* total_ms, uint32_t* n_launches) {
+  if (!ctx || !total_ms || !n_launches) return CF_E_BADARG;
+  double tot = 0;
+  uint32_t n = 0;
+  for (uint32_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    CF_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[i + 1]));
+    float ms = 0;
+    CF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *n_launches = n;
+  ctx->prof_used = 0;
+  return CF_OK;
+}
+
 int cf_scan_counters(cf_ctx* ctx, uint64_t out[2]) {
   if (!ctx || !out) return CF_E_BADARG;
-  CF_CUDA(ctx, cudaMemcpy(out, ctx->d_counters, 16, cudaMemcpyDeviceToHost));
+  CF_CUDA(ctx, cudaMemcpy(out, ctx->d_qstate + 2 * (ctx->qphase ^ 1), 16, cudaMemcpyDeviceToHost));  // pair used by the last scan
   return CF_OK;
 }
 

@@ -414,18 +414,19 @@ struct ByteSet {
   int count() const { int c = 0; for (int i = 0; i < 4; ++i) c += __builtin_popcountll(w[i]); return c; }
   int union_count(const ByteSet& o) const { int c = 0; for (int i = 0; i < 4; ++i) c += __builtin_popcountll(w[i] | o.w[i]); return c; }
 };
-struct PatFilter { ByteSet N, pos[3]; };
+static const int NPOS = 4;   // match-byte positions covered by the prefilter
+struct PatFilter { ByteSet N, pos[NPOS]; };
 
 static void explore(const DfaBuilder& B, const Classes& C, uint32_t state, int bytepos,
                     std::vector<uint8_t>& seen, PatFilter& f) {
-  if (bytepos >= 3 || state == cf::DEAD) return;
-  size_t key = (size_t)state * 3 + bytepos;
+  if (bytepos >= NPOS || state == cf::DEAD) return;
+  size_t key = (size_t)state * NPOS + bytepos;
   if (seen[key]) return;
   seen[key] = 1;
   uint32_t ncols = C.ncls + 1;
   for (uint32_t col = 0; col < ncols; ++col) {
     uint32_t e = B.trans[(size_t)state * ncols + col];
-    if (e >> cf::ACC_SHIFT) for (int k = bytepos; k < 3; ++k) f.pos[k].all();
+    if (e >> cf::ACC_SHIFT) for (int k = bytepos; k < NPOS; ++k) f.pos[k].all();
     uint32_t t = e & 0xFFFF;
     if (col == C.ncls || t == cf::DEAD) continue;
     bool any_ascii = false;
@@ -435,7 +436,7 @@ static void explore(const DfaBuilder& B, const Classes& C, uint32_t state, int b
       bool any = false;
       for (uint32_t b = 0xC0; b < 0x100; ++b) if (C.lead[L][col][b]) { f.pos[bytepos].set(b); any = true; }
       if (!any) continue;
-      for (int j = 1; j < L && bytepos + j < 3; ++j)
+      for (int j = 1; j < L && bytepos + j < NPOS; ++j)
         for (uint32_t b = 0x80; b < 0xC0; ++b) f.pos[bytepos + j].set(b);
       explore(B, C, t, bytepos + L, seen, f);
     }
@@ -450,14 +451,12 @@ static bool alive(const DfaBuilder& B, const Classes& C, uint32_t state) {
 }
 
 static int pattern_filter(const Prog& prog, const Classes& C, int pat, PatFilter& f, std::string* err) {
-  DfaBuilder B(prog, C, false, 1, 20000);
-  // single-pattern builder: remap MATCH ids is unnecessary (W covers pat index) — use npat = pat+1
   DfaBuilder B2(prog, C, false, (uint32_t)pat + 1, 20000);
   uint32_t ss[4];
   std::vector<int> k = {prog.start[pat]};
   B2.build(k, ss);
   if (B2.overflow) { if (err) *err = "pattern DFA too large"; return CF_E_TOO_LARGE; }
-  std::vector<uint8_t> seen(B2.states.size() * 3, 0);
+  std::vector<uint8_t> seen(B2.states.size() * NPOS, 0);
   bool al[4];
   for (int P = 0; P < 4; ++P) {
     al[P] = alive(B2, C, ss[P]);
@@ -467,7 +466,6 @@ static int pattern_filter(const Prog& prog, const Classes& C, int pat, PatFilter
   if (al[cf::P_START]) f.N.set(cf::TERM);
   for (uint32_t b = 0; b < 128; ++b) if (al[C.cls_ctx[C.ascii_cls[b]]]) f.N.set(b);
   if (al[cf::P_WORD] || al[cf::P_OTHER]) for (uint32_t b = 0x80; b < 0xC0; ++b) f.N.set(b);
-  (void)B;
   return 0;
 }
 
@@ -482,7 +480,7 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
     for (auto& b : bks) {
       if (memcmp(b.f.pos[0].w, pf[i].pos[0].w, sizeof(b.f.pos[0].w)) == 0 &&
           memcmp(b.f.N.w, pf[i].N.w, sizeof(b.f.N.w)) == 0) {
-        for (int k = 0; k < 3; ++k) b.f.pos[k].merge(pf[i].pos[k]);
+        for (int k = 0; k < NPOS; ++k) b.f.pos[k].merge(pf[i].pos[k]);
         b.pats.push_back((int)i); merged = true; break;
       }
     }
@@ -490,20 +488,22 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
   }
   auto cost = [](const PatFilter& f) {
     // expected admit probability proxy: product of set sizes
-    return (double)f.N.count() * f.pos[0].count() * f.pos[1].count() * f.pos[2].count();
+    double c = (double)f.N.count();
+    for (int k = 0; k < NPOS; ++k) c *= f.pos[k].count();
+    return c;
   };
-  while (bks.size() > 8) {
+  while (bks.size() > cf::F_BUCKETS) {
     size_t bi = 0, bj = 1; double best = 1e300;
     for (size_t i = 0; i < bks.size(); ++i)
       for (size_t j = i + 1; j < bks.size(); ++j) {
         PatFilter m = bks[i].f;
         m.N.merge(bks[j].f.N);
-        for (int k = 0; k < 3; ++k) m.pos[k].merge(bks[j].f.pos[k]);
+        for (int k = 0; k < NPOS; ++k) m.pos[k].merge(bks[j].f.pos[k]);
         double d = cost(m) - cost(bks[i].f) - cost(bks[j].f);
         if (d < best) { best = d; bi = i; bj = j; }
       }
     bks[bi].f.N.merge(bks[bj].f.N);
-    for (int k = 0; k < 3; ++k) bks[bi].f.pos[k].merge(bks[bj].f.pos[k]);
+    for (int k = 0; k < NPOS; ++k) bks[bi].f.pos[k].merge(bks[bj].f.pos[k]);
     bks[bi].pats.insert(bks[bi].pats.end(), bks[bj].pats.begin(), bks[bj].pats.end());
     bks.erase(bks.begin() + bj);
   }
@@ -513,9 +513,8 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
     for (uint32_t b = 0; b < 256; ++b) {
       uint32_t e = 0;
       if (bks[k].f.N.get(b)) e |= 1u << (24 + k);
-      if (bks[k].f.pos[0].get(b)) e |= 1u << (16 + k);
-      if (bks[k].f.pos[1].get(b)) e |= 1u << (8 + k);
-      if (bks[k].f.pos[2].get(b)) e |= 1u << k;
+      for (int j = 0; j < NPOS; ++j)
+        if (bks[k].f.pos[j].get(b)) e |= 1u << ((NPOS - 1 - j) * cf::F_BITS + k);
       fo.E[b] |= e;
     }
   }

@@ -40,11 +40,11 @@ int cfh_scan(cf_builder* b, const uint8_t* stream, uint64_t nbytes, const uint64
   const uint8_t* s = pad.data() + cf::FRONT_PAD;   // s[-FRONT_PAD..] valid
   uint32_t acc = 0;
   uint64_t ncand = 0, nsteps = 0;
-  // feed from 3 bytes before the stream (lookback) to 2 bytes after (the last start is nbytes-1)
-  for (int64_t p = -3; p < (int64_t)nbytes + 2; ++p) {
+  // feed from LOOKBACK bytes before the stream to START_OFF bytes after (the last start is nbytes-1)
+  for (int64_t p = -(int64_t)cf::F_LOOKBACK; p < (int64_t)nbytes + (int64_t)cf::F_START_OFF; ++p) {
     acc = cf::filter_step(acc, co.filter.E[s[p]]);
-    if (!(acc & 0xFF)) continue;
-    int64_t start = p - 2;
+    if (!(acc & cf::F_MASK)) continue;
+    int64_t start = p - (int64_t)cf::F_START_OFF;
     if (start < 0 || start >= (int64_t)nbytes) continue;
     if ((s[start] & 0xC0) == 0x80) continue;   // not a character boundary
     ++ncand;
@@ -80,10 +80,10 @@ int cfh_sub(cf_builder* b, uint32_t ordered_index, const uint8_t* unit, uint64_t
     o += k;
   };
   uint32_t acc = 0;
-  for (int64_t p = -3; p < (int64_t)len + 2; ++p) {
+  for (int64_t p = -(int64_t)cf::F_LOOKBACK; p < (int64_t)len + (int64_t)cf::F_START_OFF; ++p) {
     acc = cf::filter_step(acc, E[s[p]]);
-    if (!(acc & 0xFF)) continue;
-    int64_t start = p - 2;
+    if (!(acc & cf::F_MASK)) continue;
+    int64_t start = p - (int64_t)cf::F_START_OFF;
     if (start < 0 || start >= (int64_t)len) continue;
     if ((uint64_t)start < cur) continue;            // inside the previous match
     if ((s[start] & 0xC0) == 0x80) continue;
