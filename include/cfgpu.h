@@ -98,6 +98,15 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
 /* host buffers: upload + scan + download, synchronous; h_bitmaps = n_units*W uint64 */
 int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
                  const uint64_t* offsets, uint32_t n_units, uint64_t* h_bitmaps);
+/* ---------------- stage 2: regex_filter substitution (units the scan flagged) ---------------- */
+/* Applies every CF_PAT_ORDERED rule of `p`, in the order added, to the listed units of the batch
+ * that was last uploaded (Python `pattern.sub(replacement, value)` rule after rule,
+ * plugins/regex_filter/search_replace.py:127-130).  Rewritten units are returned back to back in
+ * out_bytes with out_offsets[n_sel+1]; a unit no rule matched comes back unchanged.
+ * CF_E_CAPACITY with *out_needed set when out_cap is too small.  Synchronous. */
+int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uint32_t n_sel, uint8_t* out_bytes,
+                uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed);
+
 /* number of kernels launched by this ctx so far (for bench.py's gpu_launches) */
 uint64_t cf_kernel_launches(const cf_ctx* ctx);
 

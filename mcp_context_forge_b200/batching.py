@@ -1,0 +1,140 @@
+"""Batch coalescer: concurrent in-flight hook calls -> one packed stream -> one GPU launch.
+
+Every request runs on the gateway's asyncio loop and awaits its plugins one after another
+(/root/reference/mcpgateway/services/tool_service.py:5866-5872), so many requests sit at `await`
+points at the same time.  Plugins submit their units here; the coalescer collects whatever arrives
+within `window_us` (0 = everything already queued in this loop iteration), packs it with
+engine.pack_units and issues ONE cf_scan_host for the whole group, then hands every caller its
+slice of the verdicts.  Per-request ordering is unaffected: a caller only resumes after its own
+future resolves, exactly as if its plugin had computed inline.
+"""
+from __future__ import annotations
+
+import asyncio
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import engine
+
+Unit = Union[str, bytes]
+
+
+class GpuBatcher:
+    _instances: Dict[int, "GpuBatcher"] = {}
+    _ilock = threading.Lock()
+
+    def __init__(self, ctx: Optional[engine.Context] = None, window_us: int = 0, max_units: int = 1 << 16):
+        self.ctx = ctx or engine.Context.get()
+        self.window_us = window_us
+        self.max_units = max_units
+        self._batch: Optional[engine.Batch] = None
+        self._pending: Dict[tuple, tuple] = {}   # (id(prog), op, arg) -> (prog, op, arg, [(units, future)])
+        self._scheduled = False
+        self.launches = 0
+        self.units_seen = 0
+
+    @classmethod
+    def get(cls, device: int = 0) -> "GpuBatcher":
+        with cls._ilock:
+            b = cls._instances.get(device)
+            if b is None:
+                b = cls._instances[device] = GpuBatcher(engine.Context.get(device))
+            return b
+
+    # ---- device batch buffer, grown geometrically
+    def _ensure_batch(self, nbytes: int, nunits: int) -> engine.Batch:
+        b = self._batch
+        if b is None or nbytes > b.max_bytes or nunits > b.max_units:
+            cap_b = max(nbytes * 2, 1 << 20, b.max_bytes if b else 0)
+            cap_u = max(nunits * 2, 1024, b.max_units if b else 0)
+            self._batch = b = engine.Batch(self.ctx, cap_b, cap_u)
+        return b
+
+    # ---- synchronous core: one launch for a list of unit lists
+    def scan_groups(self, prog: engine.Program, groups: Sequence[Sequence[Unit]]) -> List[List[int]]:
+        flat: List[bytes] = [engine.encode_unit(u) for g in groups for u in g]
+        if not flat:
+            return [[] for _ in groups]
+        if prog.h is None:
+            prog.compile(self.ctx)
+        stream, offs = engine.pack_units(flat)
+        batch = self._ensure_batch(len(stream), len(flat))
+        bm = engine.scan_host(prog, batch, stream, offs)
+        self.launches += 1
+        self.units_seen += len(flat)
+        ints = engine.bitmaps_to_ints(bm, len(flat), prog.words)
+        out, i = [], 0
+        for g in groups:
+            out.append(ints[i:i + len(g)])
+            i += len(g)
+        return out
+
+    def scan_sync(self, prog: engine.Program, units: Sequence[Unit]) -> List[int]:
+        return self.scan_groups(prog, [units])[0]
+
+    def sub_groups(self, prog: engine.Program, groups: Sequence[Sequence[Unit]], rule_mask: int) -> List[List[Optional[bytes]]]:
+        """Fused scan, then the substitution kernel on the units some rule matched.  Returns, per
+        unit, the rewritten UTF-8 bytes or None when no rule touched it."""
+        flat: List[bytes] = [engine.encode_unit(u) for g in groups for u in g]
+        if not flat:
+            return [[] for _ in groups]
+        if prog.h is None:
+            prog.compile(self.ctx)
+        stream, offs = engine.pack_units(flat)
+        batch = self._ensure_batch(len(stream), len(flat))
+        bm = engine.bitmaps_to_ints(engine.scan_host(prog, batch, stream, offs), len(flat), prog.words)
+        self.launches += 1
+        self.units_seen += len(flat)
+        dirty = [i for i, v in enumerate(bm) if v & rule_mask]
+        res: List[Optional[bytes]] = [None] * len(flat)
+        if dirty:
+            for i, new in zip(dirty, engine.sub_host(prog, batch, dirty)):
+                res[i] = new
+            self.launches += 1
+        out, i = [], 0
+        for g in groups:
+            out.append(res[i:i + len(g)])
+            i += len(g)
+        return out
+
+    # ---- asyncio front: coalesce concurrent callers
+    async def scan(self, prog: engine.Program, units: Sequence[Unit]) -> List[int]:
+        return await self._submit(prog, "scan", 0, units)
+
+    async def sub(self, prog: engine.Program, units: Sequence[Unit], rule_mask: int) -> List[Optional[bytes]]:
+        return await self._submit(prog, "sub", rule_mask, units)
+
+    async def _submit(self, prog: engine.Program, op: str, arg: int, units: Sequence[Unit]):
+        if not units:
+            return []
+        loop = asyncio.get_running_loop()
+        fut: asyncio.Future = loop.create_future()
+        key = (id(prog), op, arg)
+        if key not in self._pending:
+            self._pending[key] = (prog, op, arg, [])
+        self._pending[key][3].append((list(units), fut))
+        if not self._scheduled:
+            self._scheduled = True
+            if self.window_us > 0:
+                loop.call_later(self.window_us / 1e6, self._flush)
+            else:
+                loop.call_soon(self._flush)
+        return await fut
+
+    def _flush(self) -> None:
+        self._scheduled = False
+        pending, self._pending = self._pending, {}
+        for prog, op, arg, waiters in pending.values():
+            try:
+                groups = [w[0] for w in waiters]
+                results = self.scan_groups(prog, groups) if op == "scan" else self.sub_groups(prog, groups, arg)
+            except Exception as exc:  # surface the failure to every caller (no silent fallback)
+                for _, fut in waiters:
+                    if not fut.done():
+                        fut.set_exception(exc)
+                continue
+            for (_, fut), res in zip(waiters, results):
+                if not fut.done():
+                    fut.set_result(res)

@@ -67,6 +67,10 @@ struct cf_prog {
   std::vector<int> ordered_pat;    // pattern index of each ordered rule
   std::vector<uint8_t*> d_repl;
   std::vector<uint32_t> repl_len;
+  std::vector<uint32_t> ordered_minlen;   // minimum match length (code points) of each ordered rule
+  std::vector<uint64_t> h_offsets;        // host copy of the last batch's offsets (cf_sub_host sizing)
+  const void* h_offsets_owner = nullptr;
+  uint64_t h_offsets_gen = 0;
 };
 
 struct cf_batch {
@@ -79,6 +83,7 @@ struct cf_batch {
   uint32_t cap_units = 0;
   uint64_t nbytes = 0;
   uint32_t n = 0;
+  uint64_t generation = 0;         // bumped by every upload
   CUtensorMap tmap;                // 2-D view of d_buf: rows of 128 B, box = one scan tile, SWIZZLE_128B
 };
 
@@ -449,6 +454,127 @@ static const ScanVariant* scan_variant(uint32_t warps, uint32_t acc) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// regex_filter substitution (rare path: only units the scan flagged as containing some rule match).
+// One warp per selected unit; rules are applied one after another on the unit's current text
+// (plugins/regex_filter/search_replace.py:127-130), each rule = Python `pattern.sub(repl, text)`:
+// leftmost-first, non-overlapping matches (patterns that can match "" are rejected at compile time).
+// ------------------------------------------------------------------------------------------------
+static const uint32_t SUB_MAX_RULES = 32;
+static const uint32_t SUB_WIN = 512;            // start positions examined per warp iteration
+static const uint32_t SUB_WARPS = 4;
+
+struct SubRule {
+  cf::DfaTables dfa;
+  const uint32_t* E;
+  const uint8_t* repl;
+  uint32_t repl_len;
+};
+
+struct SubParams {
+  const uint8_t* stream;
+  const uint64_t* offsets;
+  const uint32_t* sel;        // selected unit indices
+  const uint64_t* soff;       // per selected unit: offset of its scratch area (two buffers of `bound` bytes)
+  const uint64_t* bound;
+  uint8_t* scratch;
+  uint64_t* rec;              // per selected unit: [0] = final text offset in scratch (or ~0: unchanged), [1] = length
+  uint32_t n_sel;
+  uint32_t n_rules;
+  SubRule rules[SUB_MAX_RULES];
+};
+
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t lane) {
+  for (uint64_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(SUB_WARPS * 32) sub_kernel(const __grid_constant__ SubParams P) {
+  __shared__ uint32_t mlen_s[SUB_WARPS][SUB_WIN];
+  const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t w = blockIdx.x * SUB_WARPS + wic;
+  if (w >= P.n_sel) return;
+  uint32_t* mlen = mlen_s[wic];
+  const uint32_t u = P.sel[w];
+  const uint8_t* src = P.stream + P.offsets[u];
+  uint64_t len = P.offsets[u + 1] - P.offsets[u] - 1;
+  uint8_t* bufs[2] = {P.scratch + P.soff[w], P.scratch + P.soff[w] + P.bound[w]};
+  uint32_t which = 0;
+  bool changed = false;
+
+  for (uint32_t r = 0; r < P.n_rules; ++r) {
+    const SubRule& R = P.rules[r];
+    uint8_t* dst = bufs[which];
+    uint64_t out_pos = 0, copied = 0, cur = 0;
+    uint32_t nmatch = 0;
+    for (uint64_t wbase = 0; wbase < len; wbase += SUB_WIN) {
+      // prefilter the 16 start positions owned by this lane (5-byte window: start-1 .. start+3)
+      const uint64_t b0 = wbase + (uint64_t)lane * 16;
+      uint32_t acc = 0, cand = 0;
+      for (int k = -1; k < 19; ++k) {
+        const int64_t pos = (int64_t)b0 + k;
+        const uint32_t byte = (pos < 0 || (uint64_t)pos >= len) ? (uint32_t)cf::TERM : (uint32_t)src[pos];
+        acc = cf::filter_step(acc, R.E[byte]);
+        if (k >= 3 && (acc & cf::F_MASK)) cand |= 1u << (k - 3);
+      }
+      uint32_t has = 0;
+      for (uint32_t k = 0; k < 16; ++k) mlen[lane * 16 + k] = 0;
+      while (cand) {
+        const uint32_t k = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const uint64_t sp = b0 + k;
+        if (sp >= len || (src[sp] & 0xC0) == 0x80) continue;
+        const uint64_t e = cf::match_first(R.dfa, src, 0, len, sp);
+        if (e != ~0ull && e > sp) { mlen[lane * 16 + k] = (uint32_t)(e - sp); has |= 1u << k; }
+      }
+      __syncwarp();
+      // resolve overlaps left to right (uniform across the warp) and emit
+      for (uint32_t L = 0; L < 32; ++L) {
+        uint32_t mk = __shfl_sync(0xFFFFFFFFu, has, L);
+        while (mk) {
+          const uint32_t k = __ffs(mk) - 1;
+          mk &= mk - 1;
+          const uint64_t sp = wbase + (uint64_t)L * 16 + k;
+          if (sp < cur) continue;                       // inside the previous match
+          const uint32_t ml = mlen[L * 16 + k];
+          warp_copy(dst + out_pos, src + copied, sp - copied, lane);
+          out_pos += sp - copied;
+          warp_copy(dst + out_pos, R.repl, R.repl_len, lane);
+          out_pos += R.repl_len;
+          copied = cur = sp + ml;
+          ++nmatch;
+        }
+      }
+      __syncwarp();
+    }
+    if (nmatch) {
+      warp_copy(dst + out_pos, src + copied, len - copied, lane);
+      out_pos += len - copied;
+      __syncwarp();
+      __threadfence_block();
+      src = dst;
+      len = out_pos;
+      which ^= 1;
+      changed = true;
+    }
+  }
+  if (lane == 0) {
+    P.rec[2 * (uint64_t)w] = changed ? (uint64_t)(src - P.scratch) : ~0ull;
+    P.rec[2 * (uint64_t)w + 1] = len;
+  }
+}
+
+__global__ void sub_compact_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
+                                   const uint32_t* __restrict__ sel, const uint8_t* __restrict__ scratch,
+                                   const uint64_t* __restrict__ rec, const uint64_t* __restrict__ out_off,
+                                   uint8_t* __restrict__ out, uint32_t n_sel) {
+  const uint32_t w = blockIdx.x;
+  if (w >= n_sel) return;
+  const uint64_t n = rec[2 * (uint64_t)w + 1];
+  const uint8_t* src = rec[2 * (uint64_t)w] == ~0ull ? stream + offsets[sel[w]] : scratch + rec[2 * (uint64_t)w];
+  uint8_t* dst = out + out_off[w];
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -557,6 +683,7 @@ int cf_compile(cf_ctx* ctx, cf_builder* b, cf_prog** out) {
     if (rl) CF_CUDA(ctx, cudaMemcpy(dr, b->repl[i].data(), rl, cudaMemcpyHostToDevice));
     p->d_repl.push_back(dr);
     p->repl_len.push_back((uint32_t)rl);
+    p->ordered_minlen.push_back(b->out.info[i].min_len_chars);
     ++oi;
   }
   return CF_OK;
@@ -649,6 +776,7 @@ int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t st
   }
   b->nbytes = stream_bytes;
   b->n = n_units;
+  b->generation++;
   return CF_OK;
 }
 
@@ -712,6 +840,88 @@ int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, ui
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = CF_E_CUDA; }
   }
   cudaFreeAsync(d_bm, 0);
+  return rc;
+}
+
+int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uint32_t n_sel, uint8_t* out_bytes,
+                uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed) {
+  if (!ctx || !p || !b || !units || !n_sel || !out_offsets) return CF_E_BADARG;
+  const uint32_t nr = (uint32_t)p->ordered.size();
+  if (nr == 0 || nr > SUB_MAX_RULES) { ctx->err = "program has no (or too many) substitution rules"; return CF_E_BADARG; }
+  if (p->h_offsets_owner != b || p->h_offsets_gen != b->generation || p->h_offsets.size() != (size_t)b->n + 1) {
+    // unit lengths are needed on the host to size the scratch area
+    p->h_offsets.resize((size_t)b->n + 1);
+    CF_CUDA(ctx, cudaMemcpy(p->h_offsets.data(), b->d_offsets, ((size_t)b->n + 1) * 8, cudaMemcpyDeviceToHost));
+    p->h_offsets_owner = b;
+    p->h_offsets_gen = b->generation;
+  }
+  // worst-case growth of one unit through all rules
+  double growth = 1.0;
+  for (uint32_t r = 0; r < nr; ++r) {
+    uint32_t ml = p->ordered_minlen[r] ? p->ordered_minlen[r] : 1;
+    double g = (double)((p->repl_len[r] + ml - 1) / ml);
+    growth *= g > 1.0 ? g : 1.0;
+  }
+  std::vector<uint64_t> soff(n_sel), bound(n_sel);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_sel; ++i) {
+    if (units[i] >= b->n) { ctx->err = "unit index out of range"; return CF_E_BADARG; }
+    uint64_t len = p->h_offsets[units[i] + 1] - p->h_offsets[units[i]] - 1;
+    double bd = (double)len * growth + 16.0;
+    if (bd > 4e9) { ctx->err = "substitution rules expand a unit beyond 4 GB"; return CF_E_CAPACITY; }
+    bound[i] = ((uint64_t)bd + 15) & ~15ull;
+    soff[i] = total;
+    total += 2 * bound[i];
+  }
+  if (total > (8ull << 30)) { ctx->err = "substitution scratch exceeds 8 GiB"; return CF_E_CAPACITY; }
+  uint8_t* d_scratch = nullptr;
+  uint32_t* d_sel = nullptr;
+  uint64_t *d_soff = nullptr, *d_bound = nullptr, *d_rec = nullptr, *d_ooff = nullptr;
+  uint8_t* d_out = nullptr;
+  int rc = CF_OK;
+  std::vector<uint64_t> rec(2 * (size_t)n_sel);
+  do {
+#define SUB_CUDA(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = CF_E_CUDA; break; } }
+    SUB_CUDA(cudaMalloc(&d_scratch, total ? total : 16));
+    SUB_CUDA(cudaMalloc(&d_sel, n_sel * 4));
+    SUB_CUDA(cudaMalloc(&d_soff, n_sel * 8));
+    SUB_CUDA(cudaMalloc(&d_bound, n_sel * 8));
+    SUB_CUDA(cudaMalloc(&d_rec, n_sel * 16));
+    SUB_CUDA(cudaMalloc(&d_ooff, ((size_t)n_sel + 1) * 8));
+    SUB_CUDA(cudaMemcpy(d_sel, units, n_sel * 4, cudaMemcpyHostToDevice));
+    SUB_CUDA(cudaMemcpy(d_soff, soff.data(), n_sel * 8, cudaMemcpyHostToDevice));
+    SUB_CUDA(cudaMemcpy(d_bound, bound.data(), n_sel * 8, cudaMemcpyHostToDevice));
+    SubParams SP;
+    SP.stream = b->d_buf + cf::FRONT_PAD;
+    SP.offsets = b->d_offsets;
+    SP.sel = d_sel; SP.soff = d_soff; SP.bound = d_bound; SP.scratch = d_scratch; SP.rec = d_rec;
+    SP.n_sel = n_sel; SP.n_rules = nr;
+    for (uint32_t r = 0; r < nr; ++r) {
+      SP.rules[r].dfa = p->ordered[r].t;
+      SP.rules[r].E = p->d_ordered_E[r];
+      SP.rules[r].repl = p->d_repl[r];
+      SP.rules[r].repl_len = p->repl_len[r];
+    }
+    sub_kernel<<<(n_sel + SUB_WARPS - 1) / SUB_WARPS, SUB_WARPS * 32>>>(SP);
+    ctx->launches++;
+    SUB_CUDA(cudaGetLastError());
+    SUB_CUDA(cudaMemcpy(rec.data(), d_rec, n_sel * 16, cudaMemcpyDeviceToHost));
+    uint64_t need = 0;
+    for (uint32_t i = 0; i < n_sel; ++i) { out_offsets[i] = need; need += rec[2 * (size_t)i + 1]; }
+    out_offsets[n_sel] = need;
+    if (out_needed) *out_needed = need;
+    if (need > out_cap || (!out_bytes && need)) { ctx->err = "output buffer too small"; rc = CF_E_CAPACITY; break; }
+    if (need) {
+      SUB_CUDA(cudaMalloc(&d_out, need));
+      SUB_CUDA(cudaMemcpy(d_ooff, out_offsets, ((size_t)n_sel + 1) * 8, cudaMemcpyHostToDevice));
+      sub_compact_kernel<<<n_sel, 256>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, d_sel, d_scratch, d_rec, d_ooff, d_out, n_sel);
+      ctx->launches++;
+      SUB_CUDA(cudaGetLastError());
+      SUB_CUDA(cudaMemcpy(out_bytes, d_out, need, cudaMemcpyDeviceToHost));
+    }
+#undef SUB_CUDA
+  } while (0);
+  cudaFree(d_scratch); cudaFree(d_sel); cudaFree(d_soff); cudaFree(d_bound); cudaFree(d_rec); cudaFree(d_ooff); cudaFree(d_out);
   return rc;
 }
 

@@ -202,3 +202,27 @@ def scan_units(prog: Program, units: Sequence[Union[str, bytes]], ctx: Optional[
     batch = Batch(ctx, len(stream), len(units))
     bm = scan_host(prog, batch, stream, offs)
     return bitmaps_to_ints(bm, len(units), prog.words)
+
+
+def sub_host(prog: Program, batch: Batch, unit_indices: Sequence[int]) -> List[bytes]:
+    """Apply the program's substitution rules (in order) to the listed units of the batch that was
+    last uploaded/scanned.  Returns the rewritten bytes of each listed unit (cf_sub_host)."""
+    ctx = batch.ctx
+    n = len(unit_indices)
+    if n == 0:
+        return []
+    sel = np.asarray(unit_indices, dtype=np.uint32)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    need = c_uint64(0)
+    cap = 1 << 16
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        with ctx.lock:
+            rc = ctx.lib.cf_sub_host(ctx.h, prog.h, batch.h, sel.ctypes.data, n, out.ctypes.data, cap, offs.ctypes.data, byref(need))
+        if rc == N.CF_E_CAPACITY and need.value > cap:
+            cap = int(need.value)
+            continue
+        ctx.check(rc, "cf_sub_host")
+        break
+    raw = out.tobytes()
+    return [raw[int(offs[i]):int(offs[i + 1])] for i in range(n)]

@@ -1,0 +1,11 @@
+"""GPU drop-in plugins.  Swap the `kind:` lines of plugins/config.yaml:
+
+  plugins.regex_filter.search_replace.SearchReplacePlugin
+      -> mcp_context_forge_b200.plugins.regex_filter.SearchReplacePlugin
+  plugins.deny_filter.deny.DenyListPlugin
+      -> mcp_context_forge_b200.plugins.deny_filter.DenyListPlugin
+  plugins.harmful_content_detector.harmful_content_detector.HarmfulContentDetectorPlugin
+      -> mcp_context_forge_b200.plugins.harmful_content_detector.HarmfulContentDetectorPlugin
+  plugins.toon_encoder.toon_encoder.ToonEncoderPlugin
+      -> mcp_context_forge_b200.plugins.toon_encoder.ToonEncoderPlugin
+"""

@@ -1,0 +1,114 @@
+# -*- coding: utf-8 -*-
+"""GPU drop-in for /root/reference/plugins/harmful_content_detector/harmful_content_detector.py.
+
+Same class name, config schema, hooks, violation/metadata shapes.  The 9 x `pat.search(s)` loop of
+`_scan_text` (reference :92-107) is replaced by one fused GPU scan over every string of the payload
+(bit i of a unit's bitmap == pattern i matched that string); findings are rebuilt on the host in
+the reference's order: string order, then category order, then pattern order (:190-195).
+"""
+from __future__ import annotations
+
+import re
+from typing import Any, Dict, Iterable, List, Tuple
+
+from pydantic import BaseModel
+
+from .. import engine
+from ..batching import GpuBatcher
+from ..framework import (Plugin, PluginConfig, PluginContext, PluginViolation, PromptPrehookPayload, PromptPrehookResult,
+                         ToolPostInvokePayload, ToolPostInvokeResult)
+
+# reference :36-52
+DEFAULT_LEXICONS: Dict[str, List[str]] = {
+    "self_harm": [r"\bkill myself\b", r"\bsuicide\b", r"\bself-harm\b", r"\bwant to die\b"],
+    "violence": [r"\bkill (?:him|her|them|someone)\b", r"\bshoot (?:him|her|them|someone)\b", r"\bstab (?:him|her|them|someone)\b"],
+    "hate": [r"\b(?:kill|eradicate) (?:[a-z]+) people\b", r"\b(?:racial slur|hate speech)\b"],
+}
+
+
+class HarmfulContentConfig(BaseModel):
+    """reference :55-89 (patterns are kept as source text; compilation targets the GPU engine)."""
+
+    categories: Dict[str, List[str]] = {}
+    block_on: List[str] = ["self_harm", "violence", "hate"]
+    redact: bool = False
+    redaction_text: str = "[REDACTED]"
+
+    def __init__(self, **data):
+        if "categories" not in data:
+            data["categories"] = {c: list(p) for c, p in DEFAULT_LEXICONS.items()}
+        else:
+            data["categories"] = {c: [p if isinstance(p, str) else p.pattern for p in pats] for c, pats in data["categories"].items()}
+        super().__init__(**data)
+
+
+def _iter_strings(value: Any) -> Iterable[Tuple[str, str]]:
+    """reference :110-139."""
+    def walk(obj: Any, path: str):
+        if isinstance(obj, str):
+            yield path, obj
+        elif isinstance(obj, dict):
+            for k, v in obj.items():
+                yield from walk(v, f"{path}.{k}" if path else str(k))
+        elif isinstance(obj, list):
+            for i, v in enumerate(obj):
+                yield from walk(v, f"{path}[{i}]")
+    yield from walk(value, "")
+
+
+class HarmfulContentDetectorPlugin(Plugin):
+    def __init__(self, config: PluginConfig) -> None:
+        super().__init__(config)
+        self._cfg = HarmfulContentConfig(**(config.config or {}))
+        self._bits: List[Tuple[str, str]] = []          # bit index -> (category, pattern source)
+        self._prog = engine.Program()
+        for cat, pats in self._cfg.categories.items():
+            for p in pats:
+                re.compile(p, re.IGNORECASE)            # same validation (and re.error) as the reference :76,85
+                self._prog.add_search(p, re.IGNORECASE)  # raises UnsupportedPattern loudly; no CPU fallback
+                self._bits.append((cat, p))
+        self._prog.compile_host()
+        self._batcher: GpuBatcher | None = None
+
+    def _gpu(self) -> GpuBatcher:
+        if self._batcher is None:
+            self._batcher = GpuBatcher.get()
+        return self._batcher
+
+    def _findings_from_bitmaps(self, bitmaps: List[int]) -> List[Tuple[str, str]]:
+        findings: List[Tuple[str, str]] = []
+        for bm in bitmaps:
+            if bm:
+                for i, (cat, pat) in enumerate(self._bits):
+                    if (bm >> i) & 1:
+                        findings.append((cat, pat))
+        return findings
+
+    async def _scan(self, strings: List[str]) -> List[Tuple[str, str]]:
+        if not strings or not self._bits:
+            return []
+        return self._findings_from_bitmaps(await self._gpu().scan(self._prog, strings))
+
+    def _result(self, cls, findings: List[Tuple[str, str]]):
+        cats = sorted(set(c for c, _ in findings))
+        if any(c in self._cfg.block_on for c in cats):
+            return cls(continue_processing=False,
+                       violation=PluginViolation(reason="Harmful content", description=f"Detected categories: {', '.join(cats)}", code="HARMFUL_CONTENT",
+                                                 details={"categories": cats, "findings": findings[:5]}))
+        return cls(metadata={"harmful_categories": cats} if cats else {})
+
+    async def prompt_pre_fetch(self, payload: PromptPrehookPayload, context: PluginContext) -> PromptPrehookResult:
+        """reference :157-181."""
+        strings = [s for _, s in _iter_strings(payload.args or {})]
+        return self._result(PromptPrehookResult, await self._scan(strings))
+
+    async def tool_post_invoke(self, payload: ToolPostInvokePayload, context: PluginContext) -> ToolPostInvokeResult:
+        """reference :183-213."""
+        text = payload.result
+        if isinstance(text, (dict, list)):
+            strings = [s for _, s in _iter_strings(text)]
+        elif isinstance(text, str):
+            strings = [text]
+        else:
+            strings = []
+        return self._result(ToolPostInvokeResult, await self._scan(strings))

@@ -1,0 +1,102 @@
+# -*- coding: utf-8 -*-
+"""GPU drop-in for /root/reference/plugins/regex_filter/search_replace.py.
+
+Same class name, config schema (`words: [{search, replace}]`) and hooks.  `pattern.sub(replacement,
+value)` applied rule after rule (reference :127-130, :147-155) runs on the GPU: one fused scan marks
+the values some rule matches, the substitution kernel rewrites only those (leftmost-first,
+non-overlapping, rules in order).  Invalid patterns are skipped exactly as the reference does
+(:73-75); valid patterns the GPU engine cannot express raise at construction (no CPU fallback).
+"""
+from __future__ import annotations
+
+import copy
+import re
+import re._parser as _sre_parser  # type: ignore[import]
+from typing import Any, Dict, List, Optional
+
+from pydantic import BaseModel
+
+from .. import engine
+from ..batching import GpuBatcher
+from ..framework import (Plugin, PluginConfig, PluginContext, PromptPosthookPayload, PromptPosthookResult, PromptPrehookPayload, PromptPrehookResult,
+                         ToolPostInvokePayload, ToolPostInvokeResult, ToolPreInvokePayload, ToolPreInvokeResult)
+from ..regex_frontend import UnsupportedPattern
+
+
+class SearchReplace(BaseModel):
+    search: str
+    replace: str
+
+
+class SearchReplaceConfig(BaseModel):
+    words: list[SearchReplace]
+
+
+def literal_replacement(template: str, pattern: "re.Pattern[str]") -> str:
+    """Expand a `re.sub` replacement template that has no group references to its literal text
+    (escape processing by sre's own template parser).  Group references need capture positions,
+    which the DFA engine does not produce -> UnsupportedPattern."""
+    parts = _sre_parser.parse_template(template, pattern)
+    if any(not isinstance(p, str) for p in parts):
+        raise UnsupportedPattern(f"replacement template {template!r} references groups")
+    return "".join(parts)
+
+
+class SearchReplacePlugin(Plugin):
+    def __init__(self, config: PluginConfig):
+        super().__init__(config)
+        self._srconfig = SearchReplaceConfig.model_validate(self._config.config)
+        self._prog = engine.Program()
+        self._rule_mask = 0
+        for word in self._srconfig.words:
+            try:
+                compiled = re.compile(word.search)
+            except re.error:
+                continue                                    # reference :73-75
+            repl = literal_replacement(word.replace, compiled)
+            bit = self._prog.add_sub(word.search, 0, repl)
+            self._rule_mask |= 1 << bit
+        if self._rule_mask:
+            self._prog.compile_host()
+        self._batcher: Optional[GpuBatcher] = None
+
+    async def _apply(self, values: List[str]) -> List[str]:
+        if not self._rule_mask or not values:
+            return values
+        if self._batcher is None:
+            self._batcher = GpuBatcher.get()
+        out = await self._batcher.sub(self._prog, values, self._rule_mask)
+        return [v if o is None else o.decode("utf-8", "surrogatepass") for v, o in zip(values, out)]
+
+    async def _apply_dict(self, d: Dict[str, Any]) -> Dict[str, Any]:
+        modified = dict(d)
+        keys = [k for k, v in modified.items() if isinstance(v, str)]
+        for k, v in zip(keys, await self._apply([modified[k] for k in keys])):
+            modified[k] = v
+        return modified
+
+    async def prompt_pre_fetch(self, payload: PromptPrehookPayload, context: PluginContext) -> PromptPrehookResult:
+        if payload.args:
+            payload = payload.model_copy(update={"args": await self._apply_dict(payload.args)})
+        return PromptPrehookResult(modified_payload=payload)
+
+    async def prompt_post_fetch(self, payload: PromptPosthookPayload, context: PluginContext) -> PromptPosthookResult:
+        if payload.result.messages:
+            modified_result = copy.deepcopy(payload.result)
+            texts = await self._apply([m.content.text for m in modified_result.messages])
+            for m, t in zip(modified_result.messages, texts):
+                m.content.text = t
+            payload = payload.model_copy(update={"result": modified_result})
+        return PromptPosthookResult(modified_payload=payload)
+
+    async def tool_pre_invoke(self, payload: ToolPreInvokePayload, context: PluginContext) -> ToolPreInvokeResult:
+        if payload.args:
+            payload = payload.model_copy(update={"args": await self._apply_dict(payload.args)})
+        return ToolPreInvokeResult(modified_payload=payload)
+
+    async def tool_post_invoke(self, payload: ToolPostInvokePayload, context: PluginContext) -> ToolPostInvokeResult:
+        if payload.result and isinstance(payload.result, dict):
+            payload = payload.model_copy(update={"result": await self._apply_dict(payload.result)})
+        elif payload.result and isinstance(payload.result, str):
+            payload = payload.model_copy(update={"result": (await self._apply([payload.result]))[0]})
+        return ToolPostInvokeResult(modified_payload=payload)
