@@ -25,9 +25,8 @@
 // ------------------------------------------------------------------------------------------------
 static const uint32_t LANE_BYTES = 64;
 static const uint32_t WARP_BYTES = 32 * LANE_BYTES;          // 2 KiB per warp per tile
-static const uint32_t MAX_WARPS = 24;   // padding granularity (>= every variant)
+static const uint32_t MAX_WARPS = 32;   // padding granularity (>= every variant's tile)
 static const uint32_t MAX_TILE = MAX_WARPS * WARP_BYTES;     // buffers are padded for the largest tile
-static const uint32_t STAGES = 3;
 
 struct cf_ctx {
   int device = 0;
@@ -43,9 +42,12 @@ struct cf_ctx {
   uint32_t prof_used = 0;
   bool prof_on = false;
   // scan kernel configuration (CF_SCAN_WARPS / CF_SCAN_ACC override the defaults; experiments)
-  uint32_t scan_warps = 16;
-  uint32_t scan_acc = 0;
-  uint32_t tile() const { return scan_warps * WARP_BYTES; }
+  uint32_t scan_warps = 20;        // best of the measured variants (profiles/README.md)
+  uint32_t scan_lane_bytes = 64;
+  uint32_t scan_acc = 1;
+  uint32_t scan_stages = 3;
+  uint32_t tile() const { return scan_warps * 32 * scan_lane_bytes; }
+  uint32_t box_rows() const { uint32_t rows = tile() / 128, nbox = (rows + 255) / 256; return rows / nbox; }
 };
 
 struct DevDfa {
@@ -169,6 +171,7 @@ struct ScanParams {
   uint32_t qcap_cta;
   uint32_t dfa_bytes;             // bytes needed to stage the DFA tables in shared memory (0 = too big)
   uint32_t dfa_trans_bytes, dfa_acc_bytes;
+  uint32_t mulc;                  // 64 (kept out of the instruction stream on purpose)
   uint32_t dbg;                   // experiments: 1 = skip verification, 2 = no smem staging
 };
 
@@ -226,27 +229,23 @@ __device__ __noinline__ void verify_candidate(const ScanParams& P, const cf::Dfa
   }
 }
 
-static const uint32_t WQ = 32;   // per-warp candidate staging slots in shared memory
+static const uint32_t WQ = 32;          // per-warp candidate staging slots in shared memory
+static const uint32_t SCAN_SMEM = 227 * 1024;   // whole opt-in shared memory of the SM (1 CTA per SM)
 
+// Small per-CTA bookkeeping that lives next to the tile stages.
+static const uint32_t MAX_STAGES = 5;
 template <uint32_t WARPS>
-struct ScanSmemT {
-  // Lane-private-bank prefilter table: the entry for byte value b as seen by lane l lives at byte
-  // offset b*256 + l*4, i.e. always in bank l -> every lookup is conflict-free for any input, and the
-  // offset (b << 8 | l << 2) is produced by ONE PRMT from the data word and a lane constant.
-  alignas(1024) uint32_t tbl[256 * 64];
-  // tile rows are 128 B, stored with the TMA 128-byte swizzle: 16-byte chunk c of row r sits at
-  // chunk c ^ (r & 7) -> a lane reading its own 64 contiguous bytes is bank-conflict free
-  alignas(1024) uint8_t tile[STAGES][WARPS * WARP_BYTES];
+struct ScanMisc {
   alignas(8) unsigned long long wq[WARPS][WQ];
   uint32_t wq_n[WARPS];
   uint32_t cq_n;                   // candidates in this CTA's global queue segment
-  alignas(8) uint64_t full[STAGES];
-  alignas(8) uint64_t empty[STAGES];
+  alignas(8) uint64_t full[MAX_STAGES];
+  alignas(8) uint64_t empty[MAX_STAGES];
 };
 
 // append one candidate (called by the few lanes that found one; divergent context)
 template <uint32_t WARPS>
-__device__ __noinline__ void push_candidate(ScanSmemT<WARPS>& sm, const ScanParams& P, uint32_t warp, uint64_t pos) {
+__device__ __noinline__ void push_candidate(ScanMisc<WARPS>& sm, const ScanParams& P, uint32_t warp, uint64_t pos) {
   uint32_t slot = atomicAdd(&sm.wq_n[warp], 1u);
   if (slot < WQ) { sm.wq[warp][slot] = pos; return; }
   // staging full (pathologically dense candidates): go straight to the CTA queue
@@ -257,7 +256,7 @@ __device__ __noinline__ void push_candidate(ScanSmemT<WARPS>& sm, const ScanPara
 
 // warp-cooperative flush of the staging slots into the CTA's queue segment
 template <uint32_t WARPS>
-__device__ __forceinline__ void flush_candidates(ScanSmemT<WARPS>& sm, const ScanParams& P, uint32_t warp, uint32_t lane) {
+__device__ __forceinline__ void flush_candidates(ScanMisc<WARPS>& sm, const ScanParams& P, uint32_t warp, uint32_t lane) {
   uint32_t n = sm.wq_n[warp];
   if (n > WQ) n = WQ;
   uint32_t base = 0;
@@ -273,84 +272,121 @@ __device__ __forceinline__ void flush_candidates(ScanSmemT<WARPS>& sm, const Sca
   __syncwarp();
 }
 
+// Prefilter table in shared memory, "lane-private bank" layout at a 64 KiB-aligned ABSOLUTE shared
+// address T:  entry(byte value b, lane l) = T + (b << 8) + (l << 2).
+//   * bank = l for every lookup -> conflict-free for any input bytes
+//   * the full 32-bit shared address is produced by ONE PRMT: bytes {l<<2, b, T>>16, 0} taken from the
+//     data word and the per-lane constant K = (l << 2) | T  -> no address arithmetic in the loop
+//   * (acc >> 6) | TOP is issued as IMAD.HI (FMA pipe) by multiplying with a non-immediate 2^26, so the
+//     ALU pipe only carries PRMT + the AND + the hit OR.
 template <uint32_t ACC>
-__device__ __forceinline__ uint32_t acc_shift(uint32_t acc) {
-  if (ACC == 1) {   // (acc >> 6) + 0x3F000000 as IMAD.HI on the FMA pipe instead of the ALU pipe
-    uint32_t r;
-    asm("mad.hi.u32 %0, %1, 0x4000000, 0x3F000000;" : "=r"(r) : "r"(acc));
-    return r;
-  }
-  return (acc >> 6) | 0x3F000000u;
+__device__ __forceinline__ uint32_t acc_step(uint32_t acc, uint32_t e, uint32_t mulc) {
+  // ((acc << 6) | 0x3F) & e.  ACC == 1 issues the shift-or as IMAD (acc * 64 + 63, multiplier kept
+  // out of the immediate field so ptxas cannot turn it back into an ALU-pipe LEA/SHF).
+  uint32_t t;
+  if (ACC == 1) asm("mad.lo.u32 %0, %1, %2, 63;" : "=r"(t) : "r"(acc), "r"(mulc));
+  else t = (acc << 6) | 0x3Fu;
+  return t & e;
+}
+__device__ __forceinline__ uint32_t lds_abs(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
-#define FEED(word, k, H)                                                                      \
-  {                                                                                           \
-    const uint32_t a_ = __byte_perm((word), lane4, 0x5504 | ((k) << 4)); /* b<<8 | lane<<2 */ \
-    acc = acc_shift<ACC>(acc) & *reinterpret_cast<const uint32_t*>(tblb + a_);                \
-    H |= acc;                                                                                 \
+#define FEED(word, k, H)                                                                        \
+  {                                                                                             \
+    const uint32_t a_ = __byte_perm((word), laneK, 0x7604 | ((k) << 4)); /* T | b<<8 | lane<<2 */ \
+    acc = acc_step<ACC>(acc, lds_abs(a_), mulc);                                                \
+    H |= acc;                                                                                   \
   }
 #define FEED4(word, H) FEED(word, 0, H) FEED(word, 1, H) FEED(word, 2, H) FEED(word, 3, H)
 #define FEED16(v, H) FEED4((v).x, H) FEED4((v).y, H) FEED4((v).z, H) FEED4((v).w, H)
 
 // rare path, lane-local: re-run one 16-byte group with position tracking (data still in registers)
-#define REFEED(word, k, bit)                                                                  \
-  {                                                                                           \
-    const uint32_t a_ = __byte_perm((word), lane4, 0x5504 | ((k) << 4));                      \
-    acc = ((acc >> 6) | 0x3F000000u) & *reinterpret_cast<const uint32_t*>(tblb + a_);         \
-    m |= ((acc & 0x3Fu) ? 1u : 0u) << (bit);                                                  \
+#define REFEED(word, k, bit)                                                                    \
+  {                                                                                             \
+    const uint32_t a_ = __byte_perm((word), laneK, 0x7604 | ((k) << 4));                        \
+    acc = ((acc << 6) | 0x3Fu) & lds_abs(a_);                                                   \
+    m |= ((acc & 0x3F000000u) ? 1u : 0u) << (bit);                                              \
   }
 #define REFEED4(word, b0) REFEED(word, 0, (b0)) REFEED(word, 1, (b0) + 1) REFEED(word, 2, (b0) + 2) REFEED(word, 3, (b0) + 3)
-#define REGROUP(prevword, v, gpos)                                                            \
-  {                                                                                           \
-    uint32_t acc = 0, dummy = 0, m = 0;                                                       \
-    FEED4(prevword, dummy)                                                                    \
-    (void)dummy;                                                                              \
-    REFEED4((v).x, 0) REFEED4((v).y, 4) REFEED4((v).z, 8) REFEED4((v).w, 12)                  \
-    while (m) {                                                                               \
-      const uint32_t k_ = __ffs(m) - 1;                                                       \
-      m &= m - 1;                                                                             \
-      push_candidate<WARPS>(sm, P, warp, (gpos) + k_ - 3);                                    \
-    }                                                                                         \
+#define REGROUP(prevword, v, gpos)                                                              \
+  {                                                                                             \
+    uint32_t acc = 0, m = 0;                                                                    \
+    REFEED4(prevword, 0)                                                                        \
+    m = 0;                                                                                      \
+    REFEED4((v).x, 0) REFEED4((v).y, 4) REFEED4((v).z, 8) REFEED4((v).w, 12)                    \
+    while (m) {                                                                                 \
+      const uint32_t k_ = __ffs(m) - 1;                                                         \
+      m &= m - 1;                                                                               \
+      push_candidate<WARPS>(sm, P, warp, (gpos) + k_ - 3);                                      \
+    }                                                                                           \
   }
 
-template <uint32_t WARPS, uint32_t ACC>
+template <uint32_t WARPS, uint32_t LB, uint32_t ACC, uint32_t STAGES>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_constant__ ScanParams P,
                                                                const __grid_constant__ CUtensorMap tmap) {
-  constexpr uint32_t TILE = WARPS * WARP_BYTES;
+  constexpr uint32_t NS = LB / 16;                  // 16-byte slots per lane per tile
+  constexpr uint32_t LPR = 128 / LB;                // lanes per 128-byte row
+  constexpr uint32_t TILE = WARPS * 32 * LB;
   constexpr int32_t TROWS = TILE / 128;
-  constexpr int32_t ROW0 = cf::FRONT_PAD / 128;   // stream byte 0 is row FRONT_PAD/128 of the buffer
+  constexpr int32_t NBOX = (TROWS + 255) / 256;     // TMA boxes per tile (box height <= 256 rows)
+  constexpr int32_t BROWS = TROWS / NBOX;
+  static_assert(BROWS * NBOX == TROWS, "tile rows must split evenly into TMA boxes");
+  constexpr int32_t ROW0 = cf::FRONT_PAD / 128;     // stream byte 0 is row FRONT_PAD/128 of the buffer
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  ScanSmemT<WARPS>& sm = *reinterpret_cast<ScanSmemT<WARPS>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lane4 = lane << 2;
-  const uint8_t* __restrict__ tblb = reinterpret_cast<const uint8_t*>(sm.tbl);
 
-  for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) sm.tbl[(i >> 5) * 64 + (i & 31)] = P.E[i >> 5];
-  if (tid < WARPS) sm.wq_n[tid] = 0;
-  if (tid == 0) { sm.cq_n = 0; if (blockIdx.x == 0) { P.qstate_next[0] = 0; P.qstate_next[1] = 0; } }
-  if (tid == 0) {
-    for (uint32_t s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // ---- carve shared memory: table at the first 64 KiB boundary, tile stages + misc around it
+  const uint32_t abs0 = smem_u32(smem_raw);
+  const uint32_t tbl_abs = (abs0 + 0xFFFFu) & ~0xFFFFu;
+  uint32_t a_lo = (abs0 + 1023u) & ~1023u, a_hi = tbl_abs;       // free space before the table
+  uint32_t b_lo = tbl_abs + 0x10000u, b_hi = abs0 + SCAN_SMEM;   // free space after it
+  uint8_t* stage[STAGES];
+#pragma unroll
+  for (uint32_t s = 0; s < STAGES; ++s) {
+    if (a_lo + TILE <= a_hi) { stage[s] = smem_raw + (a_lo - abs0); a_lo += TILE; }
+    else { stage[s] = smem_raw + (b_lo - abs0); b_lo += TILE; }
   }
-  __syncthreads();
+  uint32_t misc_abs;
+  if (a_lo + sizeof(ScanMisc<WARPS>) <= a_hi) misc_abs = a_lo; else { misc_abs = b_lo; b_lo += (uint32_t)sizeof(ScanMisc<WARPS>); }
+  if (b_lo > b_hi) __trap();                                     // cannot happen: variants are sized for 227 KiB
+  ScanMisc<WARPS>& sm = *reinterpret_cast<ScanMisc<WARPS>*>(smem_raw + (misc_abs - abs0));
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem_raw + (tbl_abs - abs0));
+  const uint32_t laneK = (lane << 2) | tbl_abs;                  // tbl_abs has zero low 16 bits
+  const uint32_t mulc = P.mulc;                                  // 64, deliberately not an immediate
+
+  auto load_tile = [&](uint32_t slot_, uint64_t tile_) {
+    mbar_expect_tx(&sm.full[slot_], TILE);
+#pragma unroll
+    for (int32_t bx = 0; bx < NBOX; ++bx)
+      tma_load_2d(stage[slot_] + bx * BROWS * 128, &tmap, 0, ROW0 + (int32_t)tile_ * TROWS + bx * BROWS, &sm.full[slot_]);
+  };
 
   const uint64_t first = blockIdx.x, stride = gridDim.x;
-  if (tid == 0) {   // prologue: fill STAGES-1 slots
+  if (tid < WARPS) sm.wq_n[tid] = 0;
+  if (tid == 0) {
+    sm.cq_n = 0;
+    if (blockIdx.x == 0) { P.qstate_next[0] = 0; P.qstate_next[1] = 0; }
+    for (uint32_t s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // prologue: put STAGES-1 tiles in flight right away; the table fill below overlaps their latency
     for (uint32_t j = 0; j < STAGES - 1; ++j) {
       uint64_t tj = first + (uint64_t)j * stride;
-      if (tj < P.ntiles) {
-        mbar_expect_tx(&sm.full[j], TILE);
-        tma_load_2d(sm.tile[j], &tmap, 0, ROW0 + (int32_t)tj * TROWS, &sm.full[j]);
-      }
+      if (tj < P.ntiles) load_tile(j, tj);
     }
   }
+  for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) tbl[(i >> 5) * 64 + (i & 31)] = P.E[i >> 5];
+  __syncthreads();
 
-  // per-lane swizzled offsets of its four 16-byte slots and of the word holding its look-back bytes
-  const uint32_t g = warp * 32 + lane, row = g >> 1, xr = row & 7, half4 = (g & 1) * 4;
-  const uint32_t o0 = row * 128 + (((half4 + 0) ^ xr) << 4), o1 = row * 128 + (((half4 + 1) ^ xr) << 4);
-  const uint32_t o2 = row * 128 + (((half4 + 2) ^ xr) << 4), o3 = row * 128 + (((half4 + 3) ^ xr) << 4);
-  const uint32_t gp = g ? g - 1 : 0, rowp = gp >> 1;
-  const uint32_t ob = rowp * 128 + (((((gp & 1) * 4) + 3) ^ (rowp & 7)) << 4) + 12;
+  // per-lane swizzled offsets of its 16-byte slots and of the word holding its look-back bytes
+  const uint32_t g = warp * 32 + lane, row = g / LPR, xr = row & 7, c0 = (g % LPR) * NS;
+  uint32_t off[NS];
+#pragma unroll
+  for (uint32_t j = 0; j < NS; ++j) off[j] = row * 128 + (((c0 + j) ^ xr) << 4);
+  const uint32_t gp = g ? g - 1 : 0, rowp = gp / LPR;
+  const uint32_t ob = rowp * 128 + (((((gp % LPR) * NS) + NS - 1) ^ (rowp & 7)) << 4) + 12;
   // lane 0 of the CTA takes its look-back word (last 4 bytes of the previous tile) from HBM/L2,
   // fetched one iteration ahead
   uint32_t back_next = 0;
@@ -365,39 +401,63 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
       if (tj < P.ntiles) {
         uint32_t sj = j % STAGES;
         if (j >= STAGES) mbar_wait(&sm.empty[sj], ((j / STAGES) - 1) & 1);
-        mbar_expect_tx(&sm.full[sj], TILE);
-        tma_load_2d(sm.tile[sj], &tmap, 0, ROW0 + (int32_t)tj * TROWS, &sm.full[sj]);
+        load_tile(sj, tj);
       }
     }
     uint32_t back = back_next;
     if (tid == 0 && t + stride < P.ntiles) back_next = *reinterpret_cast<const uint32_t*>(P.stream + (t + stride) * TILE - 4);
     mbar_wait(&sm.full[slot], phase);
 
-    // this lane's 64 bytes (+ the word holding its 4 look-back bytes)
-    const uint32_t chunk = g * LANE_BYTES;          // tile-relative
-    const uint8_t* base = sm.tile[slot];
+    // this lane's LB bytes (+ the word holding its 4 look-back bytes)
+    const uint32_t chunk = g * LB;          // tile-relative
+    const uint8_t* base = stage[slot];
     if (g) back = *reinterpret_cast<const uint32_t*>(base + ob);
-    const uint4 v0 = *reinterpret_cast<const uint4*>(base + o0);
-    const uint4 v1 = *reinterpret_cast<const uint4*>(base + o1);
-    const uint4 v2 = *reinterpret_cast<const uint4*>(base + o2);
-    const uint4 v3 = *reinterpret_cast<const uint4*>(base + o3);
+    uint4 v[NS];
+#pragma unroll
+    for (uint32_t j = 0; j < NS; ++j) v[j] = *reinterpret_cast<const uint4*>(base + off[j]);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[slot]);   // slot may be refilled: data is in registers
 
-    uint32_t acc = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    FEED4(back, h0)
-    h0 = 0;   // windows ending in the look-back bytes belong to the previous lane
-    FEED16(v0, h0) FEED16(v1, h1) FEED16(v2, h2) FEED16(v3, h3)
+    uint32_t h[NS];
+    if (NS == 4 && (P.dbg & 4) == 0) {
+      // two independent shift-AND chains per lane (bytes 0-31 and 32-63) for instruction-level
+      // parallelism; the second chain re-feeds the last word of the first half as its look-back
+      uint32_t accA = 0, accB = 0, dA = 0, dB = 0;
+      h[0] = h[1] = h[2] = h[3] = 0;
+#define FEEDA(word, k, H) { uint32_t acc = accA; FEED(word, k, H) accA = acc; }
+#define FEEDB(word, k, H) { uint32_t acc = accB; FEED(word, k, H) accB = acc; }
+#define FEED2(wa, wb, k, HA, HB) FEEDA(wa, k, HA) FEEDB(wb, k, HB)
+#define FEED2x4(wa, wb, HA, HB) FEED2(wa, wb, 0, HA, HB) FEED2(wa, wb, 1, HA, HB) FEED2(wa, wb, 2, HA, HB) FEED2(wa, wb, 3, HA, HB)
+      FEED2x4(back, v[1].w, dA, dB)
+      FEED2x4(v[0].x, v[2].x, h[0], h[2]) FEED2x4(v[0].y, v[2].y, h[0], h[2]) FEED2x4(v[0].z, v[2].z, h[0], h[2]) FEED2x4(v[0].w, v[2].w, h[0], h[2])
+      FEED2x4(v[1].x, v[3].x, h[1], h[3]) FEED2x4(v[1].y, v[3].y, h[1], h[3]) FEED2x4(v[1].z, v[3].z, h[1], h[3]) FEED2x4(v[1].w, v[3].w, h[1], h[3])
+#undef FEED2x4
+#undef FEED2
+#undef FEEDA
+#undef FEEDB
+      (void)dA; (void)dB;
+    } else {
+      uint32_t acc = 0;
+      h[0] = 0;
+      FEED4(back, h[0])
+#pragma unroll
+      for (uint32_t j = 0; j < NS; ++j) {
+        h[j] = 0;   // (windows ending in the look-back bytes belong to the previous lane)
+        FEED16(v[j], h[j])
+      }
+    }
 
     // rare path: an admissible 5-byte window ended in one of this lane's 16-byte groups
-    const bool anyhit = ((h0 | h1 | h2 | h3) & 0x3Fu) != 0;
+    uint32_t hany = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < NS; ++j) hany |= h[j];
+    const bool anyhit = (hany & 0x3F000000u) != 0;
     if (__any_sync(0xFFFFFFFFu, anyhit)) {
       if (anyhit) {
         const uint64_t cpos = t * TILE + chunk;   // stream offset of this lane's first byte
-        if (h0 & 0x3Fu) REGROUP(back, v0, cpos)
-        if (h1 & 0x3Fu) REGROUP(v0.w, v1, cpos + 16)
-        if (h2 & 0x3Fu) REGROUP(v1.w, v2, cpos + 32)
-        if (h3 & 0x3Fu) REGROUP(v2.w, v3, cpos + 48)
+#pragma unroll
+        for (uint32_t j = 0; j < NS; ++j)
+          if (h[j] & 0x3F000000u) REGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
       }
       __syncwarp();
       if (sm.wq_n[warp] >= WQ / 2) flush_candidates<WARPS>(sm, P, warp, lane);
@@ -405,31 +465,31 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   }
   __syncwarp();
   if (sm.wq_n[warp]) flush_candidates<WARPS>(sm, P, warp, lane);
-  __syncthreads();   // every tile this CTA requested has been consumed; the tile buffers are free
+  __syncthreads();   // every tile this CTA requested has been consumed; table + tile buffers are free
 
-  // ---- tail: verify this CTA's candidates, DFA tables staged in the (now idle) tile buffers
+  // ---- tail: verify this CTA's candidates, DFA tables staged over the (now idle) prefilter table
   const uint32_t ncand = sm.cq_n;
   if (ncand == 0) return;
   const uint32_t nq = ncand < P.qcap_cta ? ncand : P.qcap_cta;
   cf::DfaTables T = P.dfa;
-  if (P.dfa_bytes && P.dfa_bytes <= sizeof(sm.tile) && !(P.dbg & 2)) {
-    uint8_t* dst = &sm.tile[0][0];
-    uint32_t off = 0;
-    auto stage = [&](const void* src, uint32_t bytes) -> const void* {
+  if (P.dfa_bytes && P.dfa_bytes <= 0x10000u && !(P.dbg & 2)) {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(tbl);
+    uint32_t off_ = 0;
+    auto stage_tbl = [&](const void* src, uint32_t bytes) -> const void* {
       const uint32_t words = (bytes + 3) / 4;
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + off);
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + off_);
       for (uint32_t i = tid; i < words; i += WARPS * 32) d32[i] = s32[i];
-      const void* r = dst + off;
-      off += (words * 4 + 15) & ~15u;
+      const void* r = dst + off_;
+      off_ += (words * 4 + 15) & ~15u;
       return r;
     };
-    T.ascii_cls = (const uint16_t*)stage(P.dfa.ascii_cls, 128 * 2);
-    T.range_start = (const uint32_t*)stage(P.dfa.range_start, P.dfa.nranges * 4);
-    T.range_cls = (const uint16_t*)stage(P.dfa.range_cls, P.dfa.nranges * 2);
-    T.cls_ctx = (const uint8_t*)stage(P.dfa.cls_ctx, P.dfa.ncols - 1);
-    T.trans = (const uint32_t*)stage(P.dfa.trans, P.dfa_trans_bytes);
-    T.accsets = (const uint64_t*)stage(P.dfa.accsets, P.dfa_acc_bytes);
+    T.ascii_cls = (const uint16_t*)stage_tbl(P.dfa.ascii_cls, 128 * 2);
+    T.range_start = (const uint32_t*)stage_tbl(P.dfa.range_start, P.dfa.nranges * 4);
+    T.range_cls = (const uint16_t*)stage_tbl(P.dfa.range_cls, P.dfa.nranges * 2);
+    T.cls_ctx = (const uint8_t*)stage_tbl(P.dfa.cls_ctx, P.dfa.ncols - 1);
+    T.trans = (const uint32_t*)stage_tbl(P.dfa.trans, P.dfa_trans_bytes);
+    T.accsets = (const uint64_t*)stage_tbl(P.dfa.accsets, P.dfa_acc_bytes);
     __syncthreads();
   }
   uint32_t steps = 0;
@@ -443,13 +503,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
 }
 
 typedef void (*scan_fn_t)(const ScanParams, const CUtensorMap);
-struct ScanVariant { scan_fn_t fn; uint32_t warps, acc; size_t smem; };
+struct ScanVariant { scan_fn_t fn; uint32_t warps, lane_bytes, acc, stages; };
+#define SV(W, LB, A, S) {scan_kernel<W, LB, A, S>, W, LB, A, S}
 static const ScanVariant SCAN_VARIANTS[] = {
-    {scan_kernel<8, 0>, 8, 0, sizeof(ScanSmemT<8>)},    {scan_kernel<8, 1>, 8, 1, sizeof(ScanSmemT<8>)},
-    {scan_kernel<16, 0>, 16, 0, sizeof(ScanSmemT<16>)}, {scan_kernel<16, 1>, 16, 1, sizeof(ScanSmemT<16>)},
+    SV(16, 64, 0, 3), SV(16, 64, 1, 3), SV(16, 64, 1, 4), SV(16, 64, 1, 2), SV(20, 64, 1, 3), SV(24, 64, 1, 3),
+    SV(16, 32, 1, 3), SV(24, 32, 1, 4), SV(32, 32, 1, 3), SV(32, 32, 1, 4),
 };
-static const ScanVariant* scan_variant(uint32_t warps, uint32_t acc) {
-  for (const auto& v : SCAN_VARIANTS) if (v.warps == warps && v.acc == acc) return &v;
+#undef SV
+static const ScanVariant* scan_variant(uint32_t warps, uint32_t lane_bytes, uint32_t acc, uint32_t stages) {
+  for (const auto& v : SCAN_VARIANTS)
+    if (v.warps == warps && v.lane_bytes == lane_bytes && v.acc == acc && v.stages == stages) return &v;
   return nullptr;
 }
 
@@ -513,7 +576,7 @@ __global__ void __launch_bounds__(SUB_WARPS * 32) sub_kernel(const __grid_consta
         const int64_t pos = (int64_t)b0 + k;
         const uint32_t byte = (pos < 0 || (uint64_t)pos >= len) ? (uint32_t)cf::TERM : (uint32_t)src[pos];
         acc = cf::filter_step(acc, R.E[byte]);
-        if (k >= 3 && (acc & cf::F_MASK)) cand |= 1u << (k - 3);
+        if (k >= 3 && (acc & cf::F_HIT)) cand |= 1u << (k - 3);
       }
       uint32_t has = 0;
       for (uint32_t k = 0; k < 16; ++k) mlen[lane * 16 + k] = 0;
@@ -628,9 +691,11 @@ int cf_init(int device_ordinal, cf_ctx** out) {
   CF_CUDA(ctx, cudaMalloc(&ctx->d_queue, (size_t)ctx->qcap * sizeof(uint64_t)));
   if (const char* e = getenv("CF_SCAN_WARPS")) ctx->scan_warps = (uint32_t)atoi(e);
   if (const char* e = getenv("CF_SCAN_ACC")) ctx->scan_acc = (uint32_t)atoi(e);
-  if (!scan_variant(ctx->scan_warps, ctx->scan_acc)) { ctx->err = "CF_SCAN_WARPS must be 8 or 16 and CF_SCAN_ACC 0 or 1"; return CF_E_BADARG; }
+  if (const char* e = getenv("CF_SCAN_LB")) ctx->scan_lane_bytes = (uint32_t)atoi(e);
+  if (const char* e = getenv("CF_SCAN_STAGES")) ctx->scan_stages = (uint32_t)atoi(e);
+  if (!scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages)) { ctx->err = "unsupported CF_SCAN_WARPS / CF_SCAN_LB / CF_SCAN_ACC / CF_SCAN_STAGES combination"; return CF_E_BADARG; }
   for (const auto& v : SCAN_VARIANTS)
-    CF_CUDA(ctx, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    CF_CUDA(ctx, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
   return CF_OK;
 }
 
@@ -730,7 +795,7 @@ int cf_batch_create(cf_ctx* ctx, uint64_t max_stream_bytes, uint32_t max_units, 
   if (!fn || qres != cudaDriverEntryPointSuccess) { ctx->err = "cuTensorMapEncodeTiled unavailable"; return CF_E_CUDA; }
   cuuint64_t gdim[2] = {128, total / 128};
   cuuint64_t gstride[1] = {128};
-  cuuint32_t box[2] = {128, ctx->tile() / 128};
+  cuuint32_t box[2] = {128, ctx->box_rows()};
   cuuint32_t estr[2] = {1, 1};
   CUresult cr = ((encode_fn)fn)(&b->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b->d_buf, gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -812,13 +877,14 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   P.dfa_bytes = p->search.stage_bytes < (1u << 30) ? (uint32_t)p->search.stage_bytes : 0;
   P.dfa_trans_bytes = (uint32_t)p->search.trans_bytes;
   P.dfa_acc_bytes = (uint32_t)p->search.acc_bytes;
+  P.mulc = 64;
   P.dbg = getenv("CF_DBG") ? (uint32_t)atoi(getenv("CF_DBG")) : 0;
-  const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_acc);
+  const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages);
   uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM
   if (grid > ntiles) grid = ntiles;
   const bool prof = ctx->prof_on && (size_t)ctx->prof_used + 2 <= ctx->prof_ev.size();
   if (prof) cudaEventRecord(ctx->prof_ev[ctx->prof_used], st);
-  sv->fn<<<(unsigned)grid, sv->warps * 32, sv->smem, st>>>(P, b->tmap);
+  sv->fn<<<(unsigned)grid, sv->warps * 32, SCAN_SMEM, st>>>(P, b->tmap);
   if (prof) { cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], st); ctx->prof_used += 2; }
   ctx->launches++;
   CF_CUDA(ctx, cudaGetLastError());

@@ -512,9 +512,9 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
     for (int p : bks[k].pats) fo.bucket_of_pattern[p] = (int)k;
     for (uint32_t b = 0; b < 256; ++b) {
       uint32_t e = 0;
-      if (bks[k].f.N.get(b)) e |= 1u << (24 + k);
+      if (bks[k].f.N.get(b)) e |= 1u << k;
       for (int j = 0; j < NPOS; ++j)
-        if (bks[k].f.pos[j].get(b)) e |= 1u << ((NPOS - 1 - j) * cf::F_BITS + k);
+        if (bks[k].f.pos[j].get(b)) e |= 1u << ((j + 1) * cf::F_BITS + k);
       fo.E[b] |= e;
     }
   }

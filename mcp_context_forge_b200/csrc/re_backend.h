@@ -45,7 +45,7 @@ struct DfaOut {
 };
 
 struct FilterOut {
-  uint32_t E[256];           // N<<24 | P0<<18 | P1<<12 | P2<<6 | P3 (six buckets per field; scan_core.h)
+  uint32_t E[256];           // P3<<24 | P2<<18 | P1<<12 | P0<<6 | N (six buckets per field; scan_core.h)
   std::vector<int> bucket_of_pattern;
 };
 

@@ -129,15 +129,15 @@ CF_HD uint64_t match_first(const DfaTables& t, const uint8_t* s, uint64_t ustart
 }
 
 // Prefilter.  Five 6-bit fields per byte value, six pattern buckets per field:
-//   E[b] = N<<24 | P0<<18 | P1<<12 | P2<<6 | P3
+//   E[b] = P3<<24 | P2<<18 | P1<<12 | P0<<6 | N
 //   N  : bucket k admits b as the byte BEFORE a match start (\b, ^ contexts; 0xFF = start of unit)
 //   Pj : bucket k admits b as byte j of a match
-//   acc' = ((acc >> 6) | 0x3F000000) & E[b]
-// After feeding byte p, (acc & 0x3F) != 0  <=>  some bucket admits a match starting at p-3
+//   acc' = ((acc << 6) | 0x3F) & E[b]          (the shift is a multiply-add: acc * 64 + 63)
+// After feeding byte p, (acc & F_HIT) != 0  <=>  some bucket admits a match starting at p-3
 // (a 5-byte window: previous byte + first four match bytes).  No false negatives.
-static const uint32_t F_BITS = 6, F_MASK = 0x3Fu, F_TOP = 0x3F000000u, F_BUCKETS = 6;
+static const uint32_t F_BITS = 6, F_FILL = 0x3Fu, F_HIT = 0x3F000000u, F_BUCKETS = 6;
 static const uint32_t F_LOOKBACK = 4;   // bytes fed before the first owned position
 static const uint32_t F_START_OFF = 3;  // candidate start = fed position - 3
-CF_HD uint32_t filter_step(uint32_t acc, uint32_t e) { return ((acc >> F_BITS) | F_TOP) & e; }
+CF_HD uint32_t filter_step(uint32_t acc, uint32_t e) { return ((acc << F_BITS) | F_FILL) & e; }
 
 }  // namespace cf

@@ -43,7 +43,7 @@ int cfh_scan(cf_builder* b, const uint8_t* stream, uint64_t nbytes, const uint64
   // feed from LOOKBACK bytes before the stream to START_OFF bytes after (the last start is nbytes-1)
   for (int64_t p = -(int64_t)cf::F_LOOKBACK; p < (int64_t)nbytes + (int64_t)cf::F_START_OFF; ++p) {
     acc = cf::filter_step(acc, co.filter.E[s[p]]);
-    if (!(acc & cf::F_MASK)) continue;
+    if (!(acc & cf::F_HIT)) continue;
     int64_t start = p - (int64_t)cf::F_START_OFF;
     if (start < 0 || start >= (int64_t)nbytes) continue;
     if ((s[start] & 0xC0) == 0x80) continue;   // not a character boundary
@@ -82,7 +82,7 @@ int cfh_sub(cf_builder* b, uint32_t ordered_index, const uint8_t* unit, uint64_t
   uint32_t acc = 0;
   for (int64_t p = -(int64_t)cf::F_LOOKBACK; p < (int64_t)len + (int64_t)cf::F_START_OFF; ++p) {
     acc = cf::filter_step(acc, E[s[p]]);
-    if (!(acc & cf::F_MASK)) continue;
+    if (!(acc & cf::F_HIT)) continue;
     int64_t start = p - (int64_t)cf::F_START_OFF;
     if (start < 0 || start >= (int64_t)len) continue;
     if ((uint64_t)start < cur) continue;            // inside the previous match
