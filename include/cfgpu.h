@@ -107,6 +107,24 @@ int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, ui
 int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uint32_t n_sel, uint8_t* out_bytes,
                 uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed);
 
+/* ---------------- stage 4: toon_encoder (JSON text -> TOON text) ---------------- */
+/* Per unit (one JSON text): orjson.loads + toon.encode + "keep only if strictly smaller"
+ * (plugins/toon_encoder/toon_encoder.py:277-303, toon.py:82-565).  status[i] is one of CF_TOON_*;
+ * when CF_TOON_CONVERTED the TOON text is out_stream[offsets[i] .. offsets[i]+out_len[i]). */
+#define CF_TOON_CONVERTED 0
+#define CF_TOON_NOT_SMALLER 1   /* TOON would not be smaller: item keeps its JSON */
+#define CF_TOON_NOT_JSON 2      /* orjson.JSONDecodeError */
+#define CF_TOON_VALUE_ERROR 3   /* toon raises ValueError (un-encodable control character) */
+#define CF_TOON_ATTR_ERROR 4    /* toon raises AttributeError (unchecked .keys(), toon.py:400-404) */
+#define CF_TOON_UNSUPPORTED 6   /* beyond the device limits (nesting > 64, number > 3200 bits): caller must fail loudly */
+#define CF_TOON_REPORT_ERRORS 1u /* flags: keep encoding after the output outgrew the input so that VALUE/ATTR
+                                   errors are still reported (needed for skip_on_error=False) */
+/* device-resident (batch already uploaded); d_out has room for the batch's stream bytes */
+int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream);
+/* host buffers: upload + encode + download, synchronous */
+int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
+                 uint32_t n_units, uint8_t* out_stream, uint32_t* out_len, int32_t* status);
+
 /* number of kernels launched by this ctx so far (for bench.py's gpu_launches) */
 uint64_t cf_kernel_launches(const cf_ctx* ctx);
 

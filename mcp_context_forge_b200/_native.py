@@ -48,6 +48,8 @@ _SIGS = {
     "cf_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_scan_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "cf_sub_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, POINTER(c_uint64)]),
+    "cf_toon": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cf_toon_host": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "cf_kernel_launches": (c_uint64, [c_void_p]),
     "cf_scan_counters": (c_int, [c_void_p, c_void_p]),
     "cf_profile_begin": (c_int, [c_void_p, c_uint32]),

@@ -99,6 +99,26 @@ class GpuBatcher:
             i += len(g)
         return out
 
+    def toon_groups(self, groups: Sequence[Sequence[Unit]], report_errors: bool = True) -> List[List[tuple]]:
+        """JSON texts -> [(status, toon_bytes_or_None)] per text, one launch for all groups."""
+        flat: List[bytes] = [engine.encode_unit(u) for g in groups for u in g]
+        if not flat:
+            return [[] for _ in groups]
+        stream, offs = engine.pack_units(flat)
+        batch = self._ensure_batch(len(stream), len(flat))
+        status, texts = engine.toon_host(batch, stream, offs, report_errors)
+        self.launches += 1
+        self.units_seen += len(flat)
+        res = [(int(s), t) for s, t in zip(status, texts)]
+        out, i = [], 0
+        for g in groups:
+            out.append(res[i:i + len(g)])
+            i += len(g)
+        return out
+
+    async def toon(self, texts: Sequence[Unit], report_errors: bool = True) -> List[tuple]:
+        return await self._submit(None, "toon", 1 if report_errors else 0, texts)
+
     # ---- asyncio front: coalesce concurrent callers
     async def scan(self, prog: engine.Program, units: Sequence[Unit]) -> List[int]:
         return await self._submit(prog, "scan", 0, units)
@@ -111,7 +131,7 @@ class GpuBatcher:
             return []
         loop = asyncio.get_running_loop()
         fut: asyncio.Future = loop.create_future()
-        key = (id(prog), op, arg)
+        key = (id(prog) if prog is not None else 0, op, arg)
         if key not in self._pending:
             self._pending[key] = (prog, op, arg, [])
         self._pending[key][3].append((list(units), fut))
@@ -129,7 +149,12 @@ class GpuBatcher:
         for prog, op, arg, waiters in pending.values():
             try:
                 groups = [w[0] for w in waiters]
-                results = self.scan_groups(prog, groups) if op == "scan" else self.sub_groups(prog, groups, arg)
+                if op == "scan":
+                    results = self.scan_groups(prog, groups)
+                elif op == "sub":
+                    results = self.sub_groups(prog, groups, arg)
+                else:
+                    results = self.toon_groups(groups, bool(arg))
             except Exception as exc:  # surface the failure to every caller (no silent fallback)
                 for _, fut in waiters:
                     if not fut.done():

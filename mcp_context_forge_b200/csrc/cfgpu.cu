@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "cf_host.h"
+#include "json_toon.h"
 #include "scan_core.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -37,6 +38,8 @@ struct cf_ctx {
   uint32_t qphase = 0;
   uint64_t* d_queue = nullptr;      // candidate start positions
   uint32_t qcap = 1u << 20;
+  void* d_toon_scratch = nullptr;   // DOM node arrays for toon_kernel (grown on demand)
+  uint64_t toon_scratch_bytes = 0;
   // optional per-launch timing of the dominant kernel (bench.py roofline): event pairs
   std::vector<cudaEvent_t> prof_ev;
   uint32_t prof_used = 0;
@@ -638,6 +641,29 @@ __global__ void sub_compact_kernel(const uint8_t* __restrict__ stream, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
+// toon_encoder: JSON text -> TOON text, one unit per thread (csrc/json_toon.h holds the algorithm,
+// shared verbatim with the CPU unit tests).  Output for unit i goes to out + offsets[i]; a conversion
+// is only produced when it is strictly smaller than the input (plugins/toon_encoder/toon_encoder.py:295-303).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
+                                                   uint32_t n_units, cfj::JNode* __restrict__ nodes, uint8_t* __restrict__ out,
+                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t flags) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  const uint64_t b = offsets[u];
+  const uint64_t len64 = offsets[u + 1] - b - 1;
+  if (len64 > 0x7FFFFFFFull) { status[u] = cfj::TS_UNSUPPORTED; out_len[u] = 0; return; }
+  const uint32_t len = (uint32_t)len64;
+  cfj::JNode* my = nodes + (b >> 1) + 4ull * u;
+  cfj::Big big;
+  uint8_t digits[1240];
+  uint32_t ol = 0;
+  int st = cfj::toon_process(stream + b, len, my, len / 2 + 4, out + b, len ? len - 1 : 0, &ol, &big, digits, sizeof(digits), (flags & 1u) == 0);
+  status[u] = st;
+  out_len[u] = st == cfj::TS_CONVERTED ? ol : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -704,6 +730,7 @@ void cf_shutdown(cf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_qstate);
   cudaFree(ctx->d_queue);
+  cudaFree(ctx->d_toon_scratch);
   delete ctx;
 }
 
@@ -988,6 +1015,55 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
 #undef SUB_CUDA
   } while (0);
   cudaFree(d_scratch); cudaFree(d_sel); cudaFree(d_soff); cudaFree(d_bound); cudaFree(d_rec); cudaFree(d_ooff); cudaFree(d_out);
+  return rc;
+}
+
+int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
+  if (!ctx || !b || !b->n || !d_out || !d_out_len || !d_status) return CF_E_BADARG;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const uint64_t need = (b->nbytes / 2 + 4ull * b->n + 8) * sizeof(cfj::JNode);
+  if (need > ctx->toon_scratch_bytes) {
+    CF_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(ctx->d_toon_scratch);
+    ctx->d_toon_scratch = nullptr;
+    ctx->toon_scratch_bytes = 0;
+    CF_CUDA(ctx, cudaMalloc(&ctx->d_toon_scratch, need + need / 4));
+    ctx->toon_scratch_bytes = need + need / 4;
+  }
+  // CF_TOON_SMEM (experiment knob): dynamic shared memory used only as an occupancy limiter.  Measured:
+  // capping occupancy does not help — the kernel is bound by intra-warp divergence, not by L1 misses.
+  static int toon_smem = -1;
+  if (toon_smem < 0) {
+    toon_smem = getenv("CF_TOON_SMEM") ? atoi(getenv("CF_TOON_SMEM")) : 0;
+    CF_CUDA(ctx, cudaFuncSetAttribute(toon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, toon_smem > 48 * 1024 ? toon_smem : 48 * 1024));
+  }
+  toon_kernel<<<(b->n + 63) / 64, 64, (size_t)toon_smem, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfj::JNode*)ctx->d_toon_scratch, d_out, d_out_len, d_status, flags);
+  ctx->launches++;
+  CF_CUDA(ctx, cudaGetLastError());
+  return CF_OK;
+}
+
+int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
+                 uint32_t n_units, uint8_t* out_stream, uint32_t* out_len, int32_t* status) {
+  if (!out_stream || !out_len || !status) return CF_E_BADARG;
+  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  if (rc) return rc;
+  uint8_t* d_out = nullptr;
+  uint32_t* d_len = nullptr;
+  int32_t* d_st = nullptr;
+  do {
+#define T_CUDA(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = CF_E_CUDA; break; } }
+    T_CUDA(cudaMalloc(&d_out, stream_bytes + 16));
+    T_CUDA(cudaMalloc(&d_len, (size_t)n_units * 4));
+    T_CUDA(cudaMalloc(&d_st, (size_t)n_units * 4));
+    rc = cf_toon(ctx, b, flags, d_out, d_len, d_st, nullptr);
+    if (rc) break;
+    T_CUDA(cudaMemcpy(out_len, d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+    T_CUDA(cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+    T_CUDA(cudaMemcpy(out_stream, d_out, stream_bytes, cudaMemcpyDeviceToHost));
+#undef T_CUDA
+  } while (0);
+  cudaFree(d_out); cudaFree(d_len); cudaFree(d_st);
   return rc;
 }
 

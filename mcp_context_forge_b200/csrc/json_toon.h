@@ -1,0 +1,932 @@
+// json_toon.h — strict JSON -> flat DOM -> TOON text, one payload per (GPU) thread.
+// Plain sequential C++ that compiles for host and device (the CPU unit tests run the very same code
+// through tests/hostsim; the CUDA kernel toon_kernel in cfgpu.cu calls toon_process per unit).
+//
+// Reference semantics (paths relative to /root/reference):
+//   parse      orjson.loads                               plugins/toon_encoder/toon_encoder.py:281
+//   encode     toon.encode and helpers                    plugins/toon_encoder/toon.py:82-565
+//   decision   "only if strictly smaller in UTF-8 bytes"  plugins/toon_encoder/toon_encoder.py:295-303
+// Quirks reproduced on purpose are listed in SURVEY.md Appendix A-5/A-6 (hyphen anywhere forces
+// quotes, columnar header keys are never quoted, list-item indentation compounds, the unchecked
+// `.keys()` crash path, `$` admitting a final newline in the key regex, ...).
+#pragma once
+#include <stdint.h>
+
+#include "scan_core.h"
+#include "unicode_tables.h"
+
+namespace cfj {
+
+// ------------------------------------------------------------------------------------------------
+// Unicode tables (value lists generated from CPython; one copy per address space)
+// ------------------------------------------------------------------------------------------------
+static const uint32_t ND_LO_H[] = {CFU_ND_LO};
+static const uint32_t ND_HI_H[] = {CFU_ND_HI};
+static const uint32_t WS_LO_H[] = {CFU_WS_LO};
+static const uint32_t WS_HI_H[] = {CFU_WS_HI};
+#ifdef __CUDACC__
+static __device__ const uint32_t ND_LO_D[] = {CFU_ND_LO};
+static __device__ const uint32_t ND_HI_D[] = {CFU_ND_HI};
+static __device__ const uint32_t WS_LO_D[] = {CFU_WS_LO};
+static __device__ const uint32_t WS_HI_D[] = {CFU_WS_HI};
+#endif
+#ifdef __CUDA_ARCH__
+#define CFJ_TAB(name) name##_D
+#else
+#define CFJ_TAB(name) name##_H
+#endif
+
+CF_HD bool is_nd(uint32_t cp) {            // \d of a str pattern
+  if (cp < 0x80) return cp >= '0' && cp <= '9';
+  uint32_t lo = 0, hi = CFU_ND_COUNT;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (CFJ_TAB(ND_LO)[mid] <= cp) lo = mid; else hi = mid; }
+  return cp >= CFJ_TAB(ND_LO)[lo] && cp <= CFJ_TAB(ND_HI)[lo];
+}
+CF_HD bool is_pyspace(uint32_t cp) {       // str.isspace()
+  for (uint32_t i = 0; i < CFU_WS_COUNT; ++i) if (cp >= CFJ_TAB(WS_LO)[i] && cp <= CFJ_TAB(WS_HI)[i]) return true;
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DOM
+// ------------------------------------------------------------------------------------------------
+struct JNode { uint32_t t, off, len, next; };
+enum : uint32_t { J_NULL = 0, J_FALSE = 1, J_TRUE = 2, J_NUM = 3, J_STR = 4, J_ARR = 5, J_OBJ = 6, J_KEY = 7, J_TYPE = 0xF };
+enum : uint32_t { JF_ESC = 0x100, JF_NEG = 0x100, JF_FRAC = 0x200, JF_EXP = 0x400 };
+//   scalar   : off/len = raw text span (strings: between the quotes)
+//   container: off = index of first child (0 = none), len = number of children; for objects the
+//              children are J_KEY nodes, the value of key k is node k+1, keys are chained by .next
+//   array elements are chained by .next; an object value's .next holds the hash of its key
+static const int MAXD = 64;                // nesting depth handled on the device (deeper -> TS_UNSUPPORTED)
+
+enum : int { PARSE_OK = 0, PARSE_ERROR = 1, PARSE_UNSUPPORTED = 2 };
+
+CF_HD bool j_ws(uint32_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+CF_HD int hexv(uint32_t c) {
+  if (c >= '0' && c <= '9') return (int)c - '0';
+  c |= 0x20;
+  if (c >= 'a' && c <= 'f') return (int)c - 'a' + 10;
+  return -1;
+}
+
+// Validate one JSON string starting at the opening quote; returns false on any error.  On success
+// *pos is just past the closing quote.  Hash (FNV-1a) is over the DECODED UTF-8 bytes.
+CF_HD bool parse_string(const uint8_t* s, uint32_t n, uint32_t* pos, uint32_t* flags, uint32_t* hash) {
+  uint32_t p = *pos + 1, h = 2166136261u, fl = 0;
+  while (true) {
+    if (p >= n) return false;
+    uint32_t c = s[p];
+    if (c == '"') break;
+    if (c < 0x20) return false;
+    if (c == '\\') {
+      fl |= JF_ESC;
+      if (p + 1 >= n) return false;
+      uint32_t e = s[p + 1];
+      uint32_t cp;
+      switch (e) {
+        case '"': cp = '"'; break;   case '\\': cp = '\\'; break; case '/': cp = '/'; break;
+        case 'b': cp = 8; break;     case 'f': cp = 12; break;    case 'n': cp = 10; break;
+        case 'r': cp = 13; break;    case 't': cp = 9; break;
+        case 'u': {
+          if (p + 6 > n) return false;
+          int a = hexv(s[p + 2]), b = hexv(s[p + 3]), c2 = hexv(s[p + 4]), d = hexv(s[p + 5]);
+          if ((a | b | c2 | d) < 0) return false;
+          cp = (uint32_t)((a << 12) | (b << 8) | (c2 << 4) | d);
+          if (cp >= 0xDC00 && cp <= 0xDFFF) return false;                  // lone low surrogate
+          if (cp >= 0xD800 && cp <= 0xDBFF) {
+            if (p + 12 > n || s[p + 6] != '\\' || s[p + 7] != 'u') return false;
+            int a2 = hexv(s[p + 8]), b2 = hexv(s[p + 9]), c3 = hexv(s[p + 10]), d2 = hexv(s[p + 11]);
+            if ((a2 | b2 | c3 | d2) < 0) return false;
+            uint32_t lo = (uint32_t)((a2 << 12) | (b2 << 8) | (c3 << 4) | d2);
+            if (lo < 0xDC00 || lo > 0xDFFF) return false;
+            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+            p += 6;
+          }
+          p += 4;
+          break;
+        }
+        default: return false;
+      }
+      p += 2;
+      // hash the UTF-8 encoding of cp
+      if (cp < 0x80) { h = (h ^ cp) * 16777619u; }
+      else if (cp < 0x800) { h = (h ^ (0xC0 | (cp >> 6))) * 16777619u; h = (h ^ (0x80 | (cp & 63))) * 16777619u; }
+      else if (cp < 0x10000) { h = (h ^ (0xE0 | (cp >> 12))) * 16777619u; h = (h ^ (0x80 | ((cp >> 6) & 63))) * 16777619u; h = (h ^ (0x80 | (cp & 63))) * 16777619u; }
+      else { h = (h ^ (0xF0 | (cp >> 18))) * 16777619u; h = (h ^ (0x80 | ((cp >> 12) & 63))) * 16777619u; h = (h ^ (0x80 | ((cp >> 6) & 63))) * 16777619u; h = (h ^ (0x80 | (cp & 63))) * 16777619u; }
+      continue;
+    }
+    if (c < 0x80) { h = (h ^ c) * 16777619u; ++p; continue; }
+    // strict UTF-8
+    uint32_t need, mn;
+    if (c >= 0xC2 && c <= 0xDF) { need = 1; mn = 0x80; }
+    else if (c >= 0xE0 && c <= 0xEF) { need = 2; mn = 0x800; }
+    else if (c >= 0xF0 && c <= 0xF4) { need = 3; mn = 0x10000; }
+    else return false;
+    if (p + need >= n) return false;
+    uint32_t cp = c & (0x3F >> need);
+    h = (h ^ c) * 16777619u;
+    for (uint32_t k = 1; k <= need; ++k) {
+      uint32_t cc = s[p + k];
+      if ((cc & 0xC0) != 0x80) return false;
+      cp = (cp << 6) | (cc & 0x3F);
+      h = (h ^ cc) * 16777619u;
+    }
+    if (cp < mn || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+    p += need + 1;
+  }
+  *pos = p + 1;
+  *flags = fl;
+  *hash = h;
+  return true;
+}
+
+// Iterator over the decoded code points of a (validated) JSON string span.
+struct StrIter {
+  const uint8_t* p;
+  const uint8_t* e;
+  CF_HD bool done() const { return p >= e; }
+  CF_HD uint32_t next() {
+    uint32_t c = *p;
+    if (c == '\\') {
+      uint32_t x = p[1];
+      p += 2;
+      switch (x) {
+        case 'b': return 8; case 'f': return 12; case 'n': return 10; case 'r': return 13; case 't': return 9;
+        case 'u': {
+          uint32_t cp = (uint32_t)((hexv(p[0]) << 12) | (hexv(p[1]) << 8) | (hexv(p[2]) << 4) | hexv(p[3]));
+          p += 4;
+          if (cp >= 0xD800 && cp <= 0xDBFF) {
+            uint32_t lo = (uint32_t)((hexv(p[2]) << 12) | (hexv(p[3]) << 8) | (hexv(p[4]) << 4) | hexv(p[5]));
+            p += 6;
+            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+          }
+          return cp;
+        }
+        default: return x;   // " \ /
+      }
+    }
+    if (c < 0x80) { ++p; return c; }
+    uint32_t need = c >= 0xF0 ? 3u : c >= 0xE0 ? 2u : 1u;
+    uint32_t cp = c & (0x3F >> need);
+    for (uint32_t k = 1; k <= need; ++k) cp = (cp << 6) | (p[k] & 0x3F);
+    p += need + 1;
+    return cp;
+  }
+};
+
+CF_HD bool keys_equal(const uint8_t* s, const JNode& a, const JNode& b) {
+  if (!((a.t | b.t) & JF_ESC)) {
+    if (a.len != b.len) return false;
+    for (uint32_t i = 0; i < a.len; ++i) if (s[a.off + i] != s[b.off + i]) return false;
+    return true;
+  }
+  StrIter ia{s + a.off, s + a.off + a.len}, ib{s + b.off, s + b.off + b.len};
+  while (!ia.done() && !ib.done()) if (ia.next() != ib.next()) return false;
+  return ia.done() && ib.done();
+}
+
+// Parse `s[0..n)` (a whole JSON document, surrounding whitespace allowed) into nodes[0..cap).
+CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, uint32_t* out_count) {
+  uint32_t pos = 0, nn = 0;
+  uint32_t st_node[MAXD], st_last[MAXD];
+  int sp = 0;
+  enum { M_VALUE, M_KEY, M_AFTER } mode = M_VALUE;
+  while (pos < n && j_ws(s[pos])) ++pos;
+  while (true) {
+    if (mode == M_VALUE || mode == M_KEY) {
+      if (pos >= n) return PARSE_ERROR;
+      if (nn + 2 > cap) return PARSE_UNSUPPORTED;
+      uint32_t c = s[pos];
+      uint32_t idx = nn;
+      if (mode == M_KEY) {
+        if (c != '"') return PARSE_ERROR;
+        uint32_t fl, h, p0 = pos;
+        if (!parse_string(s, n, &pos, &fl, &h)) return PARSE_ERROR;
+        nodes[nn++] = JNode{J_KEY | fl, p0 + 1, pos - p0 - 2, 0};
+        uint32_t cidx = st_node[sp - 1];
+        if (st_last[sp - 1]) nodes[st_last[sp - 1]].next = idx; else nodes[cidx].off = idx;
+        st_last[sp - 1] = idx;
+        nodes[cidx].len++;
+        while (pos < n && j_ws(s[pos])) ++pos;
+        if (pos >= n || s[pos] != ':') return PARSE_ERROR;
+        ++pos;
+        while (pos < n && j_ws(s[pos])) ++pos;
+        // the value node follows immediately; remember the key hash in its .next afterwards
+        nodes[nn].next = h;   // provisional slot (overwritten fields t/off/len are set by the value parse)
+        mode = M_VALUE;
+        // mark: value belongs to an object member
+        st_last[sp - 1] |= 0x80000000u;
+        continue;
+      }
+      bool member = sp > 0 && (st_last[sp - 1] & 0x80000000u);
+      uint32_t keep_next = member ? nodes[nn].next : 0;
+      if (member) st_last[sp - 1] &= 0x7FFFFFFFu;
+      else if (sp > 0) {   // array element: chain
+        uint32_t cidx = st_node[sp - 1];
+        if (st_last[sp - 1]) nodes[st_last[sp - 1]].next = idx; else nodes[cidx].off = idx;
+        st_last[sp - 1] = idx;
+        nodes[cidx].len++;
+      }
+      if (c == '{' || c == '[') {
+        if (sp >= MAXD) return PARSE_UNSUPPORTED;
+        nodes[nn++] = JNode{c == '{' ? (uint32_t)J_OBJ : (uint32_t)J_ARR, 0, 0, keep_next};
+        st_node[sp] = idx; st_last[sp] = 0; ++sp;
+        ++pos;
+        while (pos < n && j_ws(s[pos])) ++pos;
+        if (pos < n && s[pos] == (c == '{' ? '}' : ']')) { ++pos; --sp; mode = M_AFTER; }
+        else mode = (c == '{') ? M_KEY : M_VALUE;
+        continue;
+      }
+      if (c == '"') {
+        uint32_t fl, h, p0 = pos;
+        if (!parse_string(s, n, &pos, &fl, &h)) return PARSE_ERROR;
+        nodes[nn++] = JNode{J_STR | fl, p0 + 1, pos - p0 - 2, keep_next};
+      } else if (c == '-' || (c >= '0' && c <= '9')) {
+        uint32_t p0 = pos, fl = 0;
+        if (c == '-') { fl |= JF_NEG; ++pos; if (pos >= n) return PARSE_ERROR; }
+        if (s[pos] == '0') ++pos;
+        else if (s[pos] >= '1' && s[pos] <= '9') { while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos; }
+        else return PARSE_ERROR;
+        if (pos < n && s[pos] == '.') {
+          fl |= JF_FRAC; ++pos;
+          if (pos >= n || s[pos] < '0' || s[pos] > '9') return PARSE_ERROR;
+          while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos;
+        }
+        if (pos < n && (s[pos] == 'e' || s[pos] == 'E')) {
+          fl |= JF_EXP; ++pos;
+          if (pos < n && (s[pos] == '+' || s[pos] == '-')) ++pos;
+          if (pos >= n || s[pos] < '0' || s[pos] > '9') return PARSE_ERROR;
+          while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos;
+        }
+        nodes[nn++] = JNode{J_NUM | fl, p0, pos - p0, keep_next};
+      } else if (c == 't' && pos + 4 <= n && s[pos + 1] == 'r' && s[pos + 2] == 'u' && s[pos + 3] == 'e') {
+        nodes[nn++] = JNode{J_TRUE, pos, 4, keep_next}; pos += 4;
+      } else if (c == 'f' && pos + 5 <= n && s[pos + 1] == 'a' && s[pos + 2] == 'l' && s[pos + 3] == 's' && s[pos + 4] == 'e') {
+        nodes[nn++] = JNode{J_FALSE, pos, 5, keep_next}; pos += 5;
+      } else if (c == 'n' && pos + 4 <= n && s[pos + 1] == 'u' && s[pos + 2] == 'l' && s[pos + 3] == 'l') {
+        nodes[nn++] = JNode{J_NULL, pos, 4, keep_next}; pos += 4;
+      } else return PARSE_ERROR;
+      mode = M_AFTER;
+      continue;
+    }
+    // M_AFTER: a value has just been completed
+    while (pos < n && j_ws(s[pos])) ++pos;
+    if (sp == 0) {
+      if (pos != n) return PARSE_ERROR;
+      *out_count = nn;
+      return PARSE_OK;
+    }
+    if (pos >= n) return PARSE_ERROR;
+    uint32_t cidx = st_node[sp - 1];
+    bool is_obj = (nodes[cidx].t & J_TYPE) == J_OBJ;
+    uint32_t c = s[pos];
+    if (c == ',') {
+      ++pos;
+      while (pos < n && j_ws(s[pos])) ++pos;
+      mode = is_obj ? M_KEY : M_VALUE;
+      continue;
+    }
+    if (c != (is_obj ? '}' : ']')) return PARSE_ERROR;
+    ++pos;
+    --sp;
+    if (is_obj && nodes[cidx].len > 1) {
+      // duplicate keys: the last value wins, the first position stays (Python dict / orjson)
+      uint32_t prev = nodes[cidx].off;
+      for (uint32_t k = nodes[prev].next; k;) {
+        uint32_t nxt = nodes[k].next;
+        bool dup = false;
+        for (uint32_t i = nodes[cidx].off; i != k; i = nodes[i].next)
+          if (nodes[i + 1].next == nodes[k + 1].next && keys_equal(s, nodes[i], nodes[k])) {
+            uint32_t hsh = nodes[i + 1].next;
+            nodes[i + 1] = nodes[k + 1];
+            nodes[i + 1].next = hsh;
+            dup = true;
+            break;
+          }
+        if (dup) { nodes[prev].next = nxt; nodes[cidx].len--; }
+        else prev = k;
+        k = nxt;
+      }
+    }
+    mode = M_AFTER;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact decimal <-> binary64 helpers (big integers; only used when the cheap text path cannot
+// decide: more than 15 significant digits, exponents, integers beyond 64 bits)
+// ------------------------------------------------------------------------------------------------
+static const int BIGN = 100;   // 3200 bits
+struct Big {
+  uint32_t n;
+  uint32_t w[BIGN];
+  CF_HD void set(uint32_t v) { n = v ? 1 : 0; w[0] = v; }
+  CF_HD bool zero() const { return n == 0; }
+  CF_HD bool mul_add(uint32_t m, uint32_t a) {   // this = this*m + a; false on overflow
+    uint64_t c = a;
+    for (uint32_t i = 0; i < n; ++i) { uint64_t t = (uint64_t)w[i] * m + c; w[i] = (uint32_t)t; c = t >> 32; }
+    if (c) { if (n >= BIGN) return false; w[n++] = (uint32_t)c; }
+    return true;
+  }
+  CF_HD uint32_t div_small(uint32_t d) {         // this /= d; returns remainder
+    uint64_t r = 0;
+    for (uint32_t i = n; i-- > 0;) { uint64_t t = (r << 32) | w[i]; w[i] = (uint32_t)(t / d); r = t % d; }
+    while (n && w[n - 1] == 0) --n;
+    return (uint32_t)r;
+  }
+  CF_HD bool shl(uint32_t bits) {
+    uint32_t ws = bits >> 5, bs = bits & 31;
+    if (n == 0) return true;
+    if (n + ws + 1 > BIGN) return false;
+    for (uint32_t i = n; i-- > 0;) w[i + ws] = w[i];
+    for (uint32_t i = 0; i < ws; ++i) w[i] = 0;
+    n += ws;
+    if (bs) {
+      uint32_t c = 0;
+      for (uint32_t i = ws; i < n; ++i) { uint32_t t = w[i]; w[i] = (t << bs) | c; c = t >> (32 - bs); }
+      if (c) w[n++] = c;
+    }
+    return true;
+  }
+  CF_HD uint32_t bitlen() const {
+    if (!n) return 0;
+    uint32_t t = w[n - 1], b = 0;
+    while (t) { ++b; t >>= 1; }
+    return (n - 1) * 32 + b;
+  }
+  CF_HD uint32_t bit(uint32_t i) const { return (i >> 5) < n ? (w[i >> 5] >> (i & 31)) & 1u : 0u; }
+  CF_HD bool any_below(uint32_t i) const {       // any set bit strictly below position i
+    uint32_t ws = i >> 5;
+    for (uint32_t k = 0; k < ws && k < n; ++k) if (w[k]) return true;
+    if (ws < n && (i & 31)) return (w[ws] & ((1u << (i & 31)) - 1)) != 0;
+    return false;
+  }
+};
+
+// A binary64 as sign, 53-bit integer mantissa m (0 or 2^52 <= m < 2^53 for normals) and exponent e: m * 2^e.
+struct Dbl { bool neg; bool inf; uint64_t m; int e; };
+
+// Correctly rounded (nearest-even) conversion of the decimal text to binary64.  Returns false when
+// the text needs more capacity than the big-integer workspace offers.
+CF_HD bool dec_to_double(const uint8_t* t, uint32_t len, Dbl* out, Big* X) {
+  uint32_t p = 0;
+  out->neg = false; out->inf = false; out->m = 0; out->e = 0;
+  if (p < len && t[p] == '-') { out->neg = true; ++p; }
+  X->set(0);
+  long long e10 = 0;
+  bool seen_dot = false, any = false;
+  for (; p < len; ++p) {
+    uint32_t c = t[p];
+    if (c == '.') { seen_dot = true; continue; }
+    if (c == 'e' || c == 'E') break;
+    if (!any && c == '0') { if (seen_dot) --e10; continue; }   // leading zeros carry no information
+    any = true;
+    if (!X->mul_add(10, c - '0')) return false;
+    if (seen_dot) --e10;
+  }
+  if (p < len) {   // exponent
+    ++p;
+    bool en = false;
+    if (p < len && (t[p] == '+' || t[p] == '-')) { en = t[p] == '-'; ++p; }
+    long long ex = 0;
+    for (; p < len; ++p) { if (ex < 100000) ex = ex * 10 + (t[p] - '0'); }
+    e10 += en ? -ex : ex;
+  }
+  if (X->zero()) return true;                                   // +-0
+  uint32_t nd10 = (uint32_t)((X->bitlen() * 1233) >> 12) + 1;   // ~ decimal digits of X
+  if (e10 + (long long)nd10 > 330) { out->inf = true; return true; }
+  if (e10 + (long long)nd10 < -345) return true;                // underflows to zero
+  int bin_e = 0;        // value = X * 2^bin_e (+ sticky)
+  bool sticky = false;
+  if (e10 >= 0) {
+    for (long long i = 0; i < e10; ++i) if (!X->mul_add(10, 0)) return false;
+  } else {
+    long long q = -e10;
+    uint32_t want = 64 + (uint32_t)((q * 3402) >> 10) + 2;      // bits so that the quotient keeps >= 64 bits
+    uint32_t have = X->bitlen();
+    uint32_t s = want > have ? want - have : 0;
+    if (!X->shl(s)) return false;
+    bin_e = -(int)s;
+    while (q >= 9) { if (X->div_small(1000000000u)) sticky = true; q -= 9; }
+    uint32_t d = 1;
+    for (; q > 0; --q) d *= 10;
+    if (d > 1 && X->div_small(d)) sticky = true;
+  }
+  // round X * 2^bin_e to 53 bits (or fewer for subnormals)
+  int L = (int)X->bitlen();
+  int drop = L - 53;
+  int e = bin_e + drop;                     // exponent of the kept integer mantissa
+  if (e < -1074) { drop += (-1074 - e); e = -1074; }
+  uint64_t m = 0;
+  if (drop <= 0) {
+    for (int i = L - 1; i >= 0; --i) m = (m << 1) | X->bit((uint32_t)i);
+    m <<= (uint32_t)(-drop);
+  } else {
+    if (drop > L) { m = 0; sticky = sticky || !X->zero(); }
+    else for (int i = L - 1; i >= drop; --i) m = (m << 1) | X->bit((uint32_t)i);
+    bool half = drop <= L && X->bit((uint32_t)(drop - 1));
+    bool rest = sticky || X->any_below((uint32_t)(drop - 1));
+    if (drop > L) { half = false; }
+    if (half && (rest || (m & 1))) ++m;
+    if (m == (1ull << 53)) { m >>= 1; ++e; }
+  }
+  if (m == 0) return true;
+  // normalise: value = m * 2^e ; overflow check
+  int top = 0; { uint64_t tt = m; while (tt) { ++top; tt >>= 1; } }
+  if (e + top > 1024) { out->inf = true; return true; }
+  out->m = m;
+  out->e = e;
+  return true;
+}
+
+// Decimal digits of a big integer, most significant first, into buf; returns count (0 for zero).
+CF_HD uint32_t big_to_digits(Big* X, uint8_t* buf, uint32_t cap) {
+  // generate 9 digits at a time from the least significant end, then reverse
+  uint32_t n = 0;
+  while (!X->zero()) {
+    uint32_t r = X->div_small(1000000000u);
+    for (int k = 0; k < 9; ++k) {
+      if (n >= cap) return 0xFFFFFFFFu;
+      buf[n++] = (uint8_t)('0' + r % 10);
+      r /= 10;
+      if (X->zero() && r == 0) break;
+    }
+  }
+  for (uint32_t i = 0; i < n / 2; ++i) { uint8_t t = buf[i]; buf[i] = buf[n - 1 - i]; buf[n - 1 - i] = t; }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TOON emitter
+// ------------------------------------------------------------------------------------------------
+enum : int {
+  TS_CONVERTED = 0, TS_NOT_SMALLER = 1, TS_NOT_JSON = 2, TS_VALUE_ERROR = 3 /* control character */,
+  TS_ATTR_ERROR = 4 /* the reference's unchecked .keys() */, TS_UNSUPPORTED = 6
+};
+
+struct Out {
+  uint8_t* p;
+  uint32_t n, cap;
+  bool over;
+  CF_HD void put(uint32_t c) { if (n < cap) p[n++] = (uint8_t)c; else over = true; }
+  CF_HD void puts(const char* z) { while (*z) put((uint8_t)*z++); }
+  CF_HD void spaces(uint32_t k) { for (uint32_t i = 0; i < k; ++i) put(' '); }
+  CF_HD void put_cp(uint32_t cp) {
+    if (cp < 0x80) put(cp);
+    else if (cp < 0x800) { put(0xC0 | (cp >> 6)); put(0x80 | (cp & 63)); }
+    else if (cp < 0x10000) { put(0xE0 | (cp >> 12)); put(0x80 | ((cp >> 6) & 63)); put(0x80 | (cp & 63)); }
+    else { put(0xF0 | (cp >> 18)); put(0x80 | ((cp >> 12) & 63)); put(0x80 | ((cp >> 6) & 63)); put(0x80 | (cp & 63)); }
+  }
+  CF_HD void put_uint(uint32_t v) {
+    uint8_t b[10]; int k = 0;
+    do { b[k++] = (uint8_t)('0' + v % 10); v /= 10; } while (v);
+    while (k) put(b[--k]);
+  }
+};
+
+struct Ctx {
+  const uint8_t* s;
+  const JNode* nodes;
+  Out out;
+  int err;          // 0 or TS_VALUE_ERROR / TS_ATTR_ERROR / TS_UNSUPPORTED
+  bool started;     // a line has been opened already (next line needs a '\n' first)
+  bool stop_on_over; // give up as soon as the output cannot be smaller (errors then go unreported: fine when
+                    // the caller treats encode errors and "not smaller" alike, i.e. skip_on_error=True)
+  Big* big;         // workspace for the exact number path
+  uint8_t* digits;  // decimal digit workspace
+  uint32_t digits_cap;
+};
+
+CF_HD void newline(Ctx& c, uint32_t pre) {
+  if (c.started) c.out.put('\n');
+  c.started = true;
+  c.out.spaces(pre);
+}
+
+CF_HD bool is_simple(uint32_t t) { uint32_t k = t & J_TYPE; return k != J_ARR && k != J_OBJ; }
+
+// string value -> TOON (quote only when the reference's _needs_quotes says so)
+CF_HD void emit_string(Ctx& c, const JNode& nd, bool force_quote) {
+  const uint8_t* b = c.s + nd.off;
+  const uint8_t* e = b + nd.len;
+  bool q = force_quote;
+  if (!q) {
+    if (nd.len == 0) q = true;
+    else {
+      // one pass over the decoded characters
+      StrIter it{b, e};
+      uint32_t first = 0, last = 0, count = 0;
+      int st = 0;                 // number-like automaton (see toon.py:54); -1 = failed
+      bool lead0 = true;          // ^0\d+$
+      bool special = false, ctrl = false;
+      while (!it.done()) {
+        uint32_t cp = it.next();
+        if (count == 0) first = cp;
+        last = cp;
+        if (cp < 32) ctrl = true;
+        if (cp == '\n' || cp == '\r' || cp == '\t' || cp == ',' || cp == ':' || cp == '[' || cp == ']' || cp == '{' || cp == '}' || cp == '"' || cp == '\\' || cp == '-') special = true;
+        bool d = is_nd(cp);
+        if (count == 0) lead0 = (cp == '0'); else lead0 = lead0 && d;
+        switch (st) {
+          case 0: st = (cp == '0') ? 1 : (cp >= '1' && cp <= '9') ? 2 : -1; break;
+          case 1: st = (cp == '.') ? 3 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
+          case 2: st = d ? 2 : (cp == '.') ? 3 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
+          case 3: st = d ? 4 : -1; break;
+          case 4: st = d ? 4 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
+          case 5: st = (cp == '+') ? 6 : d ? 7 : -1; break;   // '-' is handled by `special`
+          case 6: st = d ? 7 : -1; break;
+          case 7: st = d ? 7 : -1; break;
+          default: break;
+        }
+        ++count;
+      }
+      bool numlike = (st == 1 || st == 2 || st == 4 || st == 7);
+      bool reserved = false;
+      if (!(nd.t & JF_ESC)) {
+        if (nd.len == 4 && b[0] == 'n' && b[1] == 'u' && b[2] == 'l' && b[3] == 'l') reserved = true;
+        if (nd.len == 4 && b[0] == 't' && b[1] == 'r' && b[2] == 'u' && b[3] == 'e') reserved = true;
+        if (nd.len == 5 && b[0] == 'f' && b[1] == 'a' && b[2] == 'l' && b[3] == 's' && b[4] == 'e') reserved = true;
+      } else if (count == 4 || count == 5) {
+        StrIter r{b, e};
+        const char* w1 = "null"; const char* w2 = "true"; const char* w3 = "false";
+        bool m1 = count == 4, m2 = count == 4, m3 = count == 5;
+        for (uint32_t i = 0; !r.done(); ++i) { uint32_t cp = r.next(); if (m1 && cp != (uint32_t)w1[i]) m1 = false; if (m2 && cp != (uint32_t)w2[i]) m2 = false; if (m3 && cp != (uint32_t)w3[i]) m3 = false; }
+        reserved = m1 || m2 || m3;
+      }
+      q = reserved || special || numlike || (lead0 && count >= 2) || is_pyspace(first) || is_pyspace(last) || ctrl;
+    }
+  }
+  StrIter it{b, e};
+  if (!q) { while (!it.done()) c.out.put_cp(it.next()); return; }
+  c.out.put('"');
+  while (!it.done()) {
+    uint32_t cp = it.next();
+    if (cp == '\\') { c.out.put('\\'); c.out.put('\\'); }
+    else if (cp == '"') { c.out.put('\\'); c.out.put('"'); }
+    else if (cp == '\n') { c.out.put('\\'); c.out.put('n'); }
+    else if (cp == '\r') { c.out.put('\\'); c.out.put('r'); }
+    else if (cp == '\t') { c.out.put('\\'); c.out.put('t'); }
+    else if (cp < 32) { c.err = TS_VALUE_ERROR; return; }
+    else c.out.put_cp(cp);
+  }
+  c.out.put('"');
+}
+
+// object key: unquoted iff ^[A-Za-z_][A-Za-z0-9_.]*$ (where `$` admits one final "\n") and not reserved
+CF_HD void emit_key(Ctx& c, const JNode& k, bool raw) {
+  const uint8_t* b = c.s + k.off;
+  const uint8_t* e = b + k.len;
+  if (raw) { StrIter it{b, e}; while (!it.done()) c.out.put_cp(it.next()); return; }
+  bool ok = k.len > 0;
+  uint32_t count = 0;
+  bool r1 = true, r2 = true, r3 = true;
+  const char* w1 = "null"; const char* w2 = "true"; const char* w3 = "false";
+  {
+    StrIter it{b, e};
+    bool ended_nl = false;
+    while (!it.done()) {
+      uint32_t cp = it.next();
+      if (ended_nl) ok = false;                       // something after the newline
+      bool al = (cp >= 'A' && cp <= 'Z') || (cp >= 'a' && cp <= 'z') || cp == '_';
+      if (count == 0) { if (!al) ok = false; }
+      else if (!(al || (cp >= '0' && cp <= '9') || cp == '.')) { if (cp == '\n') ended_nl = true; else ok = false; }
+      if (count >= 4 || cp != (uint32_t)w1[count]) r1 = false;
+      if (count >= 4 || cp != (uint32_t)w2[count]) r2 = false;
+      if (count >= 5 || cp != (uint32_t)w3[count]) r3 = false;
+      ++count;
+    }
+  }
+  bool reserved = (r1 && count == 4) || (r2 && count == 4) || (r3 && count == 5);
+  if (ok && !reserved) { StrIter it{b, e}; while (!it.done()) c.out.put_cp(it.next()); return; }
+  JNode tmp = k;
+  emit_string(c, tmp, true);
+}
+
+// Python's float formatting as used by toon._encode_float, from the exact binary value.
+CF_HD void emit_double(Ctx& c, const Dbl& d) {
+  if (d.m == 0) { c.out.put('0'); return; }                       // +-0 -> "0"
+  // is it an integer?
+  bool integral = d.e >= 0;
+  if (!integral && -d.e < 64) integral = (d.m & ((1ull << (-d.e)) - 1)) == 0;
+  Big* X = c.big;
+  if (integral) {
+    uint64_t m = d.e >= 0 ? d.m : d.m >> (-d.e);
+    X->n = 0; X->w[0] = (uint32_t)m; X->w[1] = (uint32_t)(m >> 32);
+    X->n = X->w[1] ? 2 : (X->w[0] ? 1 : 0);
+    if (d.e > 0 && !X->shl((uint32_t)d.e)) { c.err = TS_UNSUPPORTED; return; }
+    uint32_t nd = big_to_digits(X, c.digits, c.digits_cap);
+    if (nd == 0xFFFFFFFFu) { c.err = TS_UNSUPPORTED; return; }
+    if (d.neg) c.out.put('-');
+    for (uint32_t i = 0; i < nd; ++i) c.out.put(c.digits[i]);
+    return;
+  }
+  // value = m / 2^k = (m * 5^k) / 10^k, k = -e > 0: exact decimal expansion with k fractional digits
+  uint32_t k = (uint32_t)(-d.e);
+  X->n = 0; X->w[0] = (uint32_t)d.m; X->w[1] = (uint32_t)(d.m >> 32);
+  X->n = X->w[1] ? 2 : 1;
+  for (uint32_t i = 0; i < k;) {
+    uint32_t step = k - i >= 13 ? 13 : k - i;
+    uint32_t mul = 1;
+    for (uint32_t j = 0; j < step; ++j) mul *= 5;
+    if (!X->mul_add(mul, 0)) { c.err = TS_UNSUPPORTED; return; }
+    i += step;
+  }
+  uint32_t nd = big_to_digits(X, c.digits, c.digits_cap - 2);
+  if (nd == 0xFFFFFFFFu) { c.err = TS_UNSUPPORTED; return; }
+  uint8_t* D = c.digits;                       // N = D[0..nd), value = N * 10^-k  (k >= 1)
+  int exp10 = (int)nd - (int)k - 1;            // decimal exponent of the leading digit
+  // ---- "%.15g": 15 significant digits, round-half-even on the exact value
+  uint8_t sig[18];
+  uint32_t ns = nd < 15 ? nd : 15;
+  for (uint32_t i = 0; i < ns; ++i) sig[i] = D[i];
+  int e15 = exp10;
+  if (nd > 15) {
+    bool up = false;
+    if (D[15] > '5') up = true;
+    else if (D[15] == '5') {
+      bool rest = false;
+      for (uint32_t i = 16; i < nd; ++i) if (D[i] != '0') { rest = true; break; }
+      up = rest || ((D[14] - '0') & 1);
+    }
+    if (up) {
+      int i = 14;
+      while (i >= 0 && sig[i] == '9') { sig[i] = '0'; --i; }
+      if (i >= 0) sig[i]++; else { for (int j = 14; j > 0; --j) sig[j] = sig[j - 1]; sig[0] = '1'; ++e15; }
+    }
+  }
+  if (e15 >= -4 && e15 < 15) {
+    // fixed notation; %g strips trailing zeros
+    uint32_t nsig = ns;
+    while (nsig > 1 && sig[nsig - 1] == '0') --nsig;
+    if (d.neg) c.out.put('-');
+    if (e15 >= 0) {
+      for (int i = 0; i <= e15; ++i) c.out.put(i < (int)nsig ? sig[i] : '0');
+      if ((int)nsig > e15 + 1) { c.out.put('.'); for (uint32_t i = (uint32_t)e15 + 1; i < nsig; ++i) c.out.put(sig[i]); }
+    } else {
+      c.out.put('0'); c.out.put('.');
+      for (int i = 0; i < -e15 - 1; ++i) c.out.put('0');
+      for (uint32_t i = 0; i < nsig; ++i) c.out.put(sig[i]);
+    }
+    return;
+  }
+  // ---- %g would use an exponent: the reference falls back to "%.15f", strips zeros, then a final '.'
+  int ni = (int)nd - (int)k;                   // digits before the decimal point (<= 0: the integer part is 0)
+  // fractional digit j (0-based) is D[ni + j] when ni + j >= 0, else '0'
+  uint8_t f[16];
+  for (int j = 0; j < 15; ++j) { int idx = ni + j; f[j] = (j < (int)k && idx >= 0) ? D[idx] : (uint8_t)'0'; }
+  bool carry = false;
+  if (k > 15) {
+    int idx16 = ni + 15;
+    uint8_t d16 = idx16 >= 0 ? D[idx16] : (uint8_t)'0';
+    bool up = false;
+    if (d16 > '5') up = true;
+    else if (d16 == '5') {
+      bool rest = false;
+      for (int i = idx16 + 1; i < (int)nd; ++i) if (i >= 0 && D[i] != '0') { rest = true; break; }
+      up = rest || ((f[14] - '0') & 1);
+    }
+    if (up) {
+      int i = 14;
+      while (i >= 0 && f[i] == '9') { f[i] = '0'; --i; }
+      if (i >= 0) f[i]++; else carry = true;
+    }
+  }
+
+  bool int_grew = false;
+  if (carry) {                                   // propagate into the integer digits D[0..ni)
+    int i = ni - 1;
+    while (i >= 0 && D[i] == '9') { D[i] = '0'; --i; }
+    if (i >= 0) D[i]++; else int_grew = true;
+  }
+  int nf = 15;
+  while (nf > 0 && f[nf - 1] == '0') --nf;
+  if (d.neg) c.out.put('-');
+  if (int_grew) c.out.put('1');
+  if (ni > 0) { for (int i = 0; i < ni; ++i) c.out.put(D[i]); }
+  else if (!int_grew) c.out.put('0');
+  if (nf) { c.out.put('.'); for (int i = 0; i < nf; ++i) c.out.put(f[i]); }
+}
+
+CF_HD void emit_number(Ctx& c, const JNode& nd) {
+  const uint8_t* t = c.s + nd.off;
+  uint32_t len = nd.len;
+  bool neg = (nd.t & JF_NEG) != 0;
+  const uint8_t* dg = t + (neg ? 1 : 0);
+  uint32_t dl = len - (neg ? 1 : 0);
+  if (!(nd.t & (JF_FRAC | JF_EXP))) {
+    // integer literal: Python int when it fits i64 / u64 (orjson), else a float
+    bool fits = dl < 19;
+    if (!fits && dl <= 20) {
+      const char* lim = neg ? "9223372036854775808" : "18446744073709551615";
+      uint32_t ll = neg ? 19 : 20;
+      if (dl < ll) fits = true;
+      else if (dl == ll) { fits = true; for (uint32_t i = 0; i < ll; ++i) { if (dg[i] < (uint8_t)lim[i]) break; if (dg[i] > (uint8_t)lim[i]) { fits = false; break; } } }
+    }
+    if (fits) {
+      if (dl == 1 && dg[0] == '0') { c.out.put('0'); return; }     // "-0" -> int 0
+      for (uint32_t i = 0; i < len; ++i) c.out.put(t[i]);
+      return;
+    }
+  } else if (!(nd.t & JF_EXP)) {
+    // cheap exact path: [-]INT.FRAC with at most 15 significant digits — binary64 round-trips such
+    // decimals, so "%.15g" / str(int(x)) reproduce the text digits and no arithmetic is needed
+    uint32_t dot = 0;
+    while (dg[dot] != '.') ++dot;
+    uint32_t fe = dl;
+    while (fe > dot + 1 && dg[fe - 1] == '0') --fe;        // FRAC without trailing zeros
+    const uint32_t nfrac = fe - dot - 1;
+    const bool int_zero = (dot == 1 && dg[0] == '0');
+    uint32_t lead_fz = 0;
+    if (int_zero) while (lead_fz < nfrac && dg[dot + 1 + lead_fz] == '0') ++lead_fz;
+    const uint32_t sigd = int_zero ? nfrac - lead_fz : dot + nfrac;
+    const bool tiny_long = int_zero && lead_fz >= 4 && nfrac > 15;   // "%.15f" would have to round
+    if (sigd <= 15 && !tiny_long) {
+      if (nfrac == 0) {                                    // integral float -> str(int(x)); +-0.0 -> "0"
+        if (int_zero) { c.out.put('0'); return; }
+        if (neg) c.out.put('-');
+        for (uint32_t i = 0; i < dot; ++i) c.out.put(dg[i]);
+        return;
+      }
+      if (neg) c.out.put('-');
+      for (uint32_t i = 0; i < dot + 1 + nfrac; ++i) c.out.put(dg[i]);
+      return;
+    }
+  }
+  // exact path
+  Dbl d;
+  if (!dec_to_double(t, len, &d, c.big)) { c.err = TS_UNSUPPORTED; return; }
+  if (d.inf) { c.err = TS_NOT_JSON; return; }   // yyjson/orjson reject numbers that overflow to infinity
+  emit_double(c, d);
+}
+
+CF_HD void emit_prim(Ctx& c, uint32_t idx) {
+  const JNode& nd = c.nodes[idx];
+  switch (nd.t & J_TYPE) {
+    case J_NULL: c.out.puts("null"); break;
+    case J_TRUE: c.out.puts("true"); break;
+    case J_FALSE: c.out.puts("false"); break;
+    case J_NUM: emit_number(c, nd); break;
+    case J_STR: emit_string(c, nd, false); break;
+    default: break;
+  }
+}
+
+// find the value node of the member of object `obj` whose key equals key node `k` (0 if absent)
+CF_HD uint32_t find_member(const Ctx& c, uint32_t obj, uint32_t k) {
+  uint32_t h = c.nodes[k + 1].next;
+  for (uint32_t m = c.nodes[obj].off; m; m = c.nodes[m].next)
+    if (c.nodes[m + 1].next == h && keys_equal(c.s, c.nodes[m], c.nodes[k])) return m + 1;
+  return 0;
+}
+
+enum : int { COL_YES = 1, COL_NO = 0, COL_CRASH = -1 };
+// toon.py:456-511 called on `arr` (non-empty); `checked` = caller already verified all elements are dicts
+CF_HD int columnar_check(const Ctx& c, uint32_t arr) {
+  const JNode* N = c.nodes;
+  uint32_t first = N[arr].off;
+  if ((N[first].t & J_TYPE) != J_OBJ) return COL_CRASH;
+  if (N[first].len == 0) return COL_NO;
+  for (uint32_t x = N[first].next; x; x = N[x].next) {
+    if ((N[x].t & J_TYPE) != J_OBJ) return COL_CRASH;
+    if (N[x].len != N[first].len) return COL_NO;
+    for (uint32_t k = N[first].off; k; k = N[k].next) if (!find_member(c, x, k)) return COL_NO;
+  }
+  for (uint32_t x = first; x; x = N[x].next)
+    for (uint32_t k = N[x].off; k; k = N[k].next) if (!is_simple(N[k + 1].t)) return COL_NO;
+  return COL_YES;
+}
+
+// "[n]{k1,k2}:" then one row per element at `row_pre` spaces
+CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre) {
+  const JNode* N = c.nodes;
+  uint32_t first = N[arr].off;
+  c.out.put('['); c.out.put_uint(N[arr].len); c.out.put(']'); c.out.put('{');
+  bool f0 = true;
+  for (uint32_t k = N[first].off; k; k = N[k].next) { if (!f0) c.out.put(','); f0 = false; emit_key(c, N[k], true); }
+  c.out.put('}'); c.out.put(':');
+  for (uint32_t x = first; x && !c.err && !(c.out.over && c.stop_on_over); x = N[x].next) {
+    newline(c, row_pre);
+    bool f1 = true;
+    for (uint32_t k = N[first].off; k; k = N[k].next) {
+      if (!f1) c.out.put(',');
+      f1 = false;
+      emit_prim(c, find_member(c, x, k));
+    }
+  }
+}
+
+struct Frame { uint32_t kind, node, cur, pre, indent, i; };
+enum : uint32_t { FR_OBJ = 0, FR_ARR_ITEMS = 1, FR_LIST_ITEM = 2 };
+
+// Emit an array whose line start (indentation + optional key prefix) is already written.
+// Returns true when the array pushed a frame for its items (complex form).
+CF_HD bool begin_array(Ctx& c, uint32_t arr, uint32_t pre, uint32_t indent, Frame* st, int* sp) {
+  const JNode* N = c.nodes;
+  uint32_t n = N[arr].len;
+  if (n == 0) { c.out.puts("[0]:"); return false; }
+  bool all_obj = true, all_simple = true;
+  for (uint32_t x = N[arr].off; x; x = N[x].next) {
+    uint32_t k = N[x].t & J_TYPE;
+    if (k != J_OBJ) all_obj = false;
+    if (k == J_OBJ || k == J_ARR) all_simple = false;
+  }
+  if (all_obj && columnar_check(c, arr) == COL_YES) { emit_columnar(c, arr, pre + 2); return false; }
+  c.out.put('['); c.out.put_uint(n); c.out.put(']'); c.out.put(':');
+  if (all_simple) {
+    c.out.put(' ');
+    bool f0 = true;
+    for (uint32_t x = N[arr].off; x; x = N[x].next) { if (!f0) c.out.put(','); f0 = false; emit_prim(c, x); }
+    return false;
+  }
+  if (*sp >= MAXD) { c.err = TS_UNSUPPORTED; return false; }
+  st[(*sp)++] = Frame{FR_ARR_ITEMS, arr, N[arr].off, pre, indent, 0};
+  return true;
+}
+
+CF_HD void toon_emit(Ctx& c, uint32_t root) {
+  const JNode* N = c.nodes;
+  Frame st[MAXD];
+  int sp = 0;
+  uint32_t rk = N[root].t & J_TYPE;
+  if (rk != J_ARR && rk != J_OBJ) { emit_prim(c, root); return; }
+  if (rk == J_ARR) { c.started = true; begin_array(c, root, 0, 0, st, &sp); }
+  else { if (N[root].len == 0) return; st[sp++] = Frame{FR_OBJ, root, N[root].off, 0, 0, 0}; }
+  while (sp > 0 && !c.err && !(c.out.over && c.stop_on_over)) {
+    Frame& f = st[sp - 1];
+    if (f.cur == 0) { --sp; continue; }
+    if (f.kind == FR_OBJ) {                                   // toon.py:514-565
+      uint32_t k = f.cur, v = k + 1;
+      f.cur = N[k].next;
+      uint32_t pre = f.pre, indent = f.indent;
+      newline(c, pre);
+      emit_key(c, N[k], false);
+      uint32_t vt = N[v].t & J_TYPE;
+      if (vt == J_ARR) begin_array(c, v, pre, indent, st, &sp);
+      else if (vt == J_OBJ) {
+        c.out.put(':');
+        if (N[v].len) { if (sp >= MAXD) { c.err = TS_UNSUPPORTED; break; } st[sp++] = Frame{FR_OBJ, v, N[v].off, pre + 2, indent + 1, 0}; }
+      } else { c.out.put(':'); c.out.put(' '); emit_prim(c, v); }
+    } else if (f.kind == FR_ARR_ITEMS) {                      // toon.py:349-375
+      uint32_t x = f.cur;
+      f.cur = N[x].next;
+      uint32_t pre = f.pre, indent = f.indent, ci = 2 * (indent + 1);
+      uint32_t xt = N[x].t & J_TYPE;
+      if (xt == J_OBJ) {
+        if (N[x].len == 0) { newline(c, pre + ci); c.out.put('-'); }
+        else { if (sp >= MAXD) { c.err = TS_UNSUPPORTED; break; } st[sp++] = Frame{FR_LIST_ITEM, x, N[x].off, pre, indent + 1, 0}; }
+      } else if (xt == J_ARR) {
+        newline(c, pre + ci); c.out.put('-'); c.out.put(' ');
+        begin_array(c, x, pre + ci + 2, indent + 2, st, &sp);
+      } else { newline(c, pre + ci); c.out.put('-'); c.out.put(' '); emit_prim(c, x); }
+    } else {                                                  // FR_LIST_ITEM  toon.py:378-441
+      uint32_t k = f.cur, v = k + 1, i = f.i;
+      f.cur = N[k].next;
+      f.i = i + 1;
+      uint32_t pre = f.pre, indent = f.indent, ind = 2 * indent, fi = 2 * (indent + 1);
+      newline(c, pre + (i == 0 ? ind : fi));
+      if (i == 0) { c.out.put('-'); c.out.put(' '); }
+      emit_key(c, N[k], false);
+      uint32_t vt = N[v].t & J_TYPE;
+      if (vt == J_ARR && N[v].len) {
+        if (i == 0) {
+          int cc = columnar_check(c, v);
+          if (cc == COL_CRASH) { c.err = TS_ATTR_ERROR; break; }
+          if (cc == COL_YES) { emit_columnar(c, v, pre + fi + 2); continue; }
+        }
+        c.out.put(':');
+        newline(c, pre + fi + 2);
+        begin_array(c, v, pre + fi + 2, indent + 2, st, &sp);
+      } else if (vt == J_OBJ && N[v].len) {
+        c.out.put(':');
+        if (sp >= MAXD) { c.err = TS_UNSUPPORTED; break; }
+        st[sp++] = Frame{FR_OBJ, v, N[v].off, pre + fi + 2, indent + 2, 0};
+      } else {
+        c.out.put(':'); c.out.put(' ');
+        if (vt == J_ARR) c.out.puts("[0]:");
+        else if (vt != J_OBJ) emit_prim(c, v);
+      }
+    }
+  }
+}
+
+// Whole per-unit pipeline.  The product passes out_cap = n - 1: a conversion is only kept when it is
+// strictly smaller than the n input bytes, so a longer TOON text can be abandoned mid-way.  Returns a TS_* status; *out_len is valid for TS_CONVERTED.
+CF_HD int toon_process(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t node_cap, uint8_t* out, uint32_t out_cap,
+                       uint32_t* out_len, Big* big, uint8_t* digits, uint32_t digits_cap, bool stop_on_over) {
+  uint32_t count = 0;
+  int pr = json_parse(s, n, nodes, node_cap, &count);
+  if (pr == PARSE_ERROR) return TS_NOT_JSON;
+  if (pr == PARSE_UNSUPPORTED) return TS_UNSUPPORTED;
+  Ctx c;
+  c.s = s; c.nodes = nodes;
+  c.out.p = out; c.out.n = 0; c.out.cap = out_cap; c.out.over = false;
+  c.err = 0; c.started = false; c.stop_on_over = stop_on_over;
+  c.big = big; c.digits = digits; c.digits_cap = digits_cap;
+  toon_emit(c, 0);
+  if (c.err) return c.err;
+  if (c.out.over) return TS_NOT_SMALLER;
+  *out_len = c.out.n;
+  return TS_CONVERTED;
+}
+
+}  // namespace cfj

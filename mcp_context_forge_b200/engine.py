@@ -226,3 +226,28 @@ def sub_host(prog: Program, batch: Batch, unit_indices: Sequence[int]) -> List[b
         break
     raw = out.tobytes()
     return [raw[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+
+TOON_CONVERTED, TOON_NOT_SMALLER, TOON_NOT_JSON, TOON_VALUE_ERROR, TOON_ATTR_ERROR, TOON_UNSUPPORTED = 0, 1, 2, 3, 4, 6
+
+
+def toon_host(batch: Batch, stream, offsets: np.ndarray, report_errors: bool = True):
+    """cf_toon_host: every unit is one JSON text.  Returns (status int32[n], toon texts as bytes or
+    None per unit)."""
+    ctx = batch.ctx
+    n = len(offsets) - 1
+    nbytes = int(offsets[-1])
+    out = np.empty(max(nbytes, 1), dtype=np.uint8)
+    out_len = np.empty(n, dtype=np.uint32)
+    status = np.empty(n, dtype=np.int32)
+    sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+    with ctx.lock:
+        ctx.check(ctx.lib.cf_toon_host(ctx.h, batch.h, 1 if report_errors else 0, sp, nbytes, offsets.ctypes.data, n, out.ctypes.data, out_len.ctypes.data, status.ctypes.data), "cf_toon_host")
+    texts: List[Optional[bytes]] = []
+    for i in range(n):
+        if status[i] == TOON_CONVERTED:
+            o = int(offsets[i])
+            texts.append(out[o:o + int(out_len[i])].tobytes())
+        else:
+            texts.append(None)
+    return status, texts

@@ -1,0 +1,150 @@
+# -*- coding: utf-8 -*-
+"""GPU drop-in for /root/reference/plugins/toon_encoder/toon_encoder.py.
+
+Same class name, config keys, hook, result/metadata/stats shapes.  The per-item work of
+`_process_content_item` — orjson.loads, toon.encode, "keep only if strictly smaller"
+(reference :277-303) — runs on the GPU for all eligible items of all in-flight requests in one launch
+(toon_kernel, csrc/json_toon.h).  Tool filters, size gates, annotation handling and statistics are
+host logic identical to the reference (:221-235, :260-275, :305-326, :328-363).
+"""
+from __future__ import annotations
+
+import logging
+import time
+from typing import Any, Dict, List, Optional
+
+from .. import engine
+from ..batching import GpuBatcher
+from ..framework import Plugin, PluginConfig, PluginContext, ToolPostInvokePayload, ToolPostInvokeResult
+
+logger = logging.getLogger(__name__)
+
+
+class ToonEncoderPlugin(Plugin):
+    def __init__(self, config: PluginConfig) -> None:
+        super().__init__(config)
+        plugin_config = config.config or {}
+        self._min_size_bytes: int = plugin_config.get("min_size_bytes", 100)
+        self._max_size_bytes: int = plugin_config.get("max_size_bytes", 1024 * 1024)
+        self._exclude_tools: List[str] = plugin_config.get("exclude_tools", [])
+        self._include_tools: Optional[List[str]] = plugin_config.get("include_tools")
+        self._add_format_marker: bool = plugin_config.get("add_format_marker", True)
+        self._skip_on_error: bool = plugin_config.get("skip_on_error", True)
+        self._tools_processed = 0
+        self._tools_converted = 0
+        self._items_attempted = 0
+        self._items_converted = 0
+        self._total_bytes_saved = 0
+        self._batcher: Optional[GpuBatcher] = None
+
+    def _should_process_tool(self, tool_name: str) -> bool:
+        if self._include_tools is not None:
+            return tool_name in self._include_tools
+        return tool_name not in self._exclude_tools
+
+    def _eligible(self, item: Any) -> Optional[bytes]:
+        """UTF-8 bytes of the item's text when the reference would attempt a conversion (:246-275)."""
+        if not isinstance(item, dict):
+            return None
+        text = item.get("text", "")
+        if item.get("type") != "text" or not isinstance(text, str):
+            return None
+        try:
+            raw = text.encode("utf-8")
+        except UnicodeEncodeError:          # the reference's len(text.encode("utf-8")) raises here too
+            raise
+        if len(raw) < self._min_size_bytes or len(raw) > self._max_size_bytes:
+            return None
+        return raw
+
+    def _new_item(self, item: Dict[str, Any], toon_text: str) -> Dict[str, Any]:
+        """reference :305-324."""
+        new_item: Dict[str, Any] = {"type": "text", "text": toon_text}
+        existing = item.get("annotations", {})
+        if isinstance(existing, dict) and existing:
+            new_item["annotations"] = {**existing}
+        elif existing:
+            new_item["annotations"] = existing
+        if self._add_format_marker:
+            if "annotations" not in new_item:
+                new_item["annotations"] = {}
+            if isinstance(new_item["annotations"], dict):
+                new_item["annotations"]["format"] = "toon"
+        return new_item
+
+    async def tool_post_invoke(self, payload: ToolPostInvokePayload, _context: PluginContext) -> ToolPostInvokeResult:
+        start_time = time.monotonic()
+        tool_name = payload.name
+        if not self._should_process_tool(tool_name):
+            return ToolPostInvokeResult(continue_processing=True)
+        result = payload.result
+        if not isinstance(result, dict):
+            return ToolPostInvokeResult(continue_processing=True)
+        content = result.get("content", [])
+        if not content or not isinstance(content, list):
+            return ToolPostInvokeResult(continue_processing=True)
+
+        self._tools_processed += 1
+        raws = [self._eligible(item) for item in content]
+        idx = [i for i, r in enumerate(raws) if r is not None]
+        outcomes = {}
+        if idx:
+            if self._batcher is None:
+                self._batcher = GpuBatcher.get()
+            for i, oc in zip(idx, await self._batcher.toon([raws[i] for i in idx], report_errors=not self._skip_on_error)):
+                outcomes[i] = oc
+
+        new_content = []
+        modified = False
+        total_original = total_new = 0
+        for i, item in enumerate(content):
+            oc = outcomes.get(i)
+            if oc is None:
+                new_content.append(item)
+                continue
+            self._items_attempted += 1
+            status, toon_bytes = oc
+            if status == engine.TOON_NOT_JSON:     # counted as attempted, like the reference (:278-284)
+                new_content.append(item)
+            elif status == engine.TOON_CONVERTED:
+                new_content.append(self._new_item(item, toon_bytes.decode("utf-8")))
+                modified = True
+                self._items_converted += 1
+                total_original += len(raws[i])
+                total_new += len(toon_bytes)
+            elif status in (engine.TOON_VALUE_ERROR, engine.TOON_ATTR_ERROR):
+                if not self._skip_on_error:
+                    if status == engine.TOON_VALUE_ERROR:
+                        raise ValueError("Cannot encode control character in TOON")
+                    raise AttributeError("object has no attribute 'keys'")
+                logger.warning(f"ToonEncoder: Failed to encode '{tool_name}' to TOON")
+                new_content.append(item)
+            elif status == engine.TOON_NOT_SMALLER:
+                new_content.append(item)
+            else:  # TOON_UNSUPPORTED: outside the device limits — never guess, never fall back silently
+                raise RuntimeError(f"ToonEncoder(GPU): payload of tool '{tool_name}' exceeds the device encoder's limits (nesting > 64 or number > 3200 bits)")
+
+        if modified:
+            self._tools_converted += 1
+            bytes_saved = total_original - total_new
+            self._total_bytes_saved += bytes_saved
+            duration_ms = (time.monotonic() - start_time) * 1000
+            savings_pct = (bytes_saved / total_original * 100) if total_original > 0 else 0
+            new_result = {**result, "content": new_content}
+            return ToolPostInvokeResult(
+                modified_payload=ToolPostInvokePayload(name=tool_name, result=new_result),
+                metadata={"toon_encoded": True, "bytes_saved": bytes_saved, "savings_percent": round(savings_pct, 2), "conversion_time_ms": round(duration_ms, 2)},
+            )
+        return ToolPostInvokeResult(continue_processing=True)
+
+    def get_stats(self) -> Dict[str, Any]:
+        """reference :328-363."""
+        return {
+            "tools_processed": self._tools_processed,
+            "tools_converted": self._tools_converted,
+            "tool_conversion_rate": (self._tools_converted / self._tools_processed * 100 if self._tools_processed > 0 else 0.0),
+            "items_attempted": self._items_attempted,
+            "items_converted": self._items_converted,
+            "item_conversion_rate": (self._items_converted / self._items_attempted * 100 if self._items_attempted > 0 else 0.0),
+            "total_bytes_saved": self._total_bytes_saved,
+        }

@@ -15,7 +15,7 @@ SRCS = [
 
 
 def build(force=False):
-    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h")]
+    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h", "json_toon.h", "unicode_tables.h")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", SO] + SRCS)
@@ -108,3 +108,18 @@ class HostProgram:
             self.L.cf_builder_free(self.b)
         except Exception:
             pass
+
+
+TOON_STATUS = {0: "converted", 1: "not_smaller", 2: "not_json", 3: "value_error", 4: "attr_error", 6: "unsupported"}
+
+
+def toon_host(text: str, unlimited: bool = False):
+    """(status, toon_text_or_None) from the shared json_toon.h pipeline compiled for the CPU.
+    unlimited=True lifts the product's "strictly smaller" capacity so the encoder output itself can
+    be compared with the reference's toon.encode."""
+    b = text.encode("utf-8", "surrogatepass")
+    cap = len(b) * 6 + 4096 if unlimited else max(len(b) - 1, 0)
+    out = ctypes.create_string_buffer(max(cap, 1))
+    n = ctypes.c_uint32()
+    st = lib().cfh_toon(b, len(b), out, cap, ctypes.byref(n))
+    return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)

@@ -1,0 +1,98 @@
+"""GPU parity of the toon_encoder path (toon_kernel through cf_toon_host and the drop-in plugin)
+against vectors recorded from the reference's own toon.py / toon_encoder.py and against the oracle."""
+import asyncio
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mcp_context_forge_b200 import engine, synth
+from mcp_context_forge_b200 import framework as fw
+from mcp_context_forge_b200.batching import GpuBatcher
+from mcp_context_forge_b200.plugins.toon_encoder import ToonEncoderPlugin
+from oracle import toon_ref
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "toon.json")
+CTX = fw.PluginContext(global_context=fw.GlobalContext(request_id="t"))
+
+
+def run(coro):
+    return asyncio.new_event_loop().run_until_complete(coro)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD, encoding="utf-8") as f:
+        return json.load(f)
+
+
+def test_encode_cases_one_launch(gold):
+    texts = [c["json"] for c in gold["encode"]]
+    res = GpuBatcher.get().toon_groups([texts])[0]
+    n_conv = 0
+    for c, (st, got) in zip(gold["encode"], res):
+        size = len(c["json"].encode("utf-8"))
+        if "toon" in c:
+            exp = c["toon"] if len(c["toon"].encode("utf-8")) < size else None
+            assert (got.decode("utf-8") if st == engine.TOON_CONVERTED else None) == exp, c["json"][:200]
+            assert st in (engine.TOON_CONVERTED, engine.TOON_NOT_SMALLER)
+            n_conv += st == engine.TOON_CONVERTED
+        else:
+            assert st == (engine.TOON_ATTR_ERROR if c["error"] == "AttributeError" else engine.TOON_VALUE_ERROR), (c["json"][:200], st)
+    assert n_conv > 300
+
+
+def test_plugin_matches_reference_golden(gold):
+    for block in gold["plugin"]:
+        plug = ToonEncoderPlugin(fw.PluginConfig(name="toon", kind="x", hooks=["tool_post_invoke"], config=block["config"]))
+        for c in block["cases"]:
+            payload = fw.ToolPostInvokePayload(name="t", result=c["result"])
+            if "raises" in c:
+                with pytest.raises(Exception) as ei:
+                    run(plug.tool_post_invoke(payload, CTX))
+                assert type(ei.value).__name__ == c["raises"]
+                continue
+            r = run(plug.tool_post_invoke(payload, CTX))
+            if c["modified"] is None:
+                assert r.modified_payload is None and r.continue_processing
+            else:
+                assert r.modified_payload.result == c["modified"]
+                md = dict(r.metadata)
+                assert isinstance(md.pop("conversion_time_ms"), float)
+                assert md == c["metadata"]
+        r = run(plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result="str result"), CTX))
+        assert (r.modified_payload is not None) == block["non_dict_modified"]
+        if not any("raises" in c for c in block["cases"]):
+            assert plug.get_stats() == block["stats"]
+
+
+@pytest.mark.parametrize("shape,size,n", [("A", 2048, 512), ("A", 16384, 256), ("B", 16384, 128), ("A", 262144, 16), ("B", 262144, 8), ("C", 16384, 32)])
+def test_synthetic_payloads_vs_oracle(shape, size, n):
+    texts = [synth.payload(shape, size, seed=s) for s in range(n)]
+    if shape == "C":
+        texts = [json.dumps({"doc": t, "n": i}) for i, t in enumerate(texts)]
+    res = GpuBatcher.get().toon_groups([texts])[0]
+    conv = 0
+    for t, (st, got) in zip(texts, res):
+        exp = toon_ref.process_text(t, 0, 1 << 30)
+        assert (got.decode("utf-8") if st == engine.TOON_CONVERTED else None) == exp
+        conv += exp is not None
+    assert conv >= (n // 2 if shape == "A" else 0)   # nested config JSON (shape B) rarely shrinks: indentation compounds
+
+
+def test_concurrent_requests_are_coalesced():
+    plug = ToonEncoderPlugin(fw.PluginConfig(name="toon", kind="x", hooks=["tool_post_invoke"], config={"min_size_bytes": 10}))
+    texts = [synth.payload("A", 1500, seed=s) for s in range(64)]
+    b = GpuBatcher.get()
+    before = b.launches
+
+    async def many():
+        return await asyncio.gather(*[plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result={"content": [{"type": "text", "text": t}]}), CTX) for t in texts])
+
+    out = run(many())
+    assert b.launches - before == 1                     # 64 in-flight requests -> one packed stream, one launch
+    for t, r in zip(texts, out):
+        assert r.modified_payload.result["content"][0]["text"] == toon_ref.process_text(t, 10)
+        assert r.modified_payload.result["content"][0]["annotations"] == {"format": "toon"}

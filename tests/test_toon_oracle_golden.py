@@ -1,0 +1,66 @@
+"""Pins oracle/toon_ref.py against vectors recorded from the reference's own toon.py and
+toon_encoder.py (tests/golden/toon.json; inputs harvested from the reference's unit tests + fuzz)."""
+import json
+import os
+
+import pytest
+
+from oracle import toon_ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "toon.json")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD, encoding="utf-8") as f:
+        return json.load(f)
+
+
+def test_encode_matches_reference(gold):
+    n_err = 0
+    assert gold["n_harvested_from_reference_tests"] >= 80
+    for c in gold["encode"]:
+        obj = json.loads(c["json"])
+        if "toon" in c:
+            assert toon_ref.encode(obj) == c["toon"], c["json"][:200]
+        else:
+            with pytest.raises((ValueError, toon_ref.ToonCrash)):
+                toon_ref.encode(obj)
+            n_err += 1
+    assert len(gold["encode"]) > 800 and n_err > 10
+
+
+def test_helpers_match_reference(gold):
+    for s, exp in gold["helpers"]["needs_quotes"]:
+        assert toon_ref.needs_quotes(s) == exp, repr(s)
+    for s, exp in gold["helpers"]["encode_key"]:
+        assert toon_ref.enc_key(s) == exp, repr(s)
+    for r, exp in gold["helpers"]["encode_float"]:
+        assert toon_ref.fmt_float(float(r)) == exp, r
+
+
+def test_plugin_item_decision_matches_reference(gold):
+    n = conv = 0
+    for block in gold["plugin"]:
+        cfg = block["config"] or {}
+        if "exclude_tools" in cfg or "include_tools" in cfg:
+            assert all(c.get("modified") is None for c in block["cases"])
+            continue
+        for c in block["cases"]:
+            item = c["result"]["content"][0]
+            if "raises" in c:
+                with pytest.raises(Exception):
+                    toon_ref.process_text(item["text"], cfg.get("min_size_bytes", 100), cfg.get("max_size_bytes", 1 << 20), cfg.get("skip_on_error", True))
+                continue
+            got = toon_ref.process_text(item["text"], cfg.get("min_size_bytes", 100), cfg.get("max_size_bytes", 1 << 20), cfg.get("skip_on_error", True))
+            if c["modified"] is None:
+                assert got is None, item["text"][:100]
+            else:
+                new_item = c["modified"]["content"][0]
+                if got is None:
+                    assert new_item == item
+                else:
+                    assert new_item["text"] == got and new_item["type"] == "text"
+                    conv += 1
+            n += 1
+    assert n > 300 and conv > 50

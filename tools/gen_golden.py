@@ -255,6 +255,7 @@ def gen_toon():
             j = json.dumps(jsonable(obj), ensure_ascii=False)
         except (TypeError, ValueError):
             continue
+        obj = json.loads(j)          # what a JSON parser hands to encode(): lists, never tuples
         try:
             res = {"toon": toon.encode(obj)}
         except Exception as exc:  # AttributeError crash path (A-6 iv) / ValueError control chars

@@ -1,0 +1,30 @@
+"""Quick device-resident timing of toon_kernel (development aid)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from mcp_context_forge_b200 import engine, synth
+from mcp_context_forge_b200.batching import GpuBatcher
+
+b = GpuBatcher.get()
+lib = b.ctx.lib
+for shape, size, n in (("A", 16384, 16384), ("A", 2048, 65536), ("A", 262144, 1024), ("B", 16384, 16384)):
+    base = [synth.payload(shape, size, seed=s).encode() for s in range(64)]
+    texts = [base[i % 64] for i in range(n)]
+    stream, offs = engine.pack_units(texts)
+    batch = engine.Batch(b.ctx, len(stream), n)
+    batch.upload(stream, offs)
+    d_out = torch.empty(len(stream) + 16, dtype=torch.uint8, device="cuda")
+    d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_st = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        lib.cf_toon(b.ctx.h, batch.h, 0, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lib.cf_toon(b.ctx.h, batch.h, 0, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(shape, size, n, "kernel ms", round(ms, 3), "GB/s", round(len(stream) / ms / 1e6, 1), "payloads/s", int(n / ms * 1e3), "converted", int((d_st == 0).sum()))
