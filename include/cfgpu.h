@@ -107,6 +107,22 @@ int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, ui
 int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uint32_t n_sel, uint8_t* out_bytes,
                 uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed);
 
+/* ---------------- stage 3: request_logging_masking ---------------- */
+/* mask_sensitive_json_bytes(payload, max_depth) per unit (one JSON request body per unit):
+ * crates/request_logging_masking_native_extension/src/lib.rs:346-360.  Masked compact JSON of every
+ * unit with status CF_MASK_OK is returned back to back in out_bytes / out_offsets[n+1].
+ * status: CF_MASK_OK, CF_MASK_PARSE_ERROR (the crate raises ValueError), CF_MASK_UNSUPPORTED (beyond
+ * device limits: nesting > 64, number > 3200 bits — the caller must fail loudly). */
+#define CF_MASK_OK 0
+#define CF_MASK_PARSE_ERROR 2
+#define CF_MASK_UNSUPPORTED 6
+int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
+                 int max_depth, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, int32_t* status, uint64_t* out_needed);
+/* is_sensitive_key(key) for a batch of key names (lib.rs:122-187); sensitive[i] = 0/1.  Used by the
+ * object-level entry points mask_sensitive_data / mask_sensitive_headers (lib.rs:307-344). */
+int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
+                          uint32_t n_units, uint8_t* sensitive);
+
 /* ---------------- stage 4: toon_encoder (JSON text -> TOON text) ---------------- */
 /* Per unit (one JSON text): orjson.loads + toon.encode + "keep only if strictly smaller"
  * (plugins/toon_encoder/toon_encoder.py:277-303, toon.py:82-565).  status[i] is one of CF_TOON_*;

@@ -48,6 +48,8 @@ _SIGS = {
     "cf_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_scan_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "cf_sub_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, POINTER(c_uint64)]),
+    "cf_mask_host": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_int, c_void_p, c_uint64, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "cf_classify_keys_host": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "cf_toon": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_toon_host": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "cf_kernel_launches": (c_uint64, [c_void_p]),

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "cf_host.h"
+#include "json_mask.h"
 #include "json_toon.h"
 #include "scan_core.h"
 
@@ -664,6 +665,48 @@ __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ st
 }
 
 // ------------------------------------------------------------------------------------------------
+// request_logging_masking: mask_sensitive_json_bytes per unit (csrc/json_mask.h), one unit per thread,
+// plus a key classifier kernel for the object-level entry points of the drop-in module.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) mask_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
+                                                   cfj::JNode* __restrict__ nodes, uint32_t* __restrict__ idx, uint8_t* __restrict__ out,
+                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, int max_depth) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  const uint64_t b = offsets[u];
+  const uint64_t len64 = offsets[u + 1] - b - 1;
+  if (len64 > 0x30000000ull) { status[u] = cfm::MS_UNSUPPORTED; out_len[u] = 0; return; }
+  const uint32_t len = (uint32_t)len64;
+  cfj::JNode* my = nodes + (b >> 1) + 4ull * u;
+  uint32_t* myidx = idx + (b >> 1) + 4ull * u;
+  cfj::Big big;
+  uint8_t digits[1240];
+  cfm::NumWork w{&big, &big, digits, (uint32_t)sizeof(digits)};
+  uint32_t ol = 0;
+  int st = cfm::mask_process(stream + b, len, my, len / 2 + 4, myidx, len / 2 + 4, out + 5 * b + 32ull * u, 5 * len + 32, &ol, max_depth, w);
+  status[u] = st;
+  out_len[u] = st == cfm::MS_OK ? ol : 0;
+}
+
+__global__ void mask_compact_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ out_len,
+                                    const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out, uint32_t n_units) {
+  const uint32_t u = blockIdx.x;
+  if (u >= n_units) return;
+  const uint8_t* src = arena + 5 * offsets[u] + 32ull * u;
+  uint8_t* dst = out + out_off[u];
+  for (uint32_t i = threadIdx.x; i < out_len[u]; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void classify_keys_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
+                                     uint8_t* __restrict__ sensitive) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  const uint64_t b = offsets[u];
+  cfj::JNode k{cfj::J_KEY, 0, (uint32_t)(offsets[u + 1] - b - 1), 0};   // raw key text (no JSON escapes)
+  sensitive[u] = cfm::key_sensitive(stream + b, k) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -1065,6 +1108,73 @@ int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream
   } while (0);
   cudaFree(d_out); cudaFree(d_len); cudaFree(d_st);
   return rc;
+}
+
+int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
+                 int max_depth, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, int32_t* status, uint64_t* out_needed) {
+  if (!ctx || !b || !out_offsets || !status) return CF_E_BADARG;
+  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  if (rc) return rc;
+  const uint64_t nnodes = stream_bytes / 2 + 4ull * n_units + 8;
+  const uint64_t need = nnodes * sizeof(cfj::JNode);
+  if (need > ctx->toon_scratch_bytes) {
+    cudaFree(ctx->d_toon_scratch);
+    ctx->d_toon_scratch = nullptr;
+    ctx->toon_scratch_bytes = 0;
+    CF_CUDA(ctx, cudaMalloc(&ctx->d_toon_scratch, need + need / 4));
+    ctx->toon_scratch_bytes = need + need / 4;
+  }
+  uint8_t *d_arena = nullptr, *d_out = nullptr;
+  uint32_t *d_idx = nullptr, *d_len = nullptr;
+  int32_t* d_st = nullptr;
+  uint64_t* d_ooff = nullptr;
+  std::vector<uint32_t> lens(n_units);
+  do {
+#define M_CUDA(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = CF_E_CUDA; break; } }
+    M_CUDA(cudaMalloc(&d_arena, 5 * stream_bytes + 32ull * n_units + 64));
+    M_CUDA(cudaMalloc(&d_idx, nnodes * 4));
+    M_CUDA(cudaMalloc(&d_len, (size_t)n_units * 4));
+    M_CUDA(cudaMalloc(&d_st, (size_t)n_units * 4));
+    M_CUDA(cudaMalloc(&d_ooff, ((size_t)n_units + 1) * 8));
+    mask_kernel<<<(n_units + 63) / 64, 64>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, (cfj::JNode*)ctx->d_toon_scratch, d_idx, d_arena, d_len,
+                                             d_st, max_depth);
+    ctx->launches++;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaMemcpy(lens.data(), d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+    M_CUDA(cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_units; ++i) { out_offsets[i] = total; total += lens[i]; }
+    out_offsets[n_units] = total;
+    if (out_needed) *out_needed = total;
+    if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; rc = CF_E_CAPACITY; break; }
+    if (total) {
+      M_CUDA(cudaMalloc(&d_out, total));
+      M_CUDA(cudaMemcpy(d_ooff, out_offsets, ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
+      mask_compact_kernel<<<n_units, 128>>>(d_arena, b->d_offsets, d_len, d_ooff, d_out, n_units);
+      ctx->launches++;
+      M_CUDA(cudaGetLastError());
+      M_CUDA(cudaMemcpy(out_bytes, d_out, total, cudaMemcpyDeviceToHost));
+    }
+#undef M_CUDA
+  } while (0);
+  cudaFree(d_arena); cudaFree(d_out); cudaFree(d_idx); cudaFree(d_len); cudaFree(d_st); cudaFree(d_ooff);
+  return rc;
+}
+
+int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
+                          uint8_t* sensitive) {
+  if (!ctx || !b || !sensitive) return CF_E_BADARG;
+  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  if (rc) return rc;
+  uint8_t* d = nullptr;
+  CF_CUDA(ctx, cudaMalloc(&d, n_units));
+  classify_keys_kernel<<<(n_units + 127) / 128, 128>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, d);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(sensitive, d, n_units, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return CF_E_CUDA; }
+  return CF_OK;
 }
 
 int cf_profile_begin(cf_ctx* ctx, uint32_t max_launches) {

@@ -251,3 +251,41 @@ def toon_host(batch: Batch, stream, offsets: np.ndarray, report_errors: bool = T
         else:
             texts.append(None)
     return status, texts
+
+
+MASK_OK, MASK_PARSE_ERROR, MASK_UNSUPPORTED = 0, 2, 6
+
+
+def mask_host(batch: Batch, stream, offsets: np.ndarray, max_depth: int = 10):
+    """cf_mask_host: every unit is one JSON request body.  Returns (status int32[n], masked bytes or None)."""
+    ctx = batch.ctx
+    n = len(offsets) - 1
+    nbytes = int(offsets[-1])
+    status = np.empty(n, dtype=np.int32)
+    out_offs = np.zeros(n + 1, dtype=np.uint64)
+    need = c_uint64(0)
+    cap = nbytes + 4096
+    sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        with ctx.lock:
+            rc = ctx.lib.cf_mask_host(ctx.h, batch.h, sp, nbytes, offsets.ctypes.data, n, max_depth, out.ctypes.data, cap, out_offs.ctypes.data, status.ctypes.data, byref(need))
+        if rc == N.CF_E_CAPACITY and need.value > cap:
+            cap = int(need.value)
+            continue
+        ctx.check(rc, "cf_mask_host")
+        break
+    raw = out.tobytes()
+    return status, [raw[int(out_offs[i]):int(out_offs[i + 1])] if status[i] == MASK_OK else None for i in range(n)]
+
+
+def classify_keys_host(batch: Batch, keys: Sequence[Union[str, bytes]]) -> List[bool]:
+    """is_sensitive_key for each key name on the GPU."""
+    if not keys:
+        return []
+    stream, offs = pack_units(keys)
+    ctx = batch.ctx
+    out = np.empty(len(keys), dtype=np.uint8)
+    with ctx.lock:
+        ctx.check(ctx.lib.cf_classify_keys_host(ctx.h, batch.h, ctypes.cast(ctypes.c_char_p(stream), c_void_p), len(stream), offs.ctypes.data, len(keys), out.ctypes.data), "cf_classify_keys_host")
+    return [bool(x) for x in out]

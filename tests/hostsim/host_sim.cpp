@@ -111,3 +111,19 @@ extern "C" int cfh_toon(const uint8_t* text, uint32_t n, uint8_t* out, uint32_t 
   *out_len = 0;
   return cfj::toon_process(text, n, nodes.data(), (uint32_t)nodes.size(), out, out_cap, out_len, &big, digits.data(), (uint32_t)digits.size(), false);
 }
+
+// ---- masking: shared json_mask.h pipeline on the CPU ----
+#include "../../mcp_context_forge_b200/csrc/json_mask.h"
+extern "C" int cfh_mask(const uint8_t* text, uint32_t n, int max_depth, uint8_t* out, uint32_t out_cap, uint32_t* out_len) {
+  std::vector<cfj::JNode> nodes(n / 2 + 4);
+  std::vector<uint32_t> idx(n / 2 + 4);
+  cfj::Big big;
+  std::vector<uint8_t> digits(1240);
+  cfm::NumWork w{&big, &big, digits.data(), (uint32_t)digits.size()};
+  *out_len = 0;
+  return cfm::mask_process(text, n, nodes.data(), (uint32_t)nodes.size(), idx.data(), (uint32_t)idx.size(), out, out_cap, out_len, max_depth, w);
+}
+extern "C" int cfh_key_sensitive(const uint8_t* key, uint32_t n) {
+  cfj::JNode k{cfj::J_KEY, 0, n, 0};   // raw (unescaped) key bytes
+  return cfm::key_sensitive(key, k) ? 1 : 0;
+}

@@ -15,7 +15,7 @@ SRCS = [
 
 
 def build(force=False):
-    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h", "json_toon.h", "unicode_tables.h")]
+    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h", "json_toon.h", "json_mask.h", "unicode_tables.h")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", SO] + SRCS)
@@ -123,3 +123,17 @@ def toon_host(text: str, unlimited: bool = False):
     n = ctypes.c_uint32()
     st = lib().cfh_toon(b, len(b), out, cap, ctypes.byref(n))
     return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)
+
+
+def mask_host(payload: bytes, max_depth: int = 10):
+    """(status, masked_bytes_or_None) from the shared json_mask.h pipeline compiled for the CPU."""
+    cap = len(payload) * 5 + 64
+    out = ctypes.create_string_buffer(cap)
+    n = ctypes.c_uint32()
+    st = lib().cfh_mask(payload, len(payload), max_depth, out, cap, ctypes.byref(n))
+    return st, (out.raw[: n.value] if st == 0 else None)
+
+
+def key_sensitive_host(key: str) -> bool:
+    b = key.encode("utf-8")
+    return bool(lib().cfh_key_sensitive(b, len(b)))
