@@ -100,10 +100,19 @@ def cpu_run(payloads, total_units: int, cores: int) -> float:
 
 
 def host_cores() -> int:
+    """Usable host threads: affinity mask, capped by the cgroup CPU quota when one is set."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 # ------------------------------------------------------------------------------------------------
@@ -146,6 +155,43 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def side_stages(ctx, engine, payloads):
+    """Informational device-resident timings of the other rows of the path on the same payload mix
+    (not part of the headline metric): request_logging_masking and toon_encoder, 4096 units each."""
+    import ctypes
+
+    import torch
+
+    out = {}
+    try:
+        n = 4096
+        units = [payloads[i % len(payloads)].encode("utf-8") for i in range(n)]
+        stream, offs = engine.pack_units(units)
+        batch = engine.Batch(ctx, len(stream), n)
+        batch.upload(stream, offs)
+        d_out = torch.empty(len(stream) + 16, dtype=torch.uint8, device="cuda")
+        d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_st = torch.empty(n, dtype=torch.int32, device="cuda")
+        lib = ctx.lib
+        for name in ("toon",):
+            lib.cf_toon(ctx.h, batch.h, 0, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lib.cf_toon(ctx.h, batch.h, 0, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            out[name] = {"units": n, "ms": ms, "payloads_per_s": n / ms * 1e3, "gb_per_s": len(stream) / ms / 1e6, "converted": int((d_st == 0).sum())}
+        t0 = time.perf_counter()
+        st, _ = engine.mask_host(batch, stream, offs, 10)
+        dt = time.perf_counter() - t0
+        out["mask_e2e_host_buffers"] = {"units": n, "ms": dt * 1e3, "payloads_per_s": n / dt, "ok": int((st == 0).sum())}
+    except Exception as exc:  # informational only
+        out["error"] = str(exc)
+    return out
 
 
 def read_peaks():
@@ -206,7 +252,7 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        sample = 48 * cores                               # ~2 ms per payload per core -> a few seconds
+        sample = 96 * cores                               # ~3 ms per payload per core: ~10-40 s of CPU work in total
         v = cpu_run(payloads, sample, cores)
         cpu_base = {"value": v, "unit": "payloads/s", "cores": cores, "kind": "port",
                     "sample": f"{sample} payloads of 16 KiB (same mix) over {cores} processes, oracle/hook_chain_ref.py chain (CPython re)"}
@@ -227,9 +273,9 @@ def main():
 
     ctx = engine.Context.get(local_rank)
     prog = engine.Program()
-    from oracle import hook_chain_ref as ref   # pattern list only (lexicon constants)
+    from mcp_context_forge_b200.plugins.harmful_content_detector import DEFAULT_LEXICONS   # product's copy of the reference defaults
 
-    for pats in ref.DEFAULT_LEXICONS.values():
+    for pats in DEFAULT_LEXICONS.values():
         for pat in pats:
             prog.add_search(pat, re.I)
     for w in DENY:
@@ -318,7 +364,12 @@ def main():
     # sanity: the e2e verdicts equal the resident ones, and flagged units are what the oracle says on a sample
     torch.cuda.synchronize()
     same = bool((h_bm.cuda() == d_bm).all().item())
+    stages = None
+    if rank == 0 and world == 1:
+        stages = side_stages(ctx, engine, payloads)
     if rank == 0:
+        from oracle import hook_chain_ref as ref          # checker only: parity of a sample of this run's verdicts
+
         sample_units = units[:8]
         exp = ref.scan_bitmaps(sample_units, [(p, re.I) for pats in ref.DEFAULT_LEXICONS.values() for p in pats], DENY, [(s, f) for s, f, _ in SUBS])
         got = engine.bitmaps_to_ints(h_bm.numpy().view(np.uint64), 8, W)
@@ -359,6 +410,7 @@ def main():
         "cpu_baseline": cpu_base,
         "clocks": clocks,
         "scan_counters": {"prefilter_candidates": cand, "dfa_steps": steps_dfa},
+        "other_stages": stages,
     }
     print(json.dumps(line))
     if world > 1:
