@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PAYLOAD_BYTES = 16384
-UNITS_PER_GPU = 16384          # 16384 x 16 KiB = 256 MiB per step per GPU (> 126 MB L2)
+UNITS_PER_GPU = 65536          # 65536 x 16 KiB = 1 GiB per step per GPU (8x the 126 MB L2; SURVEY §8d "64k batch")
 DISTINCT = 256                 # distinct seeded payloads, tiled to the batch
 MIX = (("A", 0.5), ("B", 0.25), ("C", 0.25))
 METRIC = "tool-call payloads/sec (16 KiB JSON), fused regex/deny/harmful scan"
@@ -219,7 +219,7 @@ def main():
     config = {"workload": f"configs[1]: batched 16 KiB payloads ({int(MIX[0][1]*100)}% tabular JSON / {int(MIX[1][1]*100)}% nested JSON / {int(MIX[2][1]*100)}% prose, hit rate 1e-4), "
                           "fused harmful(9 IGNORECASE regex)+deny(3 literals)+regex_filter(2 rules) scan",
               "payload_bytes": PAYLOAD_BYTES, "units_per_gpu": args.units, "batch_bytes_per_gpu": None,
-              "patterns": 14, "l2_policy": "inputs_larger_than_l2 (256 MiB batch per GPU vs 126 MB L2)",
+              "patterns": 14, "l2_policy": "inputs_larger_than_l2 (1 GiB batch per GPU vs 126 MB L2)",
               "parallelism": f"shard{world}: independent payload shards per GPU, one NCCL all_gather of verdict bitmaps" if world > 1 else "single GPU"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -296,7 +296,12 @@ def main():
     h_offs = torch.from_numpy(offs.astype(np.int64)).pin_memory()
     h_bm = torch.empty(n * W, dtype=torch.int64, pin_memory=True)
     d_bm = torch.zeros(n * W, dtype=torch.int64, device="cuda")
-    d_all = torch.zeros(world * n * W, dtype=torch.int64, device="cuda") if world > 1 else None
+    # N > 1: verdict bitmaps are all-gathered every step; two buffer pairs so that the gather of step k
+    # (NCCL stream) overlaps the scan of step k+1 (compute stream)
+    d_bms = [d_bm, torch.zeros(n * W, dtype=torch.int64, device="cuda")] if world > 1 else [d_bm]
+    d_alls = [torch.zeros(world * n * W, dtype=torch.int64, device="cuda") for _ in range(2)] if world > 1 else None
+    pending = []
+    step_no = [0]
     batch = engine.Batch(ctx, nbytes, n)
     lib = ctx.lib
     cs = torch.cuda.current_stream().cuda_stream
@@ -305,9 +310,17 @@ def main():
         ctx.check(lib.cf_batch_upload(ctx.h, batch.h, h_stream.data_ptr(), nbytes, h_offs.data_ptr(), n, cs), "upload")
 
     def step_resident():
-        ctx.check(lib.cf_scan(ctx.h, prog.h, batch.h, d_bm.data_ptr(), cs), "cf_scan")
+        k = step_no[0] & 1 if world > 1 else 0
+        step_no[0] += 1
+        if world > 1 and len(pending) >= 2:
+            pending.pop(0).wait()                  # buffer pair k is free again
+        ctx.check(lib.cf_scan(ctx.h, prog.h, batch.h, d_bms[k].data_ptr(), cs), "cf_scan")
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_bm)
+            pending.append(dist.all_gather_into_tensor(d_alls[k], d_bms[k], async_op=True))
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     def step_e2e():
         ctx.check(lib.cf_scan_host(ctx.h, prog.h, batch.h, h_stream.data_ptr(), nbytes, h_offs.data_ptr(), n, h_bm.data_ptr()), "cf_scan_host")
@@ -324,6 +337,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if world > 1:
+            drain()                                # every step's gather is inside the timed region
         e1.record()
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
@@ -338,6 +353,8 @@ def main():
     upload()
     for _ in range(args.warmup):
         step_resident()
+    if world > 1:
+        drain()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -363,7 +380,7 @@ def main():
 
     # sanity: the e2e verdicts equal the resident ones, and flagged units are what the oracle says on a sample
     torch.cuda.synchronize()
-    same = bool((h_bm.cuda() == d_bm).all().item())
+    same = bool((h_bm.cuda() == d_bms[0]).all().item()) and (world == 1 or bool((d_alls[0][rank * n * W:(rank + 1) * n * W] == d_bms[0]).all().item()))
     stages = None
     if rank == 0 and world == 1:
         stages = side_stages(ctx, engine, payloads)
