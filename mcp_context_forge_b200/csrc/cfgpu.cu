@@ -659,6 +659,12 @@ __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ st
   cfj::Big big;
   uint8_t digits[1240];
   uint32_t ol = 0;
+  if (flags & 4u) {   // experiment: parse only
+    uint32_t cnt = 0;
+    int pr = cfj::json_parse(stream + b, len, my, len / 2 + 4, &cnt);
+    status[u] = pr; out_len[u] = cnt;
+    return;
+  }
   int st = cfj::toon_process(stream + b, len, my, len / 2 + 4, out + b, len ? len - 1 : 0, &ol, &big, digits, sizeof(digits), (flags & 1u) == 0);
   status[u] = st;
   out_len[u] = st == cfj::TS_CONVERTED ? ol : 0;

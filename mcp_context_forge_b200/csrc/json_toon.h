@@ -15,6 +15,12 @@
 #include "scan_core.h"
 #include "unicode_tables.h"
 
+#ifdef __CUDA_ARCH__
+#define CF_OPAQUE(v) asm volatile("" : "+r"(v))
+#else
+#define CF_OPAQUE(v) ((void)0)
+#endif
+
 namespace cfj {
 
 // ------------------------------------------------------------------------------------------------
@@ -52,7 +58,10 @@ CF_HD bool is_pyspace(uint32_t cp) {       // str.isspace()
 // ------------------------------------------------------------------------------------------------
 struct JNode { uint32_t t, off, len, next; };
 enum : uint32_t { J_NULL = 0, J_FALSE = 1, J_TRUE = 2, J_NUM = 3, J_STR = 4, J_ARR = 5, J_OBJ = 6, J_KEY = 7, J_TYPE = 0xF };
-enum : uint32_t { JF_ESC = 0x100, JF_NEG = 0x100, JF_FRAC = 0x200, JF_EXP = 0x400 };
+enum : uint32_t { JF_ESC = 0x100, JF_NEG = 0x100, JF_FRAC = 0x200, JF_EXP = 0x400,
+                  // string properties computed while the parser validates the string (one pass, no re-scan at emit time)
+                  JF_Q = 0x800 /* toon._needs_quotes(s) */, JF_CTRLERR = 0x1000 /* a char toon._quote_string rejects */,
+                  JF_KEYOK = 0x2000 /* valid unquoted TOON key */ };
 //   scalar   : off/len = raw text span (strings: between the quotes)
 //   container: off = index of first child (0 = none), len = number of children; for objects the
 //              children are J_KEY nodes, the value of key k is node k+1, keys are chained by .next
@@ -62,6 +71,12 @@ static const int MAXD = 64;                // nesting depth handled on the devic
 enum : int { PARSE_OK = 0, PARSE_ERROR = 1, PARSE_UNSUPPORTED = 2 };
 
 CF_HD bool j_ws(uint32_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+CF_HD int hexv_of(uint32_t c) {
+  if (c >= '0' && c <= '9') return (int)c - '0';
+  c |= 0x20;
+  if (c >= 'a' && c <= 'f') return (int)c - 'a' + 10;
+  return -1;
+}
 CF_HD int hexv(uint32_t c) {
   if (c >= '0' && c <= '9') return (int)c - '0';
   c |= 0x20;
@@ -69,10 +84,58 @@ CF_HD int hexv(uint32_t c) {
   return -1;
 }
 
+// Incremental evaluation of the reference's string predicates over the decoded code points
+// (toon.py:163-222 _needs_quotes, :276-279 the control characters _quote_string rejects, :286-309 key rule).
+struct StrProps {
+  uint32_t count, first, last;
+  int num;            // number-like automaton state (toon.py:54); -1 = failed
+  bool lead0, special, ctrl, ctrl_bad, key_ok, key_nl, r1, r2, r3;
+  CF_HD void init() { count = first = last = 0; num = 0; lead0 = true; special = ctrl = ctrl_bad = key_nl = false; key_ok = true; r1 = r2 = r3 = true; }
+  CF_HD void feed(uint32_t cp) {
+    if (count == 0) first = cp;
+    last = cp;
+    if (cp < 32) { ctrl = true; if (cp != '\n' && cp != '\r' && cp != '\t') ctrl_bad = true; }
+    if (cp == '\n' || cp == '\r' || cp == '\t' || cp == ',' || cp == ':' || cp == '[' || cp == ']' || cp == '{' || cp == '}' || cp == '"' || cp == '\\' || cp == '-') special = true;
+    const bool d = (cp >= '0' && cp <= '9') || (cp >= 0x80 && (num > 0 || lead0) && is_nd(cp));
+    if (count == 0) lead0 = (cp == '0'); else lead0 = lead0 && d;
+    switch (num) {
+      case 0: num = (cp == '0') ? 1 : (cp >= '1' && cp <= '9') ? 2 : -1; break;
+      case 1: num = (cp == '.') ? 3 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
+      case 2: num = d ? 2 : (cp == '.') ? 3 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
+      case 3: num = d ? 4 : -1; break;
+      case 4: num = d ? 4 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
+      case 5: num = (cp == '+') ? 6 : d ? 7 : -1; break;   // '-' already forces quotes through `special`
+      case 6: num = d ? 7 : -1; break;
+      case 7: num = d ? 7 : -1; break;
+      default: break;
+    }
+    // key rule ^[A-Za-z_][A-Za-z0-9_.]*$ where `$` also admits one final "\n"
+    if (key_nl) key_ok = false;
+    const bool al = (cp >= 'A' && cp <= 'Z') || (cp >= 'a' && cp <= 'z') || cp == '_';
+    if (count == 0) { if (!al) key_ok = false; }
+    else if (!(al || (cp >= '0' && cp <= '9') || cp == '.')) { if (cp == '\n') key_nl = true; else key_ok = false; }
+    if (count >= 4 || cp != (uint32_t)(uint8_t)"null"[count]) r1 = false;
+    if (count >= 4 || cp != (uint32_t)(uint8_t)"true"[count]) r2 = false;
+    if (count >= 5 || cp != (uint32_t)(uint8_t)"false"[count]) r3 = false;
+    ++count;
+  }
+  CF_HD uint32_t flags() const {
+    const bool reserved = (r1 && count == 4) || (r2 && count == 4) || (r3 && count == 5);
+    const bool numlike = (num == 1 || num == 2 || num == 4 || num == 7);
+    uint32_t f = 0;
+    if (count == 0 || reserved || special || numlike || (lead0 && count >= 2) || ctrl || is_pyspace(first) || is_pyspace(last)) f |= JF_Q;
+    if (ctrl_bad) f |= JF_CTRLERR;
+    if (count > 0 && key_ok && !reserved) f |= JF_KEYOK;
+    return f;
+  }
+};
+
 // Validate one JSON string starting at the opening quote; returns false on any error.  On success
 // *pos is just past the closing quote.  Hash (FNV-1a) is over the DECODED UTF-8 bytes.
 CF_HD bool parse_string(const uint8_t* s, uint32_t n, uint32_t* pos, uint32_t* flags, uint32_t* hash) {
   uint32_t p = *pos + 1, h = 2166136261u, fl = 0;
+  StrProps sp_;
+  sp_.init();
   while (true) {
     if (p >= n) return false;
     uint32_t c = s[p];
@@ -108,6 +171,7 @@ CF_HD bool parse_string(const uint8_t* s, uint32_t n, uint32_t* pos, uint32_t* f
         default: return false;
       }
       p += 2;
+      sp_.feed(cp);
       // hash the UTF-8 encoding of cp
       if (cp < 0x80) { h = (h ^ cp) * 16777619u; }
       else if (cp < 0x800) { h = (h ^ (0xC0 | (cp >> 6))) * 16777619u; h = (h ^ (0x80 | (cp & 63))) * 16777619u; }
@@ -115,7 +179,7 @@ CF_HD bool parse_string(const uint8_t* s, uint32_t n, uint32_t* pos, uint32_t* f
       else { h = (h ^ (0xF0 | (cp >> 18))) * 16777619u; h = (h ^ (0x80 | ((cp >> 12) & 63))) * 16777619u; h = (h ^ (0x80 | ((cp >> 6) & 63))) * 16777619u; h = (h ^ (0x80 | (cp & 63))) * 16777619u; }
       continue;
     }
-    if (c < 0x80) { h = (h ^ c) * 16777619u; ++p; continue; }
+    if (c < 0x80) { h = (h ^ c) * 16777619u; sp_.feed(c); ++p; continue; }
     // strict UTF-8
     uint32_t need, mn;
     if (c >= 0xC2 && c <= 0xDF) { need = 1; mn = 0x80; }
@@ -132,10 +196,11 @@ CF_HD bool parse_string(const uint8_t* s, uint32_t n, uint32_t* pos, uint32_t* f
       h = (h ^ cc) * 16777619u;
     }
     if (cp < mn || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+    sp_.feed(cp);
     p += need + 1;
   }
   *pos = p + 1;
-  *flags = fl;
+  *flags = fl | sp_.flags();
   *hash = h;
   return true;
 }
@@ -186,6 +251,8 @@ CF_HD bool keys_equal(const uint8_t* s, const JNode& a, const JNode& b) {
 }
 
 // Parse `s[0..n)` (a whole JSON document, surrounding whitespace allowed) into nodes[0..cap).
+// Token-at-a-time.  (A byte-at-a-time flat state machine was tried to cut warp divergence and measured
+// 2.4x SLOWER on B200 — profiles/README.md — so the straightforward form stays.)
 CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, uint32_t* out_count) {
   uint32_t pos = 0, nn = 0;
   uint32_t st_node[MAXD], st_last[MAXD];
@@ -505,56 +572,20 @@ CF_HD void newline(Ctx& c, uint32_t pre) {
 
 CF_HD bool is_simple(uint32_t t) { uint32_t k = t & J_TYPE; return k != J_ARR && k != J_OBJ; }
 
-// string value -> TOON (quote only when the reference's _needs_quotes says so)
+// string value -> TOON (quote only when the reference's _needs_quotes says so; the predicate was
+// evaluated by the parser and sits in the node flags)
 CF_HD void emit_string(Ctx& c, const JNode& nd, bool force_quote) {
   const uint8_t* b = c.s + nd.off;
   const uint8_t* e = b + nd.len;
-  bool q = force_quote;
-  if (!q) {
-    if (nd.len == 0) q = true;
-    else {
-      // one pass over the decoded characters
-      StrIter it{b, e};
-      uint32_t first = 0, last = 0, count = 0;
-      int st = 0;                 // number-like automaton (see toon.py:54); -1 = failed
-      bool lead0 = true;          // ^0\d+$
-      bool special = false, ctrl = false;
-      while (!it.done()) {
-        uint32_t cp = it.next();
-        if (count == 0) first = cp;
-        last = cp;
-        if (cp < 32) ctrl = true;
-        if (cp == '\n' || cp == '\r' || cp == '\t' || cp == ',' || cp == ':' || cp == '[' || cp == ']' || cp == '{' || cp == '}' || cp == '"' || cp == '\\' || cp == '-') special = true;
-        bool d = is_nd(cp);
-        if (count == 0) lead0 = (cp == '0'); else lead0 = lead0 && d;
-        switch (st) {
-          case 0: st = (cp == '0') ? 1 : (cp >= '1' && cp <= '9') ? 2 : -1; break;
-          case 1: st = (cp == '.') ? 3 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
-          case 2: st = d ? 2 : (cp == '.') ? 3 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
-          case 3: st = d ? 4 : -1; break;
-          case 4: st = d ? 4 : (cp == 'e' || cp == 'E') ? 5 : -1; break;
-          case 5: st = (cp == '+') ? 6 : d ? 7 : -1; break;   // '-' is handled by `special`
-          case 6: st = d ? 7 : -1; break;
-          case 7: st = d ? 7 : -1; break;
-          default: break;
-        }
-        ++count;
-      }
-      bool numlike = (st == 1 || st == 2 || st == 4 || st == 7);
-      bool reserved = false;
-      if (!(nd.t & JF_ESC)) {
-        if (nd.len == 4 && b[0] == 'n' && b[1] == 'u' && b[2] == 'l' && b[3] == 'l') reserved = true;
-        if (nd.len == 4 && b[0] == 't' && b[1] == 'r' && b[2] == 'u' && b[3] == 'e') reserved = true;
-        if (nd.len == 5 && b[0] == 'f' && b[1] == 'a' && b[2] == 'l' && b[3] == 's' && b[4] == 'e') reserved = true;
-      } else if (count == 4 || count == 5) {
-        StrIter r{b, e};
-        const char* w1 = "null"; const char* w2 = "true"; const char* w3 = "false";
-        bool m1 = count == 4, m2 = count == 4, m3 = count == 5;
-        for (uint32_t i = 0; !r.done(); ++i) { uint32_t cp = r.next(); if (m1 && cp != (uint32_t)w1[i]) m1 = false; if (m2 && cp != (uint32_t)w2[i]) m2 = false; if (m3 && cp != (uint32_t)w3[i]) m3 = false; }
-        reserved = m1 || m2 || m3;
-      }
-      q = reserved || special || numlike || (lead0 && count >= 2) || is_pyspace(first) || is_pyspace(last) || ctrl;
-    }
+  const bool q = force_quote || (nd.t & JF_Q);
+  if (q && (nd.t & JF_CTRLERR)) { c.err = TS_VALUE_ERROR; return; }
+  if (!(nd.t & JF_ESC)) {
+    // no escapes in the source: the decoded text IS the source bytes, and nothing in it needs a TOON
+    // escape either (a raw '"' or '\' cannot occur unescaped in JSON)
+    if (q) c.out.put('"');
+    for (const uint8_t* p = b; p < e; ++p) c.out.put(*p);
+    if (q) c.out.put('"');
+    return;
   }
   StrIter it{b, e};
   if (!q) { while (!it.done()) c.out.put_cp(it.next()); return; }
@@ -566,40 +597,23 @@ CF_HD void emit_string(Ctx& c, const JNode& nd, bool force_quote) {
     else if (cp == '\n') { c.out.put('\\'); c.out.put('n'); }
     else if (cp == '\r') { c.out.put('\\'); c.out.put('r'); }
     else if (cp == '\t') { c.out.put('\\'); c.out.put('t'); }
-    else if (cp < 32) { c.err = TS_VALUE_ERROR; return; }
     else c.out.put_cp(cp);
   }
   c.out.put('"');
 }
 
-// object key: unquoted iff ^[A-Za-z_][A-Za-z0-9_.]*$ (where `$` admits one final "\n") and not reserved
+// object key: unquoted iff ^[A-Za-z_][A-Za-z0-9_.]*$ (where `$` admits one final "\n") and not reserved;
+// `raw` = columnar header, never quoted (toon.py:501)
 CF_HD void emit_key(Ctx& c, const JNode& k, bool raw) {
   const uint8_t* b = c.s + k.off;
   const uint8_t* e = b + k.len;
-  if (raw) { StrIter it{b, e}; while (!it.done()) c.out.put_cp(it.next()); return; }
-  bool ok = k.len > 0;
-  uint32_t count = 0;
-  bool r1 = true, r2 = true, r3 = true;
-  const char* w1 = "null"; const char* w2 = "true"; const char* w3 = "false";
-  {
+  if (raw || (k.t & JF_KEYOK)) {
+    if (!(k.t & JF_ESC)) { for (const uint8_t* p = b; p < e; ++p) c.out.put(*p); return; }
     StrIter it{b, e};
-    bool ended_nl = false;
-    while (!it.done()) {
-      uint32_t cp = it.next();
-      if (ended_nl) ok = false;                       // something after the newline
-      bool al = (cp >= 'A' && cp <= 'Z') || (cp >= 'a' && cp <= 'z') || cp == '_';
-      if (count == 0) { if (!al) ok = false; }
-      else if (!(al || (cp >= '0' && cp <= '9') || cp == '.')) { if (cp == '\n') ended_nl = true; else ok = false; }
-      if (count >= 4 || cp != (uint32_t)w1[count]) r1 = false;
-      if (count >= 4 || cp != (uint32_t)w2[count]) r2 = false;
-      if (count >= 5 || cp != (uint32_t)w3[count]) r3 = false;
-      ++count;
-    }
+    while (!it.done()) c.out.put_cp(it.next());
+    return;
   }
-  bool reserved = (r1 && count == 4) || (r2 && count == 4) || (r3 && count == 5);
-  if (ok && !reserved) { StrIter it{b, e}; while (!it.done()) c.out.put_cp(it.next()); return; }
-  JNode tmp = k;
-  emit_string(c, tmp, true);
+  emit_string(c, k, true);
 }
 
 // Python's float formatting as used by toon._encode_float, from the exact binary value.
@@ -779,6 +793,13 @@ CF_HD uint32_t find_member(const Ctx& c, uint32_t obj, uint32_t k) {
   return 0;
 }
 
+// same, trying the member at `*cursor` first (rows of a table almost always repeat the key order)
+CF_HD uint32_t find_member_hint(const Ctx& c, uint32_t obj, uint32_t k, uint32_t* cursor) {
+  const uint32_t m = *cursor;
+  if (m && c.nodes[m + 1].next == c.nodes[k + 1].next && keys_equal(c.s, c.nodes[m], c.nodes[k])) { *cursor = c.nodes[m].next; return m + 1; }
+  return find_member(c, obj, k);
+}
+
 enum : int { COL_YES = 1, COL_NO = 0, COL_CRASH = -1 };
 // toon.py:456-511 called on `arr` (non-empty); `checked` = caller already verified all elements are dicts
 CF_HD int columnar_check(const Ctx& c, uint32_t arr) {
@@ -789,7 +810,8 @@ CF_HD int columnar_check(const Ctx& c, uint32_t arr) {
   for (uint32_t x = N[first].next; x; x = N[x].next) {
     if ((N[x].t & J_TYPE) != J_OBJ) return COL_CRASH;
     if (N[x].len != N[first].len) return COL_NO;
-    for (uint32_t k = N[first].off; k; k = N[k].next) if (!find_member(c, x, k)) return COL_NO;
+    uint32_t cur = N[x].off;
+    for (uint32_t k = N[first].off; k; k = N[k].next) if (!find_member_hint(c, x, k, &cur)) return COL_NO;
   }
   for (uint32_t x = first; x; x = N[x].next)
     for (uint32_t k = N[x].off; k; k = N[k].next) if (!is_simple(N[k + 1].t)) return COL_NO;
@@ -807,10 +829,11 @@ CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre) {
   for (uint32_t x = first; x && !c.err && !(c.out.over && c.stop_on_over); x = N[x].next) {
     newline(c, row_pre);
     bool f1 = true;
+    uint32_t cur = N[x].off;
     for (uint32_t k = N[first].off; k; k = N[k].next) {
       if (!f1) c.out.put(',');
       f1 = false;
-      emit_prim(c, find_member(c, x, k));
+      emit_prim(c, find_member_hint(c, x, k, &cur));
     }
   }
 }

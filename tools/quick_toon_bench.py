@@ -9,7 +9,8 @@ from mcp_context_forge_b200.batching import GpuBatcher
 
 b = GpuBatcher.get()
 lib = b.ctx.lib
-for shape, size, n in (("A", 16384, 16384), ("A", 2048, 65536), ("A", 262144, 1024), ("B", 16384, 16384)):
+FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+for shape, size, n in (("A", 16384, 32768), ("A", 2048, 131072), ("B", 16384, 32768)):
     base = [synth.payload(shape, size, seed=s).encode() for s in range(64)]
     texts = [base[i % 64] for i in range(n)]
     stream, offs = engine.pack_units(texts)
@@ -19,11 +20,11 @@ for shape, size, n in (("A", 16384, 16384), ("A", 2048, 65536), ("A", 262144, 10
     d_len = torch.empty(n, dtype=torch.int32, device="cuda")
     d_st = torch.empty(n, dtype=torch.int32, device="cuda")
     for _ in range(2):
-        lib.cf_toon(b.ctx.h, batch.h, 0, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
+        lib.cf_toon(b.ctx.h, batch.h, FLAGS, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    lib.cf_toon(b.ctx.h, batch.h, 0, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
+    lib.cf_toon(b.ctx.h, batch.h, FLAGS, d_out.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), None)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
