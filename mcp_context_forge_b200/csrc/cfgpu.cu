@@ -10,6 +10,7 @@
 // This is HBM-bound byte work: no tensor cores by design.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,7 +47,7 @@ struct cf_ctx {
   uint32_t prof_used = 0;
   bool prof_on = false;
   // scan kernel configuration (CF_SCAN_WARPS / CF_SCAN_ACC override the defaults; experiments)
-  uint32_t scan_warps = 20;        // best of the measured variants (profiles/README.md)
+  uint32_t scan_warps = 16;        // best of the measured variants (profiles/README.md)
   uint32_t scan_lane_bytes = 64;
   uint32_t scan_acc = 1;
   uint32_t scan_stages = 3;
@@ -139,6 +140,44 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
           smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// --- the same primitives on 32-bit absolute shared addresses (no generic->shared conversion, true LDS) ---
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
 // 2-D tiled TMA load (rows of 128 bytes, SWIZZLE_128B): one instruction per tile
@@ -342,33 +381,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- carve shared memory: table at the first 64 KiB boundary, tile stages + misc around it
+  // ---- carve shared memory: table at the first 64 KiB boundary, tile stages + misc around it.
+  // Stage s lives at absolute shared address stage_abs(s): the first NA stages in the gap before the
+  // table, the rest behind it (pure arithmetic: no pointer array, so the tile reads stay true LDS).
   const uint32_t abs0 = smem_u32(smem_raw);
   const uint32_t tbl_abs = (abs0 + 0xFFFFu) & ~0xFFFFu;
-  uint32_t a_lo = (abs0 + 1023u) & ~1023u, a_hi = tbl_abs;       // free space before the table
-  uint32_t b_lo = tbl_abs + 0x10000u, b_hi = abs0 + SCAN_SMEM;   // free space after it
-  uint8_t* stage[STAGES];
-#pragma unroll
-  for (uint32_t s = 0; s < STAGES; ++s) {
-    if (a_lo + TILE <= a_hi) { stage[s] = smem_raw + (a_lo - abs0); a_lo += TILE; }
-    else { stage[s] = smem_raw + (b_lo - abs0); b_lo += TILE; }
-  }
+  const uint32_t a_base = (abs0 + 1023u) & ~1023u;               // free space before the table
+  const uint32_t b_base = tbl_abs + 0x10000u;                    // free space after it
+  const uint32_t na_fit = (tbl_abs - a_base) / TILE;
+  const uint32_t NA = na_fit < STAGES ? na_fit : STAGES;
+  uint32_t a_end = a_base + NA * TILE, b_end = b_base + (STAGES - NA) * TILE;
   uint32_t misc_abs;
-  if (a_lo + sizeof(ScanMisc<WARPS>) <= a_hi) misc_abs = a_lo; else { misc_abs = b_lo; b_lo += (uint32_t)sizeof(ScanMisc<WARPS>); }
-  if (b_lo > b_hi) __trap();                                     // cannot happen: variants are sized for 227 KiB
+  if (a_end + sizeof(ScanMisc<WARPS>) <= tbl_abs) misc_abs = a_end; else { misc_abs = b_end; b_end += (uint32_t)sizeof(ScanMisc<WARPS>); }
+  if (b_end > abs0 + SCAN_SMEM) __trap();                        // cannot happen: variants are sized for 227 KiB
+  auto stage_abs = [&](uint32_t sidx) -> uint32_t { return sidx < NA ? a_base + sidx * TILE : b_base + (sidx - NA) * TILE; };
   ScanMisc<WARPS>& sm = *reinterpret_cast<ScanMisc<WARPS>*>(smem_raw + (misc_abs - abs0));
+  const uint32_t full_abs = misc_abs + (uint32_t)offsetof(ScanMisc<WARPS>, full);
+  const uint32_t empty_abs = misc_abs + (uint32_t)offsetof(ScanMisc<WARPS>, empty);
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem_raw + (tbl_abs - abs0));
   const uint32_t laneK = (lane << 2) | tbl_abs;                  // tbl_abs has zero low 16 bits
   const uint32_t mulc = P.mulc;                                  // 64, deliberately not an immediate
 
-  auto load_tile = [&](uint32_t slot_, uint64_t tile_) {
-    mbar_expect_tx(&sm.full[slot_], TILE);
+  auto load_tile = [&](uint32_t slot_, uint32_t tile_) {
+    mbar_expect_tx_a(full_abs + 8 * slot_, TILE);
 #pragma unroll
     for (int32_t bx = 0; bx < NBOX; ++bx)
-      tma_load_2d(stage[slot_] + bx * BROWS * 128, &tmap, 0, ROW0 + (int32_t)tile_ * TROWS + bx * BROWS, &sm.full[slot_]);
+      tma_load_2d_a(stage_abs(slot_) + bx * BROWS * 128, &tmap, 0, ROW0 + (int32_t)tile_ * TROWS + bx * BROWS, full_abs + 8 * slot_);
   };
 
-  const uint64_t first = blockIdx.x, stride = gridDim.x;
+  const uint32_t first = blockIdx.x, stride = gridDim.x, ntiles = (uint32_t)P.ntiles;
   if (tid < WARPS) sm.wq_n[tid] = 0;
   if (tid == 0) {
     sm.cq_n = 0;
@@ -377,8 +418,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // prologue: put STAGES-1 tiles in flight right away; the table fill below overlaps their latency
     for (uint32_t j = 0; j < STAGES - 1; ++j) {
-      uint64_t tj = first + (uint64_t)j * stride;
-      if (tj < P.ntiles) load_tile(j, tj);
+      const uint32_t tj = first + j * stride;
+      if (tj < ntiles) load_tile(j, tj);
     }
   }
   for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) tbl[(i >> 5) * 64 + (i & 31)] = P.E[i >> 5];
@@ -393,37 +434,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   const uint32_t ob = rowp * 128 + (((((gp % LPR) * NS) + NS - 1) ^ (rowp & 7)) << 4) + 12;
   // lane 0 of the CTA takes its look-back word (last 4 bytes of the previous tile) from HBM/L2,
   // fetched one iteration ahead
+  const uint8_t* back_ptr = P.stream + (uint64_t)first * TILE - 4;
+  const uint64_t back_step = (uint64_t)stride * TILE;
   uint32_t back_next = 0;
-  if (tid == 0 && first < P.ntiles) back_next = *reinterpret_cast<const uint32_t*>(P.stream + first * TILE - 4);
+  if (tid == 0 && first < ntiles) back_next = *reinterpret_cast<const uint32_t*>(back_ptr);
 
-  uint32_t it = 0;
-  for (uint64_t t = first; t < P.ntiles; t += stride, ++it) {
-    const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1;
+  // ring bookkeeping kept incrementally (no div/mod in the loop)
+  uint32_t slot = 0, phase = 0;                  // consumer side
+  uint32_t pslot = STAGES - 1, pphase = 1;       // producer side: slot / parity of tile it + STAGES - 1
+  uint32_t pj = STAGES - 1;                      // its index in this CTA's tile sequence
+  for (uint32_t t = first; t < ntiles; t += stride) {
     if (tid == 0) {   // keep STAGES-1 tiles in flight
-      uint32_t j = it + STAGES - 1;
-      uint64_t tj = first + (uint64_t)j * stride;
-      if (tj < P.ntiles) {
-        uint32_t sj = j % STAGES;
-        if (j >= STAGES) mbar_wait(&sm.empty[sj], ((j / STAGES) - 1) & 1);
-        load_tile(sj, tj);
+      const uint32_t tj = t + (STAGES - 1) * stride;
+      if (tj < ntiles) {
+        if (pj >= STAGES) mbar_wait_a(empty_abs + 8 * pslot, pphase);
+        load_tile(pslot, tj);
       }
     }
+    if (++pslot == STAGES) { pslot = 0; pphase ^= 1; }
+    ++pj;
     uint32_t back = back_next;
-    if (tid == 0 && t + stride < P.ntiles) back_next = *reinterpret_cast<const uint32_t*>(P.stream + (t + stride) * TILE - 4);
-    mbar_wait(&sm.full[slot], phase);
+    back_ptr += back_step;
+    if (tid == 0 && t + stride < ntiles) back_next = *reinterpret_cast<const uint32_t*>(back_ptr);
+    mbar_wait_a(full_abs + 8 * slot, phase);
 
     // this lane's LB bytes (+ the word holding its 4 look-back bytes)
     const uint32_t chunk = g * LB;          // tile-relative
-    const uint8_t* base = stage[slot];
-    if (g) back = *reinterpret_cast<const uint32_t*>(base + ob);
+    const uint32_t base = stage_abs(slot);
+    if (g) back = lds32(base + ob);
     uint4 v[NS];
 #pragma unroll
-    for (uint32_t j = 0; j < NS; ++j) v[j] = *reinterpret_cast<const uint4*>(base + off[j]);
+    for (uint32_t j = 0; j < NS; ++j) v[j] = lds128(base + off[j]);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[slot]);   // slot may be refilled: data is in registers
+    if (lane == 0) mbar_arrive_a(empty_abs + 8 * slot);   // slot may be refilled: data is in registers
+    if (++slot == STAGES) { slot = 0; phase ^= 1; }
 
     uint32_t h[NS];
-    if (NS == 4 && (P.dbg & 4) == 0) {
+    if (NS == 4) {
       // two independent shift-AND chains per lane (bytes 0-31 and 32-63) for instruction-level
       // parallelism; the second chain re-feeds the last word of the first half as its look-back
       uint32_t accA = 0, accB = 0, dA = 0, dB = 0;
@@ -458,7 +505,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
     const bool anyhit = (hany & 0x3F000000u) != 0;
     if (__any_sync(0xFFFFFFFFu, anyhit)) {
       if (anyhit) {
-        const uint64_t cpos = t * TILE + chunk;   // stream offset of this lane's first byte
+        const uint64_t cpos = (uint64_t)t * TILE + chunk;   // stream offset of this lane's first byte
 #pragma unroll
         for (uint32_t j = 0; j < NS; ++j)
           if (h[j] & 0x3F000000u) REGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
