@@ -214,7 +214,7 @@ struct ScanParams {
   uint32_t qcap_cta;
   uint32_t dfa_bytes;             // bytes needed to stage the DFA tables in shared memory (0 = too big)
   uint32_t dfa_trans_bytes, dfa_acc_bytes;
-  uint32_t mulc;                  // 64 (kept out of the instruction stream on purpose)
+  uint32_t mulc;                  // 1024 (kept out of the instruction stream on purpose)
   uint32_t dbg;                   // experiments: 1 = skip verification, 2 = no smem staging
 };
 
@@ -315,43 +315,50 @@ __device__ __forceinline__ void flush_candidates(ScanMisc<WARPS>& sm, const Scan
   __syncwarp();
 }
 
-// Prefilter table in shared memory, "lane-private bank" layout at a 64 KiB-aligned ABSOLUTE shared
-// address T:  entry(byte value b, lane l) = T + (b << 8) + (l << 2).
+// Prefilter tables in shared memory, "lane-private bank" layout at a 64 KiB-aligned ABSOLUTE shared
+// address T.  Each byte value b owns a 256-byte row: lanes' copies of E1[b] in the first half, of F[b]
+// in the second:   E1(b, l) = T + (b << 8) + (l << 2)        F(b, l) = T + (b << 8) + 128 + (l << 2)
 //   * bank = l for every lookup -> conflict-free for any input bytes
-//   * the full 32-bit shared address is produced by ONE PRMT: bytes {l<<2, b, T>>16, 0} taken from the
-//     data word and the per-lane constant K = (l << 2) | T  -> no address arithmetic in the loop
-//   * (acc >> 6) | TOP is issued as IMAD.HI (FMA pipe) by multiplying with a non-immediate 2^26, so the
-//     ALU pipe only carries PRMT + the AND + the hit OR.
-template <uint32_t ACC>
-__device__ __forceinline__ uint32_t acc_step(uint32_t acc, uint32_t e, uint32_t mulc) {
-  // ((acc << 6) | 0x3F) & e.  ACC == 1 issues the shift-or as IMAD (acc * 64 + 63, multiplier kept
-  // out of the immediate field so ptxas cannot turn it back into an ALU-pipe LEA/SHF).
-  uint32_t t;
-  if (ACC == 1) asm("mad.lo.u32 %0, %1, %2, 63;" : "=r"(t) : "r"(acc), "r"(mulc));
-  else t = (acc << 6) | 0x3Fu;
-  return t & e;
-}
+//   * the full 32-bit shared address is produced by ONE PRMT: bytes {l<<2 (|0x80), b, T>>16, 0} taken from
+//     the data word and a per-lane constant -> no address arithmetic in the loop
+//   * TWO bytes advance per step:  acc = (acc * 1024 + 1023) & F[b0] & E1[b1]
+//       F[b]  = (E[b] << 5) | 31          first byte of the pair, pre-shifted
+//       E1[b] = E[b] | 0x3E000000         second byte; keeps the first byte's candidate field (bits 25-29)
+//     one IMAD (FMA pipe; the multiplier is kept out of the immediate field so that ptxas cannot turn it
+//     back into an ALU-pipe shift) + one 3-input LOP3 per two bytes.
+static const uint32_t HIT2 = 0x3FF00000u;   // candidate fields of both bytes of a pair
+
 __device__ __forceinline__ uint32_t lds_abs(uint32_t addr) {
   uint32_t v;
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+template <uint32_t ACC>
+__device__ __forceinline__ uint32_t pair_step(uint32_t acc, uint32_t f0, uint32_t e1, uint32_t mulc) {
+  uint32_t t;
+  if (ACC == 1) asm("mad.lo.u32 %0, %1, %2, 1023;" : "=r"(t) : "r"(acc), "r"(mulc));
+  else t = (acc << 10) | 1023u;
+  return t & f0 & e1;
+}
 
-#define FEED(word, k, H)                                                                        \
-  {                                                                                             \
-    const uint32_t a_ = __byte_perm((word), laneK, 0x7604 | ((k) << 4)); /* T | b<<8 | lane<<2 */ \
-    acc = acc_step<ACC>(acc, lds_abs(a_), mulc);                                                \
-    H |= acc;                                                                                   \
+// two bytes (k, k+1) of `word`
+#define FEEDP(word, k, H)                                                                        \
+  {                                                                                              \
+    const uint32_t a0_ = __byte_perm((word), laneKF, 0x7604 | ((k) << 4));       /* F[b_k]   */  \
+    const uint32_t a1_ = __byte_perm((word), laneK, 0x7604 | (((k) + 1) << 4));  /* E1[b_k+1] */ \
+    acc = pair_step<ACC>(acc, lds_abs(a0_), lds_abs(a1_), mulc);                                 \
+    H |= acc;                                                                                    \
   }
-#define FEED4(word, H) FEED(word, 0, H) FEED(word, 1, H) FEED(word, 2, H) FEED(word, 3, H)
+#define FEED4(word, H) FEEDP(word, 0, H) FEEDP(word, 2, H)
 #define FEED16(v, H) FEED4((v).x, H) FEED4((v).y, H) FEED4((v).z, H) FEED4((v).w, H)
 
-// rare path, lane-local: re-run one 16-byte group with position tracking (data still in registers)
+// rare path, lane-local: re-run one 16-byte group one byte at a time with position tracking
+// (data still in registers; E[b] is recovered from the E1 copy)
 #define REFEED(word, k, bit)                                                                    \
   {                                                                                             \
     const uint32_t a_ = __byte_perm((word), laneK, 0x7604 | ((k) << 4));                        \
-    acc = ((acc << 6) | 0x3Fu) & lds_abs(a_);                                                   \
-    m |= ((acc & 0x3F000000u) ? 1u : 0u) << (bit);                                              \
+    acc = ((acc << 5) | 31u) & (lds_abs(a_) & 0x01FFFFFFu);                                     \
+    m |= ((acc & 0x01F00000u) ? 1u : 0u) << (bit);                                              \
   }
 #define REFEED4(word, b0) REFEED(word, 0, (b0)) REFEED(word, 1, (b0) + 1) REFEED(word, 2, (b0) + 2) REFEED(word, 3, (b0) + 3)
 #define REGROUP(prevword, v, gpos)                                                              \
@@ -400,7 +407,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   const uint32_t empty_abs = misc_abs + (uint32_t)offsetof(ScanMisc<WARPS>, empty);
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem_raw + (tbl_abs - abs0));
   const uint32_t laneK = (lane << 2) | tbl_abs;                  // tbl_abs has zero low 16 bits
-  const uint32_t mulc = P.mulc;                                  // 64, deliberately not an immediate
+  const uint32_t laneKF = laneK | 0x80u;                         // second half of each row: the F copies
+  const uint32_t mulc = P.mulc;                                  // 1024, deliberately not an immediate
 
   auto load_tile = [&](uint32_t slot_, uint32_t tile_) {
     mbar_expect_tx_a(full_abs + 8 * slot_, TILE);
@@ -422,7 +430,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
       if (tj < ntiles) load_tile(j, tj);
     }
   }
-  for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) tbl[(i >> 5) * 64 + (i & 31)] = P.E[i >> 5];
+  for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) {
+    const uint32_t e = P.E[i >> 5];
+    tbl[(i >> 5) * 64 + (i & 31)] = e | 0x3E000000u;            // E1
+    tbl[(i >> 5) * 64 + 32 + (i & 31)] = (e << 5) | 31u;        // F
+  }
   __syncthreads();
 
   // per-lane swizzled offsets of its 16-byte slots and of the word holding its look-back bytes
@@ -475,10 +487,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
       // parallelism; the second chain re-feeds the last word of the first half as its look-back
       uint32_t accA = 0, accB = 0, dA = 0, dB = 0;
       h[0] = h[1] = h[2] = h[3] = 0;
-#define FEEDA(word, k, H) { uint32_t acc = accA; FEED(word, k, H) accA = acc; }
-#define FEEDB(word, k, H) { uint32_t acc = accB; FEED(word, k, H) accB = acc; }
+#define FEEDA(word, k, H) { uint32_t acc = accA; FEEDP(word, k, H) accA = acc; }
+#define FEEDB(word, k, H) { uint32_t acc = accB; FEEDP(word, k, H) accB = acc; }
 #define FEED2(wa, wb, k, HA, HB) FEEDA(wa, k, HA) FEEDB(wb, k, HB)
-#define FEED2x4(wa, wb, HA, HB) FEED2(wa, wb, 0, HA, HB) FEED2(wa, wb, 1, HA, HB) FEED2(wa, wb, 2, HA, HB) FEED2(wa, wb, 3, HA, HB)
+#define FEED2x4(wa, wb, HA, HB) FEED2(wa, wb, 0, HA, HB) FEED2(wa, wb, 2, HA, HB)
       FEED2x4(back, v[1].w, dA, dB)
       FEED2x4(v[0].x, v[2].x, h[0], h[2]) FEED2x4(v[0].y, v[2].y, h[0], h[2]) FEED2x4(v[0].z, v[2].z, h[0], h[2]) FEED2x4(v[0].w, v[2].w, h[0], h[2])
       FEED2x4(v[1].x, v[3].x, h[1], h[3]) FEED2x4(v[1].y, v[3].y, h[1], h[3]) FEED2x4(v[1].z, v[3].z, h[1], h[3]) FEED2x4(v[1].w, v[3].w, h[1], h[3])
@@ -502,13 +514,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
     uint32_t hany = 0;
 #pragma unroll
     for (uint32_t j = 0; j < NS; ++j) hany |= h[j];
-    const bool anyhit = (hany & 0x3F000000u) != 0;
+    const bool anyhit = (hany & HIT2) != 0;
     if (__any_sync(0xFFFFFFFFu, anyhit)) {
       if (anyhit) {
         const uint64_t cpos = (uint64_t)t * TILE + chunk;   // stream offset of this lane's first byte
 #pragma unroll
         for (uint32_t j = 0; j < NS; ++j)
-          if (h[j] & 0x3F000000u) REGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
+          if (h[j] & HIT2) REGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
       }
       __syncwarp();
       if (sm.wq_n[warp] >= WQ / 2) flush_candidates<WARPS>(sm, P, warp, lane);
@@ -1000,7 +1012,7 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   P.dfa_bytes = p->search.stage_bytes < (1u << 30) ? (uint32_t)p->search.stage_bytes : 0;
   P.dfa_trans_bytes = (uint32_t)p->search.trans_bytes;
   P.dfa_acc_bytes = (uint32_t)p->search.acc_bytes;
-  P.mulc = 64;
+  P.mulc = 1024;
   P.dbg = getenv("CF_DBG") ? (uint32_t)atoi(getenv("CF_DBG")) : 0;
   const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages);
   uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM

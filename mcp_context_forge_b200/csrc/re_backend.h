@@ -45,7 +45,7 @@ struct DfaOut {
 };
 
 struct FilterOut {
-  uint32_t E[256];           // P3<<24 | P2<<18 | P1<<12 | P0<<6 | N (six buckets per field; scan_core.h)
+  uint32_t E[256];           // P3<<20 | P2<<15 | P1<<10 | P0<<5 | N (five buckets per field; scan_core.h)
   std::vector<int> bucket_of_pattern;
 };
 

@@ -128,14 +128,17 @@ CF_HD uint64_t match_first(const DfaTables& t, const uint8_t* s, uint64_t ustart
   return last;
 }
 
-// Prefilter.  Five 6-bit fields per byte value, six pattern buckets per field:
-//   E[b] = P3<<24 | P2<<18 | P1<<12 | P0<<6 | N
+// Prefilter.  Five 5-bit fields per byte value, five pattern buckets per field:
+//   E[b] = P3<<20 | P2<<15 | P1<<10 | P0<<5 | N
 //   N  : bucket k admits b as the byte BEFORE a match start (\b, ^ contexts; 0xFF = start of unit)
 //   Pj : bucket k admits b as byte j of a match
-//   acc' = ((acc << 6) | 0x3F) & E[b]          (the shift is a multiply-add: acc * 64 + 63)
+//   acc' = ((acc << 5) | 31) & E[b]            (the shift is a multiply-add: acc * 32 + 31)
 // After feeding byte p, (acc & F_HIT) != 0  <=>  some bucket admits a match starting at p-3
 // (a 5-byte window: previous byte + first four match bytes).  No false negatives.
-static const uint32_t F_BITS = 6, F_FILL = 0x3Fu, F_HIT = 0x3F000000u, F_BUCKETS = 6;
+// 25 bits leave room to advance TWO bytes per step in the scan kernel:
+//   acc'' = ((acc << 10) | 1023) & ((E[b0] << 5) | 31) & (E[b1] | F_HIT << 5)
+// keeps the first byte's candidate field in bits 25-29 and the second byte's in bits 20-24.
+static const uint32_t F_BITS = 5, F_FILL = 31u, F_HIT = 0x01F00000u, F_BUCKETS = 5;
 static const uint32_t F_LOOKBACK = 4;   // bytes fed before the first owned position
 static const uint32_t F_START_OFF = 3;  // candidate start = fed position - 3
 CF_HD uint32_t filter_step(uint32_t acc, uint32_t e) { return ((acc << F_BITS) | F_FILL) & e; }
