@@ -469,43 +469,95 @@ static int pattern_filter(const Prog& prog, const Classes& C, int pat, PatFilter
   return 0;
 }
 
+// Rough byte-frequency prior for JSON / prose payloads; only the RANKING of bucket layouts depends on
+// it (a bad prior costs prefilter candidates, never correctness).
+static const double* byte_prior() {
+  static double f[256];
+  static bool init = false;
+  if (init) return f;
+  for (int b = 0; b < 256; ++b) f[b] = b >= 0x80 ? 0.0004 : (b < 0x20 ? 0.0005 : 0.003);
+  const char* letters = "etaoinsrhdlcumfpgwybvkxjqz";
+  const double lf[26] = {.100, .072, .065, .060, .058, .056, .052, .050, .042, .034, .034, .026, .024,
+                         .021, .019, .017, .016, .015, .015, .012, .009, .006, .002, .001, .001, .001};
+  for (int i = 0; i < 26; ++i) { f[(uint8_t)letters[i]] = lf[i]; f[(uint8_t)(letters[i] - 32)] = lf[i] * 0.06; }
+  for (int d = '0'; d <= '9'; ++d) f[d] = 0.012;
+  f[' '] = 0.12; f['"'] = 0.04; f[','] = 0.02; f[':'] = 0.02; f['.'] = 0.01; f['_'] = 0.008; f['-'] = 0.005;
+  f['\n'] = 0.005; f[0xFF] = 0.0001;
+  init = true;
+  return f;
+}
+
 static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
   size_t n = pf.size();
   fo.bucket_of_pattern.assign(n, 0);
-  struct Bk { PatFilter f; std::vector<int> pats; };
-  std::vector<Bk> bks;
-  for (size_t i = 0; i < n; ++i) {
-    // merge exact duplicates of pos[0] first
-    bool merged = false;
-    for (auto& b : bks) {
-      if (memcmp(b.f.pos[0].w, pf[i].pos[0].w, sizeof(b.f.pos[0].w)) == 0 &&
-          memcmp(b.f.N.w, pf[i].N.w, sizeof(b.f.N.w)) == 0) {
-        for (int k = 0; k < NPOS; ++k) b.f.pos[k].merge(pf[i].pos[k]);
-        b.pats.push_back((int)i); merged = true; break;
-      }
-    }
-    if (!merged) { Bk b; b.f = pf[i]; b.pats.push_back((int)i); bks.push_back(b); }
-  }
-  auto cost = [](const PatFilter& f) {
-    // expected admit probability proxy: product of set sizes
-    double c = (double)f.N.count();
-    for (int k = 0; k < NPOS; ++k) c *= f.pos[k].count();
+  const double* prior = byte_prior();
+  auto mass = [&](const ByteSet& s) {
+    double m = 0;
+    for (int b = 0; b < 256; ++b) if (s.get(b)) m += prior[b];
+    return m;
+  };
+  // expected candidates per byte of one bucket: P(N) * prod P(pos_k) under independent bytes
+  auto cost = [&](const PatFilter& f) {
+    double c = mass(f.N);
+    for (int k = 0; k < NPOS; ++k) c *= mass(f.pos[k]);
     return c;
   };
+  auto merged = [](const PatFilter& a, const PatFilter& b) {
+    PatFilter m = a;
+    m.N.merge(b.N);
+    for (int k = 0; k < NPOS; ++k) m.pos[k].merge(b.pos[k]);
+    return m;
+  };
+  struct Bk { PatFilter f; std::vector<int> pats; };
+  std::vector<Bk> bks;
+  for (size_t i = 0; i < n; ++i) { Bk b; b.f = pf[i]; b.pats.push_back((int)i); bks.push_back(b); }
+  // greedy agglomeration ...
   while (bks.size() > cf::F_BUCKETS) {
     size_t bi = 0, bj = 1; double best = 1e300;
     for (size_t i = 0; i < bks.size(); ++i)
       for (size_t j = i + 1; j < bks.size(); ++j) {
-        PatFilter m = bks[i].f;
-        m.N.merge(bks[j].f.N);
-        for (int k = 0; k < NPOS; ++k) m.pos[k].merge(bks[j].f.pos[k]);
-        double d = cost(m) - cost(bks[i].f) - cost(bks[j].f);
+        double d = cost(merged(bks[i].f, bks[j].f)) - cost(bks[i].f) - cost(bks[j].f);
         if (d < best) { best = d; bi = i; bj = j; }
       }
-    bks[bi].f.N.merge(bks[bj].f.N);
-    for (int k = 0; k < NPOS; ++k) bks[bi].f.pos[k].merge(bks[bj].f.pos[k]);
+    bks[bi].f = merged(bks[bi].f, bks[bj].f);
     bks[bi].pats.insert(bks[bi].pats.end(), bks[bj].pats.begin(), bks[bj].pats.end());
     bks.erase(bks.begin() + bj);
+  }
+  // ... then single-pattern moves while they lower the total
+  auto rebuild = [&](Bk& b) {
+    b.f = PatFilter();
+    for (int p : b.pats) b.f = merged(b.f, pf[p]);
+  };
+  auto total = [&]() { double t = 0; for (auto& b : bks) if (!b.pats.empty()) t += cost(b.f); return t; };
+  const int rounds = n > 256 ? 2 : 16;   // bound compile time for very large rule sets
+  for (int round = 0; round < rounds; ++round) {
+    bool moved = false;
+    for (size_t from = 0; from < bks.size(); ++from)
+      for (size_t pi = 0; pi < bks[from].pats.size(); ++pi) {
+        int pat = bks[from].pats[pi];
+        double base = total();
+        size_t best_to = from; double best_t = base;
+        for (size_t to = 0; to < bks.size(); ++to) {
+          if (to == from) continue;
+          Bk sf = bks[from], st = bks[to];
+          bks[from].pats.erase(bks[from].pats.begin() + pi);
+          rebuild(bks[from]);
+          bks[to].pats.push_back(pat);
+          rebuild(bks[to]);
+          double t = total();
+          if (t < best_t * (1 - 1e-9)) { best_t = t; best_to = to; }
+          bks[from] = sf; bks[to] = st;
+        }
+        if (best_to != from) {
+          bks[from].pats.erase(bks[from].pats.begin() + pi);
+          rebuild(bks[from]);
+          bks[best_to].pats.push_back(pat);
+          rebuild(bks[best_to]);
+          moved = true;
+          --pi;
+        }
+      }
+    if (!moved) break;
   }
   memset(fo.E, 0, sizeof(fo.E));
   for (size_t k = 0; k < bks.size(); ++k) {

@@ -10,6 +10,7 @@ sys.path.insert(0, ".")
 from mcp_context_forge_b200 import engine, synth
 from oracle import hook_chain_ref as ref
 
+# usage: quick_scan_bench.py [units] [payload_bytes] [shape A|B|C]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 shape = sys.argv[3] if len(sys.argv) > 3 else "A"
