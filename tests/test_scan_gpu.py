@@ -116,3 +116,27 @@ def test_full_size_checksum_property():
     exp = oracle_bits(base)
     assert got1[:64] == exp
     assert all(got1[i] == exp[i % 64] for i in range(4096))
+
+
+def test_candidate_dense_input_overflows_queue():
+    """Every few bytes is a prefilter candidate (several million in one launch, more than the
+    candidate queue holds): the in-place verification path must give the same bitmaps."""
+    prog = default_program()
+    rng = random.Random(7)
+    words = ["kill", "bomb", "crap", "crud", "killer", "skill", "innovative", "suicid", "bombs", "kil", "k1ll",
+             "assault", "Kill yourself", "self-harm", "I hate", "innovativ"]
+    base = []
+    for s in range(16):
+        parts = []
+        n = 0
+        while n < 16000:
+            w = rng.choice(words)
+            parts.append(w)
+            n += len(w) + 1
+        base.append(" ".join(parts))
+    units = [base[i % 16] for i in range(2048)]
+    got = engine.scan_units(prog, units)
+    exp = oracle_bits(base)
+    assert all(got[i] == exp[i % 16] for i in range(2048))
+    cand, _ = engine.Context.get().scan_counters()
+    assert cand > (1 << 20)          # really did exceed the queue capacity
