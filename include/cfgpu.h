@@ -135,6 +135,8 @@ int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint6
 #define CF_TOON_UNSUPPORTED 6   /* beyond the device limits (nesting > 64, number > 3200 bits): caller must fail loudly */
 #define CF_TOON_REPORT_ERRORS 1u /* flags: keep encoding after the output outgrew the input so that VALUE/ATTR
                                    errors are still reported (needed for skip_on_error=False) */
+#define CF_TOON_PARSE_ONLY 4u    /* flags, diagnostic: only parse; status = 0 ok / 1 invalid JSON / 2 beyond limits,
+                                  * out_len = DOM node count (used by tools/toon_prof.py to time the parser alone) */
 /* device-resident (batch already uploaded); d_out has room for the batch's stream bytes */
 int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream);
 /* host buffers: upload + encode + download, synchronous */

@@ -215,7 +215,6 @@ struct ScanParams {
   uint32_t dfa_bytes;             // bytes needed to stage the DFA tables in shared memory (0 = too big)
   uint32_t dfa_trans_bytes, dfa_acc_bytes;
   uint32_t mulc;                  // 1024 (kept out of the instruction stream on purpose)
-  uint32_t dbg;                   // experiments: 1 = skip verification, 2 = no smem staging
 };
 
 // Verify one candidate start: run the anchored class DFA from `start` until it dies or reaches the
@@ -535,7 +534,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   if (ncand == 0) return;
   const uint32_t nq = ncand < P.qcap_cta ? ncand : P.qcap_cta;
   cf::DfaTables T = P.dfa;
-  if (P.dfa_bytes && P.dfa_bytes <= 0x10000u && !(P.dbg & 2)) {
+  if (P.dfa_bytes && P.dfa_bytes <= 0x10000u) {
     uint8_t* dst = reinterpret_cast<uint8_t*>(tbl);
     uint32_t off_ = 0;
     auto stage_tbl = [&](const void* src, uint32_t bytes) -> const void* {
@@ -557,9 +556,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   }
   uint32_t steps = 0;
   const unsigned long long* q = P.queue + (uint64_t)blockIdx.x * P.qcap_cta;
-  if (!(P.dbg & 1))
-    for (uint32_t i = lane * WARPS + warp; i < nq; i += WARPS * 32)   // spread over warps: less divergence
-      verify_candidate(P, T, q[i], steps);
+  for (uint32_t i = lane * WARPS + warp; i < nq; i += WARPS * 32)   // spread over warps: less divergence
+    verify_candidate(P, T, q[i], steps);
   for (int o = 16; o; o >>= 1) steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
   if (lane == 0 && steps) atomicAdd(&P.qstate[1], (unsigned long long)steps);
   if (tid == 0) atomicAdd(&P.qstate[0], (unsigned long long)ncand);
@@ -718,7 +716,7 @@ __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ st
   cfj::Big big;
   uint8_t digits[1240];
   uint32_t ol = 0;
-  if (flags & 4u) {   // experiment: parse only
+  if (flags & 4u) {   // CF_TOON_PARSE_ONLY (diagnostic): status = parse result, out_len = node count
     uint32_t cnt = 0;
     int pr = cfj::json_parse(stream + b, len, my, len / 2 + 4, &cnt);
     status[u] = pr; out_len[u] = cnt;
@@ -1013,7 +1011,6 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   P.dfa_trans_bytes = (uint32_t)p->search.trans_bytes;
   P.dfa_acc_bytes = (uint32_t)p->search.acc_bytes;
   P.mulc = 1024;
-  P.dbg = getenv("CF_DBG") ? (uint32_t)atoi(getenv("CF_DBG")) : 0;
   const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages);
   uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM
   if (grid > ntiles) grid = ntiles;

@@ -15,12 +15,6 @@
 #include "scan_core.h"
 #include "unicode_tables.h"
 
-#ifdef __CUDA_ARCH__
-#define CF_OPAQUE(v) asm volatile("" : "+r"(v))
-#else
-#define CF_OPAQUE(v) ((void)0)
-#endif
-
 namespace cfj {
 
 // ------------------------------------------------------------------------------------------------
@@ -71,12 +65,6 @@ static const int MAXD = 64;                // nesting depth handled on the devic
 enum : int { PARSE_OK = 0, PARSE_ERROR = 1, PARSE_UNSUPPORTED = 2 };
 
 CF_HD bool j_ws(uint32_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
-CF_HD int hexv_of(uint32_t c) {
-  if (c >= '0' && c <= '9') return (int)c - '0';
-  c |= 0x20;
-  if (c >= 'a' && c <= 'f') return (int)c - 'a' + 10;
-  return -1;
-}
 CF_HD int hexv(uint32_t c) {
   if (c >= '0' && c <= '9') return (int)c - '0';
   c |= 0x20;
