@@ -36,6 +36,20 @@ static __device__ const uint32_t WS_HI_D[] = {CFU_WS_HI};
 #define CFJ_TAB(name) name##_H
 #endif
 
+// ASCII classes for the plain-string fast path of parse_string
+enum : uint32_t { AC_STOP = 1 /* '"', '\\', control, non-ASCII */, AC_SPECIAL = 2 /* , : [ ] { } - */, AC_KEYCH = 4 /* [A-Za-z0-9_.] */ };
+#define CFJ_AC_ROW(b) \
+  ((uint8_t)((((b) < 0x20 || (b) >= 0x80 || (b) == '"' || (b) == '\\') ? 1 : 0) | \
+             (((b) == ',' || (b) == ':' || (b) == '[' || (b) == ']' || (b) == '{' || (b) == '}' || (b) == '-') ? 2 : 0) | \
+             ((((b) >= 'A' && (b) <= 'Z') || ((b) >= 'a' && (b) <= 'z') || ((b) >= '0' && (b) <= '9') || (b) == '_' || (b) == '.') ? 4 : 0)))
+#define CFJ_AC_8(b) CFJ_AC_ROW(b), CFJ_AC_ROW((b) + 1), CFJ_AC_ROW((b) + 2), CFJ_AC_ROW((b) + 3), CFJ_AC_ROW((b) + 4), CFJ_AC_ROW((b) + 5), CFJ_AC_ROW((b) + 6), CFJ_AC_ROW((b) + 7)
+#define CFJ_AC_64(b) CFJ_AC_8(b), CFJ_AC_8((b) + 8), CFJ_AC_8((b) + 16), CFJ_AC_8((b) + 24), CFJ_AC_8((b) + 32), CFJ_AC_8((b) + 40), CFJ_AC_8((b) + 48), CFJ_AC_8((b) + 56)
+#define CFJ_AC_ALL CFJ_AC_64(0), CFJ_AC_64(64), CFJ_AC_64(128), CFJ_AC_64(192)
+static const uint8_t ACLS_H[256] = {CFJ_AC_ALL};
+#ifdef __CUDACC__
+static __device__ const uint8_t ACLS_D[256] = {CFJ_AC_ALL};
+#endif
+
 CF_HD bool is_nd(uint32_t cp) {            // \d of a str pattern
   if (cp < 0x80) return cp >= '0' && cp <= '9';
   uint32_t lo = 0, hi = CFU_ND_COUNT;
@@ -121,6 +135,54 @@ struct StrProps {
 // Validate one JSON string starting at the opening quote; returns false on any error.  On success
 // *pos is just past the closing quote.  Hash (FNV-1a) is over the DECODED UTF-8 bytes.
 CF_HD bool parse_string(const uint8_t* s, uint32_t n, uint32_t* pos, uint32_t* flags, uint32_t* hash) {
+  // Fast path: the string is plain printable ASCII without escapes and does not start with a digit
+  // (so the number-like rules cannot apply).  Four bytes per step: the loads and class lookups of a
+  // step are independent, which is what a lone GPU thread needs (no speculation across the branch).
+  {
+    const uint32_t b = *pos + 1;
+    uint32_t q = b, h = 2166136261u, orb = 0, andb = 0xFF;
+    const uint8_t* T = CFJ_TAB(ACLS);
+    bool plain = false;
+    if (b < n && !(s[b] >= '0' && s[b] <= '9')) {
+      while (true) {
+        if (q + 4 <= n) {
+          const uint32_t c0 = s[q], c1 = s[q + 1], c2 = s[q + 2], c3 = s[q + 3];
+          const uint32_t k0 = T[c0], k1 = T[c1], k2 = T[c2], k3 = T[c3];
+          if (!((k0 | k1 | k2 | k3) & AC_STOP)) {
+            orb |= k0 | k1 | k2 | k3; andb &= k0 & k1 & k2 & k3;
+            h = (h ^ c0) * 16777619u; h = (h ^ c1) * 16777619u; h = (h ^ c2) * 16777619u; h = (h ^ c3) * 16777619u;
+            q += 4;
+            continue;
+          }
+        }
+        // tail: one byte at a time up to the stopping byte
+        while (q < n) {
+          const uint32_t c = s[q], k = T[c];
+          if (k & AC_STOP) { plain = (c == '"'); break; }
+          orb |= k; andb &= k; h = (h ^ c) * 16777619u; ++q;
+        }
+        break;
+      }
+    }
+    if (plain) {
+      const uint32_t count = q - b;
+      uint32_t f = 0;
+      if (count == 0) f = JF_Q;
+      else {
+        const uint32_t first = s[b], last = s[q - 1];
+        const bool reserved = (count == 4 && ((first == 'n' && s[b + 1] == 'u' && s[b + 2] == 'l' && s[b + 3] == 'l') ||
+                                              (first == 't' && s[b + 1] == 'r' && s[b + 2] == 'u' && s[b + 3] == 'e'))) ||
+                              (count == 5 && first == 'f' && s[b + 1] == 'a' && s[b + 2] == 'l' && s[b + 3] == 's' && s[b + 4] == 'e');
+        if (reserved || (orb & AC_SPECIAL) || first == ' ' || last == ' ') f |= JF_Q;   // ' ' is the only printable-ASCII str.isspace() char
+        const bool al = (first >= 'A' && first <= 'Z') || (first >= 'a' && first <= 'z') || first == '_';
+        if (al && (andb & AC_KEYCH) && !reserved) f |= JF_KEYOK;
+      }
+      *pos = q + 1;
+      *flags = f;
+      *hash = h;
+      return true;
+    }
+  }
   uint32_t p = *pos + 1, h = 2166136261u, fl = 0;
   StrProps sp_;
   sp_.init();
@@ -524,6 +586,22 @@ struct Out {
   uint32_t n, cap;
   bool over;
   CF_HD void put(uint32_t c) { if (n < cap) p[n++] = (uint8_t)c; else over = true; }
+  // copy a span of source bytes; the in-capacity case is unrolled so that a lone GPU thread has
+  // several independent loads in flight
+  CF_HD void put_span(const uint8_t* b, uint32_t len) {
+    if (n + len <= cap) {
+      uint8_t* d = p + n;
+      uint32_t i = 0;
+      for (; i + 4 <= len; i += 4) {
+        const uint8_t a0 = b[i], a1 = b[i + 1], a2 = b[i + 2], a3 = b[i + 3];
+        d[i] = a0; d[i + 1] = a1; d[i + 2] = a2; d[i + 3] = a3;
+      }
+      for (; i < len; ++i) d[i] = b[i];
+      n += len;
+    } else {
+      for (uint32_t i = 0; i < len; ++i) put(b[i]);
+    }
+  }
   CF_HD void puts(const char* z) { while (*z) put((uint8_t)*z++); }
   CF_HD void spaces(uint32_t k) { for (uint32_t i = 0; i < k; ++i) put(' '); }
   CF_HD void put_cp(uint32_t cp) {
@@ -571,7 +649,7 @@ CF_HD void emit_string(Ctx& c, const JNode& nd, bool force_quote) {
     // no escapes in the source: the decoded text IS the source bytes, and nothing in it needs a TOON
     // escape either (a raw '"' or '\' cannot occur unescaped in JSON)
     if (q) c.out.put('"');
-    for (const uint8_t* p = b; p < e; ++p) c.out.put(*p);
+    c.out.put_span(b, nd.len);
     if (q) c.out.put('"');
     return;
   }
@@ -596,7 +674,7 @@ CF_HD void emit_key(Ctx& c, const JNode& k, bool raw) {
   const uint8_t* b = c.s + k.off;
   const uint8_t* e = b + k.len;
   if (raw || (k.t & JF_KEYOK)) {
-    if (!(k.t & JF_ESC)) { for (const uint8_t* p = b; p < e; ++p) c.out.put(*p); return; }
+    if (!(k.t & JF_ESC)) { c.out.put_span(b, k.len); return; }
     StrIter it{b, e};
     while (!it.done()) c.out.put_cp(it.next());
     return;
@@ -726,7 +804,7 @@ CF_HD void emit_number(Ctx& c, const JNode& nd) {
     }
     if (fits) {
       if (dl == 1 && dg[0] == '0') { c.out.put('0'); return; }     // "-0" -> int 0
-      for (uint32_t i = 0; i < len; ++i) c.out.put(t[i]);
+      c.out.put_span(t, len);
       return;
     }
   } else if (!(nd.t & JF_EXP)) {
@@ -746,11 +824,11 @@ CF_HD void emit_number(Ctx& c, const JNode& nd) {
       if (nfrac == 0) {                                    // integral float -> str(int(x)); +-0.0 -> "0"
         if (int_zero) { c.out.put('0'); return; }
         if (neg) c.out.put('-');
-        for (uint32_t i = 0; i < dot; ++i) c.out.put(dg[i]);
+        c.out.put_span(dg, dot);
         return;
       }
       if (neg) c.out.put('-');
-      for (uint32_t i = 0; i < dot + 1 + nfrac; ++i) c.out.put(dg[i]);
+      c.out.put_span(dg, dot + 1 + nfrac);
       return;
     }
   }

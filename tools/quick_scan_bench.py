@@ -10,10 +10,11 @@ sys.path.insert(0, ".")
 from mcp_context_forge_b200 import engine, synth
 from oracle import hook_chain_ref as ref
 
-# usage: quick_scan_bench.py [units] [payload_bytes] [shape A|B|C]
+# usage: quick_scan_bench.py [units] [payload_bytes] [shape A|B|C] [hit_rate]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 shape = sys.argv[3] if len(sys.argv) > 3 else "A"
+hit = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 ctx = engine.Context.get()
 p = engine.Program()
 for pats in ref.DEFAULT_LEXICONS.values():
@@ -24,7 +25,7 @@ for w in ["innovative", "groundbreaking", "revolutionary"]:
 p.add_sub("crap", 0, "crud")
 p.add_sub("crud", 0, "yikes")
 p.compile(ctx)
-base = [synth.payload(shape, size, seed=s) for s in range(32)]
+base = [synth.payload(shape, size, seed=s, hit_rate=hit) for s in range(32)]
 units = [base[i % 32] for i in range(n)]
 stream, offs = engine.pack_units(units)
 print("stream bytes", len(stream), "units", n)

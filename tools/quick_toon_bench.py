@@ -9,8 +9,13 @@ from mcp_context_forge_b200.batching import GpuBatcher
 
 b = GpuBatcher.get()
 lib = b.ctx.lib
+# usage: quick_toon_bench.py [flags] [shape size n]...
 FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-for shape, size, n in (("A", 16384, 32768), ("A", 2048, 131072), ("B", 16384, 32768)):
+CASES = [("A", 16384, 32768), ("A", 2048, 131072), ("B", 16384, 32768)]
+if len(sys.argv) > 2:
+    a = sys.argv[2:]
+    CASES = [(a[i], int(a[i + 1]), int(a[i + 2])) for i in range(0, len(a), 3)]
+for shape, size, n in CASES:
     base = [synth.payload(shape, size, seed=s).encode() for s in range(64)]
     texts = [base[i % 64] for i in range(n)]
     stream, offs = engine.pack_units(texts)
