@@ -42,6 +42,10 @@ struct cf_ctx {
   uint32_t qcap = 1u << 20;
   void* d_toon_scratch = nullptr;   // DOM node arrays for toon_kernel (grown on demand)
   uint64_t toon_scratch_bytes = 0;
+  struct DevBuf { void* p = nullptr; size_t cap = 0; };
+  DevBuf tmp[8];                    // grow-only device scratch of the *_host entry points (no cudaMalloc per call)
+  void* h_stage = nullptr;          // pinned host staging for gathered results
+  size_t h_stage_bytes = 0;
   // optional per-launch timing of the dominant kernel (bench.py roofline): event pairs
   std::vector<cudaEvent_t> prof_ev;
   uint32_t prof_used = 0;
@@ -705,8 +709,12 @@ __global__ void sub_compact_kernel(const uint8_t* __restrict__ stream, const uin
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
                                                    uint32_t n_units, cfj::JNode* __restrict__ nodes, uint8_t* __restrict__ out,
-                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t flags) {
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t flags, uint32_t upw) {
+  // `upw` units per warp (lanes >= upw idle): small batches spread over more warps, so fewer unrelated
+  // state machines share (and serialise inside) a warp
+  const uint32_t lane = threadIdx.x & 31;
+  if (lane >= upw) return;
+  const uint32_t u = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * upw + lane;
   if (u >= n_units) return;
   const uint64_t b = offsets[u];
   const uint64_t len64 = offsets[u + 1] - b - 1;
@@ -733,8 +741,10 @@ __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ st
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) mask_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
                                                    cfj::JNode* __restrict__ nodes, uint32_t* __restrict__ idx, uint8_t* __restrict__ out,
-                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, int max_depth) {
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, int max_depth, uint32_t upw) {
+  const uint32_t lane = threadIdx.x & 31;
+  if (lane >= upw) return;
+  const uint32_t u = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * upw + lane;
   if (u >= n_units) return;
   const uint64_t b = offsets[u];
   const uint64_t len64 = offsets[u + 1] - b - 1;
@@ -751,13 +761,15 @@ __global__ void __launch_bounds__(64) mask_kernel(const uint8_t* __restrict__ st
   out_len[u] = st == cfm::MS_OK ? ol : 0;
 }
 
-__global__ void mask_compact_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ out_len,
-                                    const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out, uint32_t n_units) {
+// gather per-unit results (unit u at src + mul*offsets[u] + add*u, out_len[u] bytes) into one contiguous buffer
+__global__ void compact_kernel(const uint8_t* __restrict__ src, uint32_t mul, uint32_t add, const uint64_t* __restrict__ offsets,
+                               const uint32_t* __restrict__ out_len, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out,
+                               uint32_t n_units) {
   const uint32_t u = blockIdx.x;
   if (u >= n_units) return;
-  const uint8_t* src = arena + 5 * offsets[u] + 32ull * u;
+  const uint8_t* s = src + (uint64_t)mul * offsets[u] + (uint64_t)add * u;
   uint8_t* dst = out + out_off[u];
-  for (uint32_t i = threadIdx.x; i < out_len[u]; i += blockDim.x) dst[i] = src[i];
+  for (uint32_t i = threadIdx.x; i < out_len[u]; i += blockDim.x) dst[i] = s[i];
 }
 
 __global__ void classify_keys_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
@@ -837,6 +849,8 @@ void cf_shutdown(cf_ctx* ctx) {
   cudaFree(ctx->d_qstate);
   cudaFree(ctx->d_queue);
   cudaFree(ctx->d_toon_scratch);
+  for (auto& t : ctx->tmp) cudaFree(t.p);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;
 }
 
@@ -1123,6 +1137,34 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
   return rc;
 }
 
+static int dev_reserve(cf_ctx* ctx, cf_ctx::DevBuf& b, size_t need) {
+  if (need <= b.cap) return CF_OK;
+  cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+  const size_t c = need + need / 4 + 256;
+  CF_CUDA(ctx, cudaMalloc(&b.p, c));
+  b.cap = c;
+  return CF_OK;
+}
+static int stage_reserve(cf_ctx* ctx, size_t need) {
+  if (need <= ctx->h_stage_bytes) return CF_OK;
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+  const size_t c = need + need / 4 + 4096;
+  CF_CUDA(ctx, cudaHostAlloc(&ctx->h_stage, c, cudaHostAllocDefault));
+  ctx->h_stage_bytes = c;
+  return CF_OK;
+}
+// units per warp for the thread-per-unit JSON kernels: fill the GPU with warps first (about 12 resident
+// warps per SM at their register footprint), only then put several units into one warp
+static uint32_t units_per_warp(const cf_ctx* ctx, uint32_t n) {
+  const uint32_t warps = (uint32_t)ctx->sm_count * 12u;
+  uint32_t u = 1;
+  while (u < 32 && (n + u - 1) / u > warps) u <<= 1;
+  return u;
+}
+static uint32_t json_blocks(uint32_t n, uint32_t upw) { return ((n + upw - 1) / upw + 1) / 2; }   // two warps per block
+
 int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
   if (!ctx || !b || !b->n || !d_out || !d_out_len || !d_status) return CF_E_BADARG;
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -1135,14 +1177,9 @@ int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* 
     CF_CUDA(ctx, cudaMalloc(&ctx->d_toon_scratch, need + need / 4));
     ctx->toon_scratch_bytes = need + need / 4;
   }
-  // CF_TOON_SMEM (experiment knob): dynamic shared memory used only as an occupancy limiter.  Measured:
-  // capping occupancy does not help — the kernel is bound by intra-warp divergence, not by L1 misses.
-  static int toon_smem = -1;
-  if (toon_smem < 0) {
-    toon_smem = getenv("CF_TOON_SMEM") ? atoi(getenv("CF_TOON_SMEM")) : 0;
-    CF_CUDA(ctx, cudaFuncSetAttribute(toon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, toon_smem > 48 * 1024 ? toon_smem : 48 * 1024));
-  }
-  toon_kernel<<<(b->n + 63) / 64, 64, (size_t)toon_smem, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfj::JNode*)ctx->d_toon_scratch, d_out, d_out_len, d_status, flags);
+  const uint32_t upw = units_per_warp(ctx, b->n);
+  toon_kernel<<<json_blocks(b->n, upw), 64, 0, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfj::JNode*)ctx->d_toon_scratch, d_out, d_out_len,
+                                                     d_status, flags, upw);
   ctx->launches++;
   CF_CUDA(ctx, cudaGetLastError());
   return CF_OK;
@@ -1153,23 +1190,35 @@ int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream
   if (!out_stream || !out_len || !status) return CF_E_BADARG;
   int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
   if (rc) return rc;
-  uint8_t* d_out = nullptr;
-  uint32_t* d_len = nullptr;
-  int32_t* d_st = nullptr;
-  do {
-#define T_CUDA(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = CF_E_CUDA; break; } }
-    T_CUDA(cudaMalloc(&d_out, stream_bytes + 16));
-    T_CUDA(cudaMalloc(&d_len, (size_t)n_units * 4));
-    T_CUDA(cudaMalloc(&d_st, (size_t)n_units * 4));
-    rc = cf_toon(ctx, b, flags, d_out, d_len, d_st, nullptr);
-    if (rc) break;
-    T_CUDA(cudaMemcpy(out_len, d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-    T_CUDA(cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-    T_CUDA(cudaMemcpy(out_stream, d_out, stream_bytes, cudaMemcpyDeviceToHost));
-#undef T_CUDA
-  } while (0);
-  cudaFree(d_out); cudaFree(d_len); cudaFree(d_st);
-  return rc;
+  // device: encode in the input's layout, then gather the converted texts so that only they cross PCIe
+  if ((rc = dev_reserve(ctx, ctx->tmp[0], stream_bytes + 16))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[1], (size_t)n_units * 4))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[3], ((size_t)n_units + 1) * 8))) return rc;
+  uint8_t* d_out = (uint8_t*)ctx->tmp[0].p;
+  uint32_t* d_len = (uint32_t*)ctx->tmp[1].p;
+  int32_t* d_st = (int32_t*)ctx->tmp[2].p;
+  uint64_t* d_ooff = (uint64_t*)ctx->tmp[3].p;
+  rc = cf_toon(ctx, b, flags, d_out, d_len, d_st, nullptr);
+  if (rc) return rc;
+  CF_CUDA(ctx, cudaMemcpy(out_len, d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+  CF_CUDA(ctx, cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+  if (flags & CF_TOON_PARSE_ONLY) return CF_OK;
+  std::vector<uint64_t> ooff((size_t)n_units + 1);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_units; ++i) { ooff[i] = total; total += out_len[i]; }
+  ooff[n_units] = total;
+  if (!total) return CF_OK;
+  if ((rc = dev_reserve(ctx, ctx->tmp[4], total))) return rc;
+  if ((rc = stage_reserve(ctx, total))) return rc;
+  CF_CUDA(ctx, cudaMemcpy(d_ooff, ooff.data(), ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
+  compact_kernel<<<n_units, 128>>>(d_out, 1, 0, b->d_offsets, d_len, d_ooff, (uint8_t*)ctx->tmp[4].p, n_units);
+  ctx->launches++;
+  CF_CUDA(ctx, cudaGetLastError());
+  CF_CUDA(ctx, cudaMemcpy(ctx->h_stage, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n_units; ++i)
+    if (out_len[i]) memcpy(out_stream + offsets[i], (const uint8_t*)ctx->h_stage + ooff[i], out_len[i]);
+  return CF_OK;
 }
 
 int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
@@ -1186,41 +1235,40 @@ int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t strea
     CF_CUDA(ctx, cudaMalloc(&ctx->d_toon_scratch, need + need / 4));
     ctx->toon_scratch_bytes = need + need / 4;
   }
-  uint8_t *d_arena = nullptr, *d_out = nullptr;
-  uint32_t *d_idx = nullptr, *d_len = nullptr;
-  int32_t* d_st = nullptr;
-  uint64_t* d_ooff = nullptr;
+  if ((rc = dev_reserve(ctx, ctx->tmp[0], 5 * stream_bytes + 32ull * n_units + 64))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[1], (size_t)n_units * 4))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[3], ((size_t)n_units + 1) * 8))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->tmp[5], nnodes * 4))) return rc;
+  uint8_t* d_arena = (uint8_t*)ctx->tmp[0].p;
+  uint32_t* d_len = (uint32_t*)ctx->tmp[1].p;
+  int32_t* d_st = (int32_t*)ctx->tmp[2].p;
+  uint64_t* d_ooff = (uint64_t*)ctx->tmp[3].p;
+  uint32_t* d_idx = (uint32_t*)ctx->tmp[5].p;
   std::vector<uint32_t> lens(n_units);
-  do {
-#define M_CUDA(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = CF_E_CUDA; break; } }
-    M_CUDA(cudaMalloc(&d_arena, 5 * stream_bytes + 32ull * n_units + 64));
-    M_CUDA(cudaMalloc(&d_idx, nnodes * 4));
-    M_CUDA(cudaMalloc(&d_len, (size_t)n_units * 4));
-    M_CUDA(cudaMalloc(&d_st, (size_t)n_units * 4));
-    M_CUDA(cudaMalloc(&d_ooff, ((size_t)n_units + 1) * 8));
-    mask_kernel<<<(n_units + 63) / 64, 64>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, (cfj::JNode*)ctx->d_toon_scratch, d_idx, d_arena, d_len,
-                                             d_st, max_depth);
+  const uint32_t upw = units_per_warp(ctx, n_units);
+  mask_kernel<<<json_blocks(n_units, upw), 64>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, (cfj::JNode*)ctx->d_toon_scratch, d_idx, d_arena, d_len,
+                                                 d_st, max_depth, upw);
+  ctx->launches++;
+  CF_CUDA(ctx, cudaGetLastError());
+  CF_CUDA(ctx, cudaMemcpy(lens.data(), d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+  CF_CUDA(ctx, cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_units; ++i) { out_offsets[i] = total; total += lens[i]; }
+  out_offsets[n_units] = total;
+  if (out_needed) *out_needed = total;
+  if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; return CF_E_CAPACITY; }
+  if (total) {
+    if ((rc = dev_reserve(ctx, ctx->tmp[4], total))) return rc;
+    if ((rc = stage_reserve(ctx, total))) return rc;
+    CF_CUDA(ctx, cudaMemcpy(d_ooff, out_offsets, ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
+    compact_kernel<<<n_units, 128>>>(d_arena, 5, 32, b->d_offsets, d_len, d_ooff, (uint8_t*)ctx->tmp[4].p, n_units);
     ctx->launches++;
-    M_CUDA(cudaGetLastError());
-    M_CUDA(cudaMemcpy(lens.data(), d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-    M_CUDA(cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < n_units; ++i) { out_offsets[i] = total; total += lens[i]; }
-    out_offsets[n_units] = total;
-    if (out_needed) *out_needed = total;
-    if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; rc = CF_E_CAPACITY; break; }
-    if (total) {
-      M_CUDA(cudaMalloc(&d_out, total));
-      M_CUDA(cudaMemcpy(d_ooff, out_offsets, ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
-      mask_compact_kernel<<<n_units, 128>>>(d_arena, b->d_offsets, d_len, d_ooff, d_out, n_units);
-      ctx->launches++;
-      M_CUDA(cudaGetLastError());
-      M_CUDA(cudaMemcpy(out_bytes, d_out, total, cudaMemcpyDeviceToHost));
-    }
-#undef M_CUDA
-  } while (0);
-  cudaFree(d_arena); cudaFree(d_out); cudaFree(d_idx); cudaFree(d_len); cudaFree(d_st); cudaFree(d_ooff);
-  return rc;
+    CF_CUDA(ctx, cudaGetLastError());
+    CF_CUDA(ctx, cudaMemcpy(ctx->h_stage, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
+    memcpy(out_bytes, ctx->h_stage, total);
+  }
+  return CF_OK;
 }
 
 int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
@@ -1228,14 +1276,12 @@ int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint6
   if (!ctx || !b || !sensitive) return CF_E_BADARG;
   int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
   if (rc) return rc;
-  uint8_t* d = nullptr;
-  CF_CUDA(ctx, cudaMalloc(&d, n_units));
+  if ((rc = dev_reserve(ctx, ctx->tmp[6], n_units))) return rc;
+  uint8_t* d = (uint8_t*)ctx->tmp[6].p;
   classify_keys_kernel<<<(n_units + 127) / 128, 128>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, d);
   ctx->launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpy(sensitive, d, n_units, cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return CF_E_CUDA; }
+  CF_CUDA(ctx, cudaGetLastError());
+  CF_CUDA(ctx, cudaMemcpy(sensitive, d, n_units, cudaMemcpyDeviceToHost));
   return CF_OK;
 }
 

@@ -64,7 +64,7 @@ CF_HD bool is_pyspace(uint32_t cp) {       // str.isspace()
 // ------------------------------------------------------------------------------------------------
 // DOM
 // ------------------------------------------------------------------------------------------------
-struct JNode { uint32_t t, off, len, next; };
+struct alignas(16) JNode { uint32_t t, off, len, next; };   // one 128-bit load/store per node
 enum : uint32_t { J_NULL = 0, J_FALSE = 1, J_TRUE = 2, J_NUM = 3, J_STR = 4, J_ARR = 5, J_OBJ = 6, J_KEY = 7, J_TYPE = 0xF };
 enum : uint32_t { JF_ESC = 0x100, JF_NEG = 0x100, JF_FRAC = 0x200, JF_EXP = 0x400,
                   // string properties computed while the parser validates the string (one pass, no re-scan at emit time)
@@ -292,7 +292,14 @@ struct StrIter {
 CF_HD bool keys_equal(const uint8_t* s, const JNode& a, const JNode& b) {
   if (!((a.t | b.t) & JF_ESC)) {
     if (a.len != b.len) return false;
-    for (uint32_t i = 0; i < a.len; ++i) if (s[a.off + i] != s[b.off + i]) return false;
+    const uint8_t* x = s + a.off;
+    const uint8_t* y = s + b.off;
+    uint32_t i = 0;
+    for (; i + 4 <= a.len; i += 4) {    // independent loads, one branch per four bytes
+      const uint32_t d = (uint32_t)(x[i] ^ y[i]) | (uint32_t)(x[i + 1] ^ y[i + 1]) | (uint32_t)(x[i + 2] ^ y[i + 2]) | (uint32_t)(x[i + 3] ^ y[i + 3]);
+      if (d) return false;
+    }
+    for (; i < a.len; ++i) if (x[i] != y[i]) return false;
     return true;
   }
   StrIter ia{s + a.off, s + a.off + a.len}, ib{s + b.off, s + b.off + b.len};
@@ -303,10 +310,20 @@ CF_HD bool keys_equal(const uint8_t* s, const JNode& a, const JNode& b) {
 // Parse `s[0..n)` (a whole JSON document, surrounding whitespace allowed) into nodes[0..cap).
 // Token-at-a-time.  (A byte-at-a-time flat state machine was tried to cut warp divergence and measured
 // 2.4x SLOWER on B200 — profiles/README.md — so the straightforward form stays.)
+// All per-container running state (child count, last child, kind, the key hashes of the open objects)
+// lives in thread-local arrays: a read-after-write through the node array in HBM costs an L2 round
+// trip per token, local memory stays in L1.  Nodes are written once, when complete.
+static const uint32_t KH_CAP = 512;        // key hashes of all currently open objects (an object whose hashes did not fit -> slow dedupe)
 CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, uint32_t* out_count) {
   uint32_t pos = 0, nn = 0;
-  uint32_t st_node[MAXD], st_last[MAXD];
+  uint32_t st_node[MAXD], st_last[MAXD], st_len[MAXD], st_kh[MAXD];
+  uint32_t kh[KH_CAP];
+  uint32_t khn = 0;                 // used entries of kh
+  uint64_t khbad = 0;               // bit d: the object at depth d has keys whose hashes did not fit
+  uint64_t objbits = 0;             // bit d: the container at depth d is an object
   int sp = 0;
+  bool member = false;              // the value being parsed belongs to an object member
+  uint32_t member_hash = 0;
   enum { M_VALUE, M_KEY, M_AFTER } mode = M_VALUE;
   while (pos < n && j_ws(s[pos])) ++pos;
   while (true) {
@@ -320,34 +337,32 @@ CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, u
         uint32_t fl, h, p0 = pos;
         if (!parse_string(s, n, &pos, &fl, &h)) return PARSE_ERROR;
         nodes[nn++] = JNode{J_KEY | fl, p0 + 1, pos - p0 - 2, 0};
-        uint32_t cidx = st_node[sp - 1];
-        if (st_last[sp - 1]) nodes[st_last[sp - 1]].next = idx; else nodes[cidx].off = idx;
+        if (st_last[sp - 1]) nodes[st_last[sp - 1]].next = idx; else nodes[st_node[sp - 1]].off = idx;
         st_last[sp - 1] = idx;
-        nodes[cidx].len++;
+        st_len[sp - 1]++;
+        if (khn < KH_CAP) kh[khn++] = h; else khbad |= 1ull << (sp - 1);
         while (pos < n && j_ws(s[pos])) ++pos;
         if (pos >= n || s[pos] != ':') return PARSE_ERROR;
         ++pos;
         while (pos < n && j_ws(s[pos])) ++pos;
-        // the value node follows immediately; remember the key hash in its .next afterwards
-        nodes[nn].next = h;   // provisional slot (overwritten fields t/off/len are set by the value parse)
+        member = true;          // the value node follows immediately and carries the key hash in .next
+        member_hash = h;
         mode = M_VALUE;
-        // mark: value belongs to an object member
-        st_last[sp - 1] |= 0x80000000u;
         continue;
       }
-      bool member = sp > 0 && (st_last[sp - 1] & 0x80000000u);
-      uint32_t keep_next = member ? nodes[nn].next : 0;
-      if (member) st_last[sp - 1] &= 0x7FFFFFFFu;
-      else if (sp > 0) {   // array element: chain
-        uint32_t cidx = st_node[sp - 1];
-        if (st_last[sp - 1]) nodes[st_last[sp - 1]].next = idx; else nodes[cidx].off = idx;
+      const uint32_t keep_next = member ? member_hash : 0;
+      if (!member && sp > 0) {   // array element: chain
+        if (st_last[sp - 1]) nodes[st_last[sp - 1]].next = idx; else nodes[st_node[sp - 1]].off = idx;
         st_last[sp - 1] = idx;
-        nodes[cidx].len++;
+        st_len[sp - 1]++;
       }
+      member = false;
       if (c == '{' || c == '[') {
         if (sp >= MAXD) return PARSE_UNSUPPORTED;
         nodes[nn++] = JNode{c == '{' ? (uint32_t)J_OBJ : (uint32_t)J_ARR, 0, 0, keep_next};
-        st_node[sp] = idx; st_last[sp] = 0; ++sp;
+        st_node[sp] = idx; st_last[sp] = 0; st_len[sp] = 0; st_kh[sp] = khn;
+        if (c == '{') objbits |= 1ull << sp; else objbits &= ~(1ull << sp);
+        ++sp;
         ++pos;
         while (pos < n && j_ws(s[pos])) ++pos;
         if (pos < n && s[pos] == (c == '{' ? '}' : ']')) { ++pos; --sp; mode = M_AFTER; }
@@ -394,8 +409,7 @@ CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, u
       return PARSE_OK;
     }
     if (pos >= n) return PARSE_ERROR;
-    uint32_t cidx = st_node[sp - 1];
-    bool is_obj = (nodes[cidx].t & J_TYPE) == J_OBJ;
+    const bool is_obj = (objbits >> (sp - 1)) & 1;
     uint32_t c = s[pos];
     if (c == ',') {
       ++pos;
@@ -406,25 +420,39 @@ CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, u
     if (c != (is_obj ? '}' : ']')) return PARSE_ERROR;
     ++pos;
     --sp;
-    if (is_obj && nodes[cidx].len > 1) {
-      // duplicate keys: the last value wins, the first position stays (Python dict / orjson)
-      uint32_t prev = nodes[cidx].off;
-      for (uint32_t k = nodes[prev].next; k;) {
-        uint32_t nxt = nodes[k].next;
-        bool dup = false;
-        for (uint32_t i = nodes[cidx].off; i != k; i = nodes[i].next)
-          if (nodes[i + 1].next == nodes[k + 1].next && keys_equal(s, nodes[i], nodes[k])) {
-            uint32_t hsh = nodes[i + 1].next;
-            nodes[i + 1] = nodes[k + 1];
-            nodes[i + 1].next = hsh;
-            dup = true;
-            break;
-          }
-        if (dup) { nodes[prev].next = nxt; nodes[cidx].len--; }
-        else prev = k;
-        k = nxt;
+    const uint32_t cidx = st_node[sp];
+    uint32_t clen = st_len[sp];
+    if (is_obj) {
+      // duplicate keys: the last value wins, the first position stays (Python dict / orjson).
+      // Cheap screen on the hashes held in local memory; the node walk only runs when two hashes collide.
+      const uint32_t kb = st_kh[sp];
+      bool maybe_dup = (khbad >> sp) & 1;
+      khbad &= ~(1ull << sp);
+      if (!maybe_dup)
+        for (uint32_t i = kb + 1; i < khn && !maybe_dup; ++i)
+          for (uint32_t j = kb; j < i; ++j) if (kh[j] == kh[i]) { maybe_dup = true; break; }
+      khn = kb;
+      if (maybe_dup && clen > 1) {
+        const uint32_t first = nodes[cidx].off;   // stored when the first key arrived
+        uint32_t prev = first;
+        for (uint32_t k = nodes[prev].next; k;) {
+          uint32_t nxt = nodes[k].next;
+          bool dup = false;
+          for (uint32_t i = first; i != k; i = nodes[i].next)
+            if (nodes[i + 1].next == nodes[k + 1].next && keys_equal(s, nodes[i], nodes[k])) {
+              uint32_t hsh = nodes[i + 1].next;
+              nodes[i + 1] = nodes[k + 1];
+              nodes[i + 1].next = hsh;
+              dup = true;
+              break;
+            }
+          if (dup) { nodes[prev].next = nxt; clen--; }
+          else prev = k;
+          k = nxt;
+        }
       }
     }
+    nodes[cidx].len = clen;
     mode = M_AFTER;
   }
 }
@@ -866,26 +894,38 @@ CF_HD uint32_t find_member_hint(const Ctx& c, uint32_t obj, uint32_t k, uint32_t
   return find_member(c, obj, k);
 }
 
-enum : int { COL_YES = 1, COL_NO = 0, COL_CRASH = -1 };
-// toon.py:456-511 called on `arr` (non-empty); `checked` = caller already verified all elements are dicts
+enum : int { COL_YES = 1, COL_YES_ALIGNED = 2, COL_NO = 0, COL_CRASH = -1 };
+// toon.py:456-511 called on `arr` (non-empty).  COL_YES_ALIGNED: additionally every row lists the keys in
+// the first row's order, so the emitter can walk the members without looking anything up.
+// Evaluation order matters for parity: a non-dict row raises only if no earlier row already returned None.
 CF_HD int columnar_check(const Ctx& c, uint32_t arr) {
   const JNode* N = c.nodes;
-  uint32_t first = N[arr].off;
-  if ((N[first].t & J_TYPE) != J_OBJ) return COL_CRASH;
-  if (N[first].len == 0) return COL_NO;
-  for (uint32_t x = N[first].next; x; x = N[x].next) {
-    if ((N[x].t & J_TYPE) != J_OBJ) return COL_CRASH;
-    if (N[x].len != N[first].len) return COL_NO;
-    uint32_t cur = N[x].off;
-    for (uint32_t k = N[first].off; k; k = N[k].next) if (!find_member_hint(c, x, k, &cur)) return COL_NO;
+  const uint32_t first = N[arr].off;
+  const JNode f = N[first];
+  if ((f.t & J_TYPE) != J_OBJ) return COL_CRASH;
+  if (f.len == 0) return COL_NO;
+  bool aligned = true, simple = true;
+  for (uint32_t k = f.off; k; k = N[k].next) if (!is_simple(N[k + 1].t)) simple = false;
+  for (uint32_t x = f.next; x; ) {
+    const JNode r = N[x];
+    if ((r.t & J_TYPE) != J_OBJ) return COL_CRASH;
+    if (r.len != f.len) return COL_NO;
+    uint32_t cur = r.off;
+    for (uint32_t k = f.off; k; k = N[k].next) {
+      const uint32_t before = cur;
+      const uint32_t v = find_member_hint(c, x, k, &cur);
+      if (!v) return COL_NO;
+      if (v != before + 1) aligned = false;
+      if (!is_simple(N[v].t)) simple = false;
+    }
+    x = r.next;
   }
-  for (uint32_t x = first; x; x = N[x].next)
-    for (uint32_t k = N[x].off; k; k = N[k].next) if (!is_simple(N[k + 1].t)) return COL_NO;
-  return COL_YES;
+  if (!simple) return COL_NO;
+  return aligned ? COL_YES_ALIGNED : COL_YES;
 }
 
 // "[n]{k1,k2}:" then one row per element at `row_pre` spaces
-CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre) {
+CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre, bool aligned) {
   const JNode* N = c.nodes;
   uint32_t first = N[arr].off;
   c.out.put('['); c.out.put_uint(N[arr].len); c.out.put(']'); c.out.put('{');
@@ -895,6 +935,14 @@ CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre) {
   for (uint32_t x = first; x && !c.err && !(c.out.over && c.stop_on_over); x = N[x].next) {
     newline(c, row_pre);
     bool f1 = true;
+    if (aligned) {
+      for (uint32_t m = N[x].off; m; m = N[m].next) {
+        if (!f1) c.out.put(',');
+        f1 = false;
+        emit_prim(c, m + 1);
+      }
+      continue;
+    }
     uint32_t cur = N[x].off;
     for (uint32_t k = N[first].off; k; k = N[k].next) {
       if (!f1) c.out.put(',');
@@ -919,7 +967,10 @@ CF_HD bool begin_array(Ctx& c, uint32_t arr, uint32_t pre, uint32_t indent, Fram
     if (k != J_OBJ) all_obj = false;
     if (k == J_OBJ || k == J_ARR) all_simple = false;
   }
-  if (all_obj && columnar_check(c, arr) == COL_YES) { emit_columnar(c, arr, pre + 2); return false; }
+  if (all_obj) {
+    const int cc = columnar_check(c, arr);
+    if (cc >= COL_YES) { emit_columnar(c, arr, pre + 2, cc == COL_YES_ALIGNED); return false; }
+  }
   c.out.put('['); c.out.put_uint(n); c.out.put(']'); c.out.put(':');
   if (all_simple) {
     c.out.put(' ');
@@ -980,7 +1031,7 @@ CF_HD void toon_emit(Ctx& c, uint32_t root) {
         if (i == 0) {
           int cc = columnar_check(c, v);
           if (cc == COL_CRASH) { c.err = TS_ATTR_ERROR; break; }
-          if (cc == COL_YES) { emit_columnar(c, v, pre + fi + 2); continue; }
+          if (cc >= COL_YES) { emit_columnar(c, v, pre + fi + 2, cc == COL_YES_ALIGNED); continue; }
         }
         c.out.put(':');
         newline(c, pre + fi + 2);

@@ -113,3 +113,33 @@ def test_strict_json_rejections_and_edge_cases():
         assert st == 0 and got == exp, (t, got)
     deep = "[" * 70 + "]" * 70
     assert hs.toon_host(deep, unlimited=True)[0] == 6          # deeper than the device handles: reported, never guessed
+
+
+def test_duplicate_keys_last_wins_small_and_huge_objects():
+    """Duplicate keys keep the first position and the last value (dict semantics of orjson.loads), for
+    small objects (hash screen in thread-local memory) and for objects with more keys than the screen
+    holds (falls back to the node walk), nested inside each other."""
+    rng = random.Random(3)
+
+    def obj_text(nkeys, ndup, depth):
+        keys = [f"k{i}" for i in range(nkeys)]
+        items = [(k, rng.randint(0, 999)) for k in keys]
+        for _ in range(ndup):
+            items.insert(rng.randint(1, len(items)), (rng.choice(keys), rng.randint(1000, 1999)))
+        parts = []
+        for j, (k, v) in enumerate(items):
+            if depth and j % 97 == 5:
+                parts.append(f'"{k}":' + obj_text(rng.choice([3, 8, 40]), rng.randint(0, 3), depth - 1))
+            else:
+                parts.append(f'"{k}":{v}')
+        return "{" + ",".join(parts) + "}"
+
+    for nkeys, ndup in ((2, 1), (6, 2), (50, 5), (511, 3), (512, 2), (513, 2), (700, 9), (1500, 4)):
+        text = obj_text(nkeys, ndup, 2)
+        exp = toon_ref.encode(toon_ref.loads_strict(text))
+        st, got = hs.toon_host(text, unlimited=True)
+        assert st == 0 and got == exp, (nkeys, ndup)
+    # escaped vs raw spelling of the same key are duplicates too
+    text = '{"a\\u0062c": 1, "x": 2, "abc": 3}'
+    st, got = hs.toon_host(text, unlimited=True)
+    assert st == 0 and got == toon_ref.encode(toon_ref.loads_strict(text)) == "abc: 3\nx: 2"

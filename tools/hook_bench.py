@@ -75,7 +75,7 @@ def main():
         out = {"requests_per_wave": n}
         for name, hook, payloads in (("prompt_pre_fetch 2 KiB (harmful+deny+regex_filter)", "prompt_pre_fetch", pre),
                                      ("tool_post_invoke 16 KiB JSON (harmful+regex_filter+toon)", "tool_post_invoke", post)):
-            loop.run_until_complete(wave(hook, payloads[:64]))      # warm-up (compiles, buffers)
+            loop.run_until_complete(wave(hook, payloads))           # warm-up at full size (compiles, buffer growth)
             b = GpuBatcher.get()
             l0 = b.launches
             prof = None
