@@ -21,6 +21,10 @@
  *   cf_toon_host
  *       -> `orjson.loads` + `toon.encode` + "only if smaller" of `_process_content_item`:
  *          plugins/toon_encoder/toon_encoder.py:277-303, plugins/toon_encoder/toon.py:82-565
+ *   cf_json_index / cf_json_index_host
+ *       -> no single reference function: the shared JSON structural index SURVEY.md §8(f)-2 asks for —
+ *          what `orjson.loads` (toon_encoder.py:281), `serde_json::from_slice` (lib.rs:353) and the
+ *          string walk `_iter_strings` (harmful_content_detector.py:110-139) each recompute per payload
  *
  * Conventions: every function returns CF_OK (0) or a negative CF_E_* code and never throws.
  * All buffers are caller-owned.  A cf_ctx belongs to one device; calls on one ctx must be
@@ -122,6 +126,20 @@ int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t strea
  * object-level entry points mask_sensitive_data / mask_sensitive_headers (lib.rs:307-344). */
 int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
                           uint32_t n_units, uint8_t* sensitive);
+
+/* ---------------- JSON structural index (reusable op) ---------------- */
+/* Per unit (one JSON text), in text order: the positions of every structural character { } [ ] : , outside
+ * strings, every string's opening and closing quote (a quote preceded by an odd-length run of backslashes is
+ * not a quote), and the first byte of every other run of non-whitespace bytes outside strings (scalars).
+ * Tokens of unit i are tokens[offsets[i] .. offsets[i] + (counts[i] & 0x7FFFFFFF)) — the token buffer is indexed
+ * like the stream and needs `stream_bytes` entries; counts[i] bit 31 = the text ends inside a string.
+ * With CF_INDEX_CLASSIFY each token also carries `aux`: strings are validated (escapes, strict UTF-8, control
+ * characters) and get their emit-time predicates + hash, scalars their kind/flags/length; 0xFFFFFFFF = invalid. */
+typedef struct cf_json_token { uint32_t pos; /* byte offset in the unit; bit 31 = closing quote */ uint32_t aux; } cf_json_token;
+#define CF_INDEX_CLASSIFY 1u
+int cf_json_index(cf_ctx* ctx, cf_batch* b, uint32_t flags, cf_json_token* d_tokens, uint32_t* d_counts, void* cuda_stream);
+int cf_json_index_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
+                       uint32_t n_units, cf_json_token* tokens, uint32_t* counts);
 
 /* ---------------- stage 4: toon_encoder (JSON text -> TOON text) ---------------- */
 /* Per unit (one JSON text): orjson.loads + toon.encode + "keep only if strictly smaller"

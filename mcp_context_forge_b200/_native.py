@@ -52,6 +52,8 @@ _SIGS = {
     "cf_classify_keys_host": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "cf_toon": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_toon_host": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "cf_json_index": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "cf_json_index_host": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p]),
     "cf_kernel_launches": (c_uint64, [c_void_p]),
     "cf_scan_counters": (c_int, [c_void_p, c_void_p]),
     "cf_profile_begin": (c_int, [c_void_p, c_uint32]),

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "cf_host.h"
+#include "json_index.h"
 #include "json_mask.h"
 #include "json_toon.h"
 #include "scan_core.h"
@@ -44,6 +45,7 @@ struct cf_ctx {
   uint64_t toon_scratch_bytes = 0;
   struct DevBuf { void* p = nullptr; size_t cap = 0; };
   DevBuf tmp[8];                    // grow-only device scratch of the *_host entry points (no cudaMalloc per call)
+  DevBuf d_tok, d_ntok;             // structural index of the current batch (json_index_kernel)
   void* h_stage = nullptr;          // pinned host staging for gathered results
   size_t h_stage_bytes = 0;
   // optional per-launch timing of the dominant kernel (bench.py roofline): event pairs
@@ -703,15 +705,86 @@ __global__ void sub_compact_kernel(const uint8_t* __restrict__ stream, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// toon_encoder: JSON text -> TOON text, one unit per thread (csrc/json_toon.h holds the algorithm,
-// shared verbatim with the CPU unit tests).  Output for unit i goes to out + offsets[i]; a conversion
-// is only produced when it is strictly smaller than the input (plugins/toon_encoder/toon_encoder.py:295-303).
+// JSON structural index (csrc/json_index.h), one WARP per unit:
+//   stage 1   one ballot per byte class and 32 bytes (bytes prefetched eight chunks ahead): escape parity,
+//             in-string mask by prefix XOR, structural characters, scalar starts -> token positions
+//   stage 1b  (CF_INDEX_CLASSIFY) lane-parallel over the tokens: strings validated + their predicates/hash,
+//             scalars validated — the same functions the sequential parser uses
+// Measured as a front end of the TOON / masking kernels (index kernel + token-driven DOM build per lane)
+// it LOSES to the sequential per-lane parser on B200 at large batches (15.8 vs 10.1 ms for 32 768 x 16 KiB:
+// stage 1b is issue-bound at ~12 warp-instructions per byte and the tokens triple the memory traffic), so
+// those kernels keep json_parse; the index stands alone as a reusable op (string extraction, length
+// guards) and as the first stage of the token-parallel design the next round needs.
 // ------------------------------------------------------------------------------------------------
+static const uint32_t IDX_AHEAD = 8;     // chunks of 32 bytes in flight per warp
+__device__ __forceinline__ uint32_t warp_index(const uint8_t* __restrict__ s, uint32_t n, cfx::Tok* __restrict__ tk, bool* unterminated,
+                                               uint32_t lane) {
+  cfx::IndexCarry cy;
+  cy.init();
+  uint32_t nt = 0;
+  const uint32_t below = (1u << lane) - 1u;
+  for (uint32_t base0 = 0; base0 < n; base0 += 32 * IDX_AHEAD) {
+    uint32_t cs[IDX_AHEAD];
+#pragma unroll
+    for (uint32_t k = 0; k < IDX_AHEAD; ++k) {
+      const uint32_t p = base0 + 32 * k + lane;
+      cs[k] = p < n ? (uint32_t)s[p] : (uint32_t)' ';
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < IDX_AHEAD; ++k) {
+      const uint32_t base = base0 + 32 * k;
+      if (base >= n) break;
+      const uint32_t c = cs[k];
+      const uint32_t bs = __ballot_sync(0xFFFFFFFFu, c == '\\');
+      const uint32_t qm = __ballot_sync(0xFFFFFFFFu, c == '"');
+      const uint32_t st = __ballot_sync(0xFFFFFFFFu, cfx::is_structural(c));
+      const uint32_t ws = __ballot_sync(0xFFFFFFFFu, cfj::j_ws(c));
+      uint32_t esc = 0;
+      if (bs | cy.bs_parity) {
+        esc = __ballot_sync(0xFFFFFFFFu, cfx::escaped_bit(bs, lane, cy.bs_parity) != 0);
+        cy.bs_parity = cfx::next_bs_parity(bs, cy.bs_parity);
+      }
+      uint32_t close;
+      const uint32_t tm = cfx::index_chunk(qm & ~esc, st, ws, cy, &close);
+      if ((tm >> lane) & 1u) {
+        cfx::Tok t;
+        t.pos = (base + lane) | (((close >> lane) & 1u) ? cfx::T_CLOSE : 0u);
+        t.aux = 0;
+        tk[nt + __popc(tm & below)] = t;
+      }
+      nt += __popc(tm);
+    }
+  }
+  *unterminated = cy.in_string != 0;
+  return nt;
+}
+
+static const uint32_t NTOK_UNTERMINATED = 0x80000000u;
+// tokens of unit u at toks + offsets[u] (capacity len + 1: offsets count one terminator per unit); ntok[u] = count | flag
+__global__ void __launch_bounds__(128) json_index_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
+                                                          cfx::Tok* __restrict__ toks, uint32_t* __restrict__ ntok, uint64_t max_len,
+                                                          uint32_t flags) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n_units) return;
+  const uint64_t b = offsets[u];
+  const uint64_t len64 = offsets[u + 1] - b - 1;
+  if (len64 > max_len) { if (lane == 0) ntok[u] = 0; return; }
+  const uint32_t len = (uint32_t)len64;
+  cfx::Tok* tk = toks + b;
+  bool unt;
+  const uint32_t nt = warp_index(stream + b, len, tk, &unt, lane);
+  __syncwarp();
+  if (flags & CF_INDEX_CLASSIFY)
+    for (uint32_t t = lane; t < nt; t += 32) tk[t].aux = cfx::classify_token(stream + b, len, tk[t].pos);
+  if (lane == 0) ntok[u] = nt | (unt ? NTOK_UNTERMINATED : 0u);
+}
+
+// toon_encoder: output for unit i goes to out + offsets[i]; a conversion is only produced when it is strictly
+// smaller than the input (plugins/toon_encoder/toon_encoder.py:295-303).
 __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
                                                    uint32_t n_units, cfj::JNode* __restrict__ nodes, uint8_t* __restrict__ out,
                                                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t flags, uint32_t upw) {
-  // `upw` units per warp (lanes >= upw idle): small batches spread over more warps, so fewer unrelated
-  // state machines share (and serialise inside) a warp
   const uint32_t lane = threadIdx.x & 31;
   if (lane >= upw) return;
   const uint32_t u = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * upw + lane;
@@ -721,24 +794,22 @@ __global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ st
   if (len64 > 0x7FFFFFFFull) { status[u] = cfj::TS_UNSUPPORTED; out_len[u] = 0; return; }
   const uint32_t len = (uint32_t)len64;
   cfj::JNode* my = nodes + (b >> 1) + 4ull * u;
-  cfj::Big big;
-  uint8_t digits[1240];
-  uint32_t ol = 0;
-  if (flags & 4u) {   // CF_TOON_PARSE_ONLY (diagnostic): status = parse result, out_len = node count
+  if (flags & CF_TOON_PARSE_ONLY) {
     uint32_t cnt = 0;
-    int pr = cfj::json_parse(stream + b, len, my, len / 2 + 4, &cnt);
+    const int pr = cfj::json_parse(stream + b, len, my, len / 2 + 4, &cnt);
     status[u] = pr; out_len[u] = cnt;
     return;
   }
-  int st = cfj::toon_process(stream + b, len, my, len / 2 + 4, out + b, len ? len - 1 : 0, &ol, &big, digits, sizeof(digits), (flags & 1u) == 0);
+  cfj::Big big;
+  uint8_t digits[1240];
+  uint32_t ol = 0;
+  const int st = cfj::toon_process(stream + b, len, my, len / 2 + 4, out + b, len ? len - 1 : 0, &ol, &big, digits, sizeof(digits), (flags & 1u) == 0);
   status[u] = st;
   out_len[u] = st == cfj::TS_CONVERTED ? ol : 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// request_logging_masking: mask_sensitive_json_bytes per unit (csrc/json_mask.h), one unit per thread,
-// plus a key classifier kernel for the object-level entry points of the drop-in module.
-// ------------------------------------------------------------------------------------------------
+// request_logging_masking: mask_sensitive_json_bytes per unit (csrc/json_mask.h), plus a key classifier
+// kernel for the object-level entry points of the drop-in module.
 __global__ void __launch_bounds__(64) mask_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
                                                    cfj::JNode* __restrict__ nodes, uint32_t* __restrict__ idx, uint8_t* __restrict__ out,
                                                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, int max_depth, uint32_t upw) {
@@ -756,7 +827,7 @@ __global__ void __launch_bounds__(64) mask_kernel(const uint8_t* __restrict__ st
   uint8_t digits[1240];
   cfm::NumWork w{&big, &big, digits, (uint32_t)sizeof(digits)};
   uint32_t ol = 0;
-  int st = cfm::mask_process(stream + b, len, my, len / 2 + 4, myidx, len / 2 + 4, out + 5 * b + 32ull * u, 5 * len + 32, &ol, max_depth, w);
+  const int st = cfm::mask_process(stream + b, len, my, len / 2 + 4, myidx, len / 2 + 4, out + 5 * b + 32ull * u, 5 * len + 32, &ol, max_depth, w);
   status[u] = st;
   out_len[u] = st == cfm::MS_OK ? ol : 0;
 }
@@ -850,6 +921,7 @@ void cf_shutdown(cf_ctx* ctx) {
   cudaFree(ctx->d_queue);
   cudaFree(ctx->d_toon_scratch);
   for (auto& t : ctx->tmp) cudaFree(t.p);
+  cudaFree(ctx->d_tok.p); cudaFree(ctx->d_ntok.p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;
 }
@@ -1164,6 +1236,29 @@ static uint32_t units_per_warp(const cf_ctx* ctx, uint32_t n) {
   return u;
 }
 static uint32_t json_blocks(uint32_t n, uint32_t upw) { return ((n + upw - 1) / upw + 1) / 2; }   // two warps per block
+int cf_json_index(cf_ctx* ctx, cf_batch* b, uint32_t flags, cf_json_token* d_tokens, uint32_t* d_counts, void* cuda_stream) {
+  if (!ctx || !b || !d_tokens || !d_counts) return CF_E_BADARG;
+  if (b->n == 0) return CF_OK;
+  static_assert(sizeof(cf_json_token) == sizeof(cfx::Tok), "token layout");
+  json_index_kernel<<<(b->n + 3) / 4, 128, 0, (cudaStream_t)cuda_stream>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfx::Tok*)d_tokens, d_counts,
+                                                                            0x7FFFFFFFull, flags);
+  ctx->launches++;
+  CF_CUDA(ctx, cudaGetLastError());
+  return CF_OK;
+}
+
+int cf_json_index_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
+                       uint32_t n_units, cf_json_token* tokens, uint32_t* counts) {
+  if (!ctx || !b || !tokens || !counts) return CF_E_BADARG;
+  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  if (rc) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_tok, (size_t)(stream_bytes + 64) * sizeof(cfx::Tok)))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_ntok, (size_t)(n_units + 1) * 4))) return rc;
+  if ((rc = cf_json_index(ctx, b, flags, (cf_json_token*)ctx->d_tok.p, (uint32_t*)ctx->d_ntok.p, nullptr))) return rc;
+  CF_CUDA(ctx, cudaMemcpy(counts, ctx->d_ntok.p, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+  CF_CUDA(ctx, cudaMemcpy(tokens, ctx->d_tok.p, (size_t)stream_bytes * sizeof(cfx::Tok), cudaMemcpyDeviceToHost));
+  return CF_OK;
+}
 
 int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
   if (!ctx || !b || !b->n || !d_out || !d_out_len || !d_status) return CF_E_BADARG;

@@ -418,11 +418,20 @@ CF_HD int mask_emit(const uint8_t* s, const JNode* N, Out& o, int max_depth, uin
   return err;
 }
 
+CF_HD int mask_finish(int pr, const uint8_t* s, const JNode* nodes, uint32_t* idx, uint32_t idx_cap, uint8_t* out, uint32_t out_cap,
+                      uint32_t* out_len, int max_depth, NumWork& w);
+
 // Whole per-unit pipeline: mask_sensitive_json_bytes(payload, max_depth).
 CF_HD int mask_process(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t node_cap, uint32_t* idx, uint32_t idx_cap, uint8_t* out,
                        uint32_t out_cap, uint32_t* out_len, int max_depth, NumWork& w) {
   uint32_t count = 0;
   int pr = cfj::json_parse(s, n, nodes, node_cap, &count);
+  return mask_finish(pr, s, nodes, idx, idx_cap, out, out_cap, out_len, max_depth, w);
+}
+
+// the part after the parse (pr = PARSE_* of whichever parser built `nodes`)
+CF_HD int mask_finish(int pr, const uint8_t* s, const JNode* nodes, uint32_t* idx, uint32_t idx_cap, uint8_t* out, uint32_t out_cap,
+                      uint32_t* out_len, int max_depth, NumWork& w) {
   if (pr == cfj::PARSE_ERROR) return MS_PARSE_ERROR;
   if (pr == cfj::PARSE_UNSUPPORTED) return MS_UNSUPPORTED;
   Out o;

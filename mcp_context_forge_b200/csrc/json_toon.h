@@ -307,6 +307,28 @@ CF_HD bool keys_equal(const uint8_t* s, const JNode& a, const JNode& b) {
   return ia.done() && ib.done();
 }
 
+// JSON number grammar from *pos (at '-' or a digit); on success *pos is just past it and *fl holds JF_NEG/FRAC/EXP.
+CF_HD bool scan_number(const uint8_t* s, uint32_t n, uint32_t* ppos, uint32_t* pfl) {
+  uint32_t pos = *ppos, fl = 0;
+  if (s[pos] == '-') { fl |= JF_NEG; ++pos; if (pos >= n) return false; }
+  if (s[pos] == '0') ++pos;
+  else if (s[pos] >= '1' && s[pos] <= '9') { while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos; }
+  else return false;
+  if (pos < n && s[pos] == '.') {
+    fl |= JF_FRAC; ++pos;
+    if (pos >= n || s[pos] < '0' || s[pos] > '9') return false;
+    while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos;
+  }
+  if (pos < n && (s[pos] == 'e' || s[pos] == 'E')) {
+    fl |= JF_EXP; ++pos;
+    if (pos < n && (s[pos] == '+' || s[pos] == '-')) ++pos;
+    if (pos >= n || s[pos] < '0' || s[pos] > '9') return false;
+    while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos;
+  }
+  *ppos = pos; *pfl = fl;
+  return true;
+}
+
 // Parse `s[0..n)` (a whole JSON document, surrounding whitespace allowed) into nodes[0..cap).
 // Token-at-a-time.  (A byte-at-a-time flat state machine was tried to cut warp divergence and measured
 // 2.4x SLOWER on B200 — profiles/README.md — so the straightforward form stays.)
@@ -375,21 +397,7 @@ CF_HD int json_parse(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t cap, u
         nodes[nn++] = JNode{J_STR | fl, p0 + 1, pos - p0 - 2, keep_next};
       } else if (c == '-' || (c >= '0' && c <= '9')) {
         uint32_t p0 = pos, fl = 0;
-        if (c == '-') { fl |= JF_NEG; ++pos; if (pos >= n) return PARSE_ERROR; }
-        if (s[pos] == '0') ++pos;
-        else if (s[pos] >= '1' && s[pos] <= '9') { while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos; }
-        else return PARSE_ERROR;
-        if (pos < n && s[pos] == '.') {
-          fl |= JF_FRAC; ++pos;
-          if (pos >= n || s[pos] < '0' || s[pos] > '9') return PARSE_ERROR;
-          while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos;
-        }
-        if (pos < n && (s[pos] == 'e' || s[pos] == 'E')) {
-          fl |= JF_EXP; ++pos;
-          if (pos < n && (s[pos] == '+' || s[pos] == '-')) ++pos;
-          if (pos >= n || s[pos] < '0' || s[pos] > '9') return PARSE_ERROR;
-          while (pos < n && s[pos] >= '0' && s[pos] <= '9') ++pos;
-        }
+        if (!scan_number(s, n, &pos, &fl)) return PARSE_ERROR;
         nodes[nn++] = JNode{J_NUM | fl, p0, pos - p0, keep_next};
       } else if (c == 't' && pos + 4 <= n && s[pos + 1] == 'r' && s[pos + 2] == 'u' && s[pos + 3] == 'e') {
         nodes[nn++] = JNode{J_TRUE, pos, 4, keep_next}; pos += 4;
@@ -1049,12 +1057,21 @@ CF_HD void toon_emit(Ctx& c, uint32_t root) {
   }
 }
 
+CF_HD int toon_finish(int pr, const uint8_t* s, const JNode* nodes, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Big* big,
+                      uint8_t* digits, uint32_t digits_cap, bool stop_on_over);
+
 // Whole per-unit pipeline.  The product passes out_cap = n - 1: a conversion is only kept when it is
 // strictly smaller than the n input bytes, so a longer TOON text can be abandoned mid-way.  Returns a TS_* status; *out_len is valid for TS_CONVERTED.
 CF_HD int toon_process(const uint8_t* s, uint32_t n, JNode* nodes, uint32_t node_cap, uint8_t* out, uint32_t out_cap,
                        uint32_t* out_len, Big* big, uint8_t* digits, uint32_t digits_cap, bool stop_on_over) {
   uint32_t count = 0;
   int pr = json_parse(s, n, nodes, node_cap, &count);
+  return toon_finish(pr, s, nodes, out, out_cap, out_len, big, digits, digits_cap, stop_on_over);
+}
+
+// the part after the parse (pr = PARSE_* of whichever parser built `nodes`)
+CF_HD int toon_finish(int pr, const uint8_t* s, const JNode* nodes, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Big* big,
+                      uint8_t* digits, uint32_t digits_cap, bool stop_on_over) {
   if (pr == PARSE_ERROR) return TS_NOT_JSON;
   if (pr == PARSE_UNSUPPORTED) return TS_UNSUPPORTED;
   Ctx c;

@@ -253,6 +253,25 @@ def toon_host(batch: Batch, stream, offsets: np.ndarray, report_errors: bool = T
     return status, texts
 
 
+def json_index_host(batch: Batch, stream, offsets: np.ndarray, classify: bool = False):
+    """cf_json_index_host: structural index of every unit (one JSON text each).  Returns per unit
+    (tokens uint32[k, 2] = (pos | close_quote << 31, aux), unterminated flag)."""
+    ctx = batch.ctx
+    n = len(offsets) - 1
+    nbytes = int(offsets[-1])
+    toks = np.zeros((max(nbytes, 1), 2), dtype=np.uint32)
+    counts = np.zeros(max(n, 1), dtype=np.uint32)
+    sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+    with ctx.lock:
+        ctx.check(ctx.lib.cf_json_index_host(ctx.h, batch.h, 1 if classify else 0, sp, nbytes, offsets.ctypes.data, n, toks.ctypes.data, counts.ctypes.data), "cf_json_index_host")
+    out = []
+    for i in range(n):
+        o = int(offsets[i])
+        k = int(counts[i]) & 0x7FFFFFFF
+        out.append((toks[o:o + k].copy(), bool(int(counts[i]) >> 31)))
+    return out
+
+
 MASK_OK, MASK_PARSE_ERROR, MASK_UNSUPPORTED = 0, 2, 6
 
 

@@ -127,3 +127,62 @@ extern "C" int cfh_key_sensitive(const uint8_t* key, uint32_t n) {
   cfj::JNode k{cfj::J_KEY, 0, n, 0};   // raw (unescaped) key bytes
   return cfm::key_sensitive(key, k) ? 1 : 0;
 }
+
+// ---- structural index + token-driven DOM builder (json_index.h), the path the CUDA kernels take ----
+#include "../../mcp_context_forge_b200/csrc/json_index.h"
+static int indexed_parse(const uint8_t* text, uint32_t n, std::vector<cfj::JNode>& nodes, uint32_t* count) {
+  std::vector<cfx::Tok> tok(n + 1);
+  bool unt = false;
+  const uint32_t nt = cfx::index_host(text, n, tok.data(), &unt);
+  for (uint32_t t = 0; t < nt; ++t) tok[t].aux = cfx::classify_token(text, n, tok[t].pos);
+  return cfx::json_build(text, n, tok.data(), nt, unt, nodes.data(), (uint32_t)nodes.size(), count);
+}
+// 0 = both parsers agree (same status and, when it parsed, identical node arrays); else a diagnostic code
+extern "C" int cfh_index_equiv(const uint8_t* text, uint32_t n, int* status_seq, int* status_idx) {
+  std::vector<cfj::JNode> a(n / 2 + 4), b(n / 2 + 4);
+  uint32_t ca = 0, cb = 0;
+  const int pa = cfj::json_parse(text, n, a.data(), (uint32_t)a.size(), &ca);
+  const int pb = indexed_parse(text, n, b, &cb);
+  *status_seq = pa; *status_idx = pb;
+  if (pa != pb) return 1;
+  if (pa != cfj::PARSE_OK) return 0;
+  if (ca != cb) return 2;
+  for (uint32_t i = 0; i < ca; ++i)
+    if (a[i].t != b[i].t || a[i].off != b[i].off || a[i].len != b[i].len) return 3;
+  // .next: sibling links and, for object member values, the key hash (28 bits kept by the index path)
+  for (uint32_t i = 0; i < ca; ++i) {
+    const bool member_value = i > 0 && (a[i - 1].t & cfj::J_TYPE) == cfj::J_KEY;
+    if (member_value) { if ((a[i].next & 0x0FFFFFFFu) != (b[i].next & 0x0FFFFFFFu)) return 4; }
+    else if (a[i].next != b[i].next) return 5;
+  }
+  return 0;
+}
+// token list of the index alone: pos (bit 31 = closing quote); returns the count, *unterminated as flag
+extern "C" uint32_t cfh_json_index(const uint8_t* text, uint32_t n, uint32_t* pos_out, uint32_t* aux_out, int* unterminated) {
+  std::vector<cfx::Tok> tok(n + 1);
+  bool unt = false;
+  const uint32_t nt = cfx::index_host(text, n, tok.data(), &unt);
+  for (uint32_t t = 0; t < nt; ++t) { pos_out[t] = tok[t].pos; aux_out[t] = cfx::classify_token(text, n, tok[t].pos); }
+  *unterminated = unt ? 1 : 0;
+  return nt;
+}
+extern "C" int cfh_toon_indexed(const uint8_t* text, uint32_t n, uint8_t* out, uint32_t out_cap, uint32_t* out_len) {
+  std::vector<cfj::JNode> nodes(n / 2 + 4);
+  cfj::Big big;
+  std::vector<uint8_t> digits(1240);
+  uint32_t cnt = 0;
+  *out_len = 0;
+  const int pr = indexed_parse(text, n, nodes, &cnt);
+  return cfj::toon_finish(pr, text, nodes.data(), out, out_cap, out_len, &big, digits.data(), (uint32_t)digits.size(), false);
+}
+extern "C" int cfh_mask_indexed(const uint8_t* text, uint32_t n, int max_depth, uint8_t* out, uint32_t out_cap, uint32_t* out_len) {
+  std::vector<cfj::JNode> nodes(n / 2 + 4);
+  std::vector<uint32_t> idx(n / 2 + 4);
+  cfj::Big big;
+  std::vector<uint8_t> digits(1240);
+  cfm::NumWork w{&big, &big, digits.data(), (uint32_t)digits.size()};
+  uint32_t cnt = 0;
+  *out_len = 0;
+  const int pr = indexed_parse(text, n, nodes, &cnt);
+  return cfm::mask_finish(pr, text, nodes.data(), idx.data(), (uint32_t)idx.size(), out, out_cap, out_len, max_depth, w);
+}

@@ -113,24 +113,46 @@ class HostProgram:
 TOON_STATUS = {0: "converted", 1: "not_smaller", 2: "not_json", 3: "value_error", 4: "attr_error", 6: "unsupported"}
 
 
-def toon_host(text: str, unlimited: bool = False):
+def toon_host(text: str, unlimited: bool = False, indexed: bool = False):
     """(status, toon_text_or_None) from the shared json_toon.h pipeline compiled for the CPU.
     unlimited=True lifts the product's "strictly smaller" capacity so the encoder output itself can
-    be compared with the reference's toon.encode."""
+    be compared with the reference's toon.encode.  indexed=True parses through the structural index +
+    token-driven builder (json_index.h — the path the CUDA kernels take) instead of the sequential parser."""
     b = text.encode("utf-8", "surrogatepass")
     cap = len(b) * 6 + 4096 if unlimited else max(len(b) - 1, 0)
     out = ctypes.create_string_buffer(max(cap, 1))
     n = ctypes.c_uint32()
-    st = lib().cfh_toon(b, len(b), out, cap, ctypes.byref(n))
+    fn = lib().cfh_toon_indexed if indexed else lib().cfh_toon
+    st = fn(b, len(b), out, cap, ctypes.byref(n))
     return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)
 
 
-def mask_host(payload: bytes, max_depth: int = 10):
+def index_equiv(data: bytes):
+    """(code, status_sequential, status_indexed): code 0 = the sequential parser and index+builder agree."""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    rc = lib().cfh_index_equiv(data, len(data), ctypes.byref(a), ctypes.byref(b))
+    return rc, a.value, b.value
+
+
+def json_index(data: bytes):
+    """Token list of the structural index: [(pos, is_close_quote, aux)], unterminated flag."""
+    n = len(data)
+    pos = (ctypes.c_uint32 * (n + 1))()
+    aux = (ctypes.c_uint32 * (n + 1))()
+    unt = ctypes.c_int()
+    L = lib()
+    L.cfh_json_index.restype = ctypes.c_uint32
+    nt = L.cfh_json_index(data, n, pos, aux, ctypes.byref(unt))
+    return [(pos[i] & 0x7FFFFFFF, bool(pos[i] >> 31), aux[i]) for i in range(nt)], bool(unt.value)
+
+
+def mask_host(payload: bytes, max_depth: int = 10, indexed: bool = False):
     """(status, masked_bytes_or_None) from the shared json_mask.h pipeline compiled for the CPU."""
     cap = len(payload) * 5 + 64
     out = ctypes.create_string_buffer(cap)
     n = ctypes.c_uint32()
-    st = lib().cfh_mask(payload, len(payload), max_depth, out, cap, ctypes.byref(n))
+    fn = lib().cfh_mask_indexed if indexed else lib().cfh_mask
+    st = fn(payload, len(payload), max_depth, out, cap, ctypes.byref(n))
     return st, (out.raw[: n.value] if st == 0 else None)
 
 
