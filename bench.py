@@ -159,7 +159,8 @@ class ClockSampler:
 
 def side_stages(ctx, engine, payloads):
     """Informational device-resident timings of the other rows of the path on the same payload mix
-    (not part of the headline metric): request_logging_masking and toon_encoder, 4096 units each."""
+    (not part of the headline metric): toon_encoder, the JSON structural index and request_logging_masking,
+    4096 units each."""
     import ctypes
 
     import torch
@@ -185,6 +186,19 @@ def side_stages(ctx, engine, payloads):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             out[name] = {"units": n, "ms": ms, "payloads_per_s": n / ms * 1e3, "gb_per_s": len(stream) / ms / 1e6, "converted": int((d_st == 0).sum())}
+        toks = torch.empty((len(stream) + 64, 2), dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            lib.cf_json_index(ctx.h, batch.h, 0, toks.data_ptr(), d_len.data_ptr(), None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.cf_json_index(ctx.h, batch.h, 0, toks.data_ptr(), d_len.data_ptr(), None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out["json_index_stage1"] = {"units": n, "ms": ms, "gb_per_s": len(stream) / ms / 1e6, "tokens": int((d_len & 0x7FFFFFFF).sum())}
+        del toks
+        engine.mask_host(batch, stream, offs, 10)          # warm-up: scratch buffers grow once
         t0 = time.perf_counter()
         st, _ = engine.mask_host(batch, stream, offs, 10)
         dt = time.perf_counter() - t0
