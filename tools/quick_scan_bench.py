@@ -22,6 +22,17 @@ for pats in ref.DEFAULT_LEXICONS.values():
         p.add_search(pat, re.I)
 for w in ["innovative", "groundbreaking", "revolutionary"]:
     p.add_literal(w)
+# CF_QS_EXTRA=N adds N more deny words that do not occur in the payloads (large-rule-set probe)
+import os
+RARE = """xylophone quagmire zephyr jackhammer blizzard buzzword quizzical jukebox wizardry zigzagging
+kumquat vortex pixelate fjord gazebo haphazard ivory jinx kiosk larynx mnemonic nymph oxygen pajama
+quartz rhythm sphinx topaz unzip vixen waltz yacht zodiac abyss bayou crypt dwarves espionage fishhook
+galaxy hyphen icebox jaundice keyhole luxury matrix nightclub ovary pneumonia queue rickshaw strength
+transcript uptown vaporize whiskey xenon youthful zombie absurd bikini cobweb duplex embezzle fluffy
+glowworm hymn injury jogging knapsack lucky microwave numbskull onyx peekaboo quorum razzmatazz subway
+thumbscrew unknown voodoo wave wheezy yippee zilch askew bagpipes cycle disavow equip frizzled gossip""".split()
+for w in RARE[:int(os.environ.get("CF_QS_EXTRA", "0"))]:
+    p.add_literal(w)
 p.add_sub("crap", 0, "crud")
 p.add_sub("crud", 0, "yikes")
 p.compile(ctx)
