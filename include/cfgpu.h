@@ -74,7 +74,9 @@ int cf_builder_set_replacement(cf_builder* b, uint32_t pattern_index, const uint
 /* run the host part of compilation now (idempotent); reports table sizes */
 typedef struct cf_compile_stats {
   uint32_t n_patterns, words_per_bitmap, n_classes, n_states, n_accsets, n_ordered;
-  uint32_t trans_bytes, reserved;
+  uint32_t trans_bytes;
+  uint32_t prefilter;   /* 0 = byte filter (5-byte window of per-position byte sets), 1 = pair filter (keyed on byte pairs;
+                         * chosen when the byte filter would admit too many windows, i.e. large rule sets) */
 } cf_compile_stats;
 int cf_builder_compile_host(cf_builder* b, cf_compile_stats* out);
 

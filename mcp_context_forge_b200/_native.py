@@ -22,7 +22,7 @@ class CfError(RuntimeError):
 
 
 class CompileStats(ctypes.Structure):
-    _fields_ = [(n, c_uint32) for n in ("n_patterns", "words_per_bitmap", "n_classes", "n_states", "n_accsets", "n_ordered", "trans_bytes", "reserved")]
+    _fields_ = [(n, c_uint32) for n in ("n_patterns", "words_per_bitmap", "n_classes", "n_states", "n_accsets", "n_ordered", "trans_bytes", "prefilter")]
 
 
 _SIGS = {

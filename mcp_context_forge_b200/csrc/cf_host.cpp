@@ -76,6 +76,7 @@ int cf_builder_compile_host(cf_builder* b, cf_compile_stats* out) {
     out->n_accsets = (uint32_t)(b->out.search.accsets.size() / b->out.search.W);
     out->n_ordered = (uint32_t)b->out.ordered.size();
     out->trans_bytes = (uint32_t)(b->out.search.trans.size() * 4);
+    out->prefilter = b->out.filter.use_pairs ? 1u : 0u;
   }
   return CF_OK;
 }

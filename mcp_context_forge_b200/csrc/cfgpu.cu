@@ -71,7 +71,8 @@ struct cf_prog {
   cf_ctx* ctx = nullptr;
   uint32_t npat = 0, W = 1;
   DevDfa search;
-  uint32_t* d_E = nullptr;
+  uint32_t* d_E = nullptr;         // byte prefilter E[256], or the pair prefilter's T[PF_SLOTS] when use_pairs
+  bool use_pairs = false;
   uint64_t* d_always = nullptr;
   bool any_always = false;
   bool search_empty = false;       // every pattern is "always" -> no automaton work at all
@@ -379,7 +380,50 @@ __device__ __forceinline__ uint32_t pair_step(uint32_t acc, uint32_t f0, uint32_
     }                                                                                           \
   }
 
-template <uint32_t WARPS, uint32_t LB, uint32_t ACC, uint32_t STAGES>
+// ---- pair prefilter (scan_core.h; chosen at compile time of the rule set when the byte filter would admit
+// too many windows).  Table: PF_SLOTS rows of 128 bytes, lane-private banks again:
+//   T(h, l) = tbl + (h << 7) + (l << 2),   h = pair_hash(previous byte, byte)
+// Per byte: PRMT {prev, cur, prev, cur} -> IMAD (hash) -> SHF -> IMAD (address) -> LDS -> IMAD (acc*256+255) -> LOP3.
+template <uint32_t K>
+__device__ __forceinline__ uint32_t pair_u(uint32_t pw, uint32_t w) {
+  if (K == 0) return __byte_perm(pw, w, 0x4343);                                 // last byte of the previous word, first of this
+  return __byte_perm(w, 0u, (K << 12) | ((K - 1) << 8) | (K << 4) | (K - 1));
+}
+__device__ __forceinline__ uint32_t pairq_step(uint32_t acc, uint32_t u, uint32_t lane_base, uint32_t mulc) {
+  const uint32_t h = (u * cf::PF_MULT) >> 22;
+  const uint32_t e = lds_abs(h * 128u + lane_base);
+  uint32_t t;
+  asm("mad.lo.u32 %0, %1, %2, 255;" : "=r"(t) : "r"(acc), "r"(mulc));
+  return t & e;
+}
+// look-back: bytes 1..3 of `w` (byte 0 only serves as the first predecessor); hits belong to the previous owner
+#define QFEED_LB(ACCV, w)                                             \
+  ACCV = pairq_step(ACCV, pair_u<1>(0u, (w)), lane_base, mulc);       \
+  ACCV = pairq_step(ACCV, pair_u<2>(0u, (w)), lane_base, mulc);       \
+  ACCV = pairq_step(ACCV, pair_u<3>(0u, (w)), lane_base, mulc);
+#define QFEED4(ACCV, pw, w, H)                                        \
+  ACCV = pairq_step(ACCV, pair_u<0>((pw), (w)), lane_base, mulc); H |= ACCV; \
+  ACCV = pairq_step(ACCV, pair_u<1>(0u, (w)), lane_base, mulc); H |= ACCV;   \
+  ACCV = pairq_step(ACCV, pair_u<2>(0u, (w)), lane_base, mulc); H |= ACCV;   \
+  ACCV = pairq_step(ACCV, pair_u<3>(0u, (w)), lane_base, mulc); H |= ACCV;
+// rare path: exact positions inside one 16-byte group
+#define QREFEED(pw, w, K, bit)                                        \
+  acc_ = pairq_step(acc_, pair_u<K>((pw), (w)), lane_base, mulc);     \
+  m_ |= ((acc_ & cf::PF_HIT) ? 1u : 0u) << (bit);
+#define QREFEED4(pw, w, b0) QREFEED(pw, w, 0, (b0)) QREFEED(pw, w, 1, (b0) + 1) QREFEED(pw, w, 2, (b0) + 2) QREFEED(pw, w, 3, (b0) + 3)
+#define QREGROUP(prevword, v, gpos)                                   \
+  {                                                                   \
+    uint32_t acc_ = 0, m_ = 0;                                        \
+    QFEED_LB(acc_, (prevword))                                        \
+    QREFEED4((prevword), (v).x, 0) QREFEED4((v).x, (v).y, 4) QREFEED4((v).y, (v).z, 8) QREFEED4((v).z, (v).w, 12) \
+    while (m_) {                                                      \
+      const uint32_t k_ = __ffs(m_) - 1;                              \
+      m_ &= m_ - 1;                                                   \
+      push_candidate<WARPS>(sm, P, warp, (gpos) + k_ - 3);            \
+    }                                                                 \
+  }
+
+template <uint32_t WARPS, uint32_t LB, uint32_t ACC, uint32_t STAGES, uint32_t PAIR = 0>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_constant__ ScanParams P,
                                                                const __grid_constant__ CUtensorMap tmap) {
   constexpr uint32_t NS = LB / 16;                  // 16-byte slots per lane per tile
@@ -397,9 +441,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   // Stage s lives at absolute shared address stage_abs(s): the first NA stages in the gap before the
   // table, the rest behind it (pure arithmetic: no pointer array, so the tile reads stay true LDS).
   const uint32_t abs0 = smem_u32(smem_raw);
-  const uint32_t tbl_abs = (abs0 + 0xFFFFu) & ~0xFFFFu;
+  constexpr uint32_t TBL_BYTES = PAIR ? cf::PF_SLOTS * 128u : 0x10000u;
+  // byte filter: the one-PRMT address needs a 64 KiB-aligned table; the pair table only needs its 1 KiB alignment
+  const uint32_t tbl_abs = PAIR ? ((abs0 + 1023u) & ~1023u) : ((abs0 + 0xFFFFu) & ~0xFFFFu);
   const uint32_t a_base = (abs0 + 1023u) & ~1023u;               // free space before the table
-  const uint32_t b_base = tbl_abs + 0x10000u;                    // free space after it
+  const uint32_t b_base = tbl_abs + TBL_BYTES;                   // free space after it
   const uint32_t na_fit = (tbl_abs - a_base) / TILE;
   const uint32_t NA = na_fit < STAGES ? na_fit : STAGES;
   uint32_t a_end = a_base + NA * TILE, b_end = b_base + (STAGES - NA) * TILE;
@@ -413,7 +459,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem_raw + (tbl_abs - abs0));
   const uint32_t laneK = (lane << 2) | tbl_abs;                  // tbl_abs has zero low 16 bits
   const uint32_t laneKF = laneK | 0x80u;                         // second half of each row: the F copies
-  const uint32_t mulc = P.mulc;                                  // 1024, deliberately not an immediate
+  const uint32_t mulc = P.mulc;                                  // 1024 (pair filter: 256), deliberately not an immediate
+  const uint32_t lane_base = tbl_abs + (lane << 2);              // pair filter: T(h, lane) = lane_base + (h << 7)
+  (void)laneKF; (void)lane_base;
 
   auto load_tile = [&](uint32_t slot_, uint32_t tile_) {
     mbar_expect_tx_a(full_abs + 8 * slot_, TILE);
@@ -435,10 +483,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
       if (tj < ntiles) load_tile(j, tj);
     }
   }
-  for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) {
-    const uint32_t e = P.E[i >> 5];
-    tbl[(i >> 5) * 64 + (i & 31)] = e | 0x3E000000u;            // E1
-    tbl[(i >> 5) * 64 + 32 + (i & 31)] = (e << 5) | 31u;        // F
+  if (PAIR) {
+    for (uint32_t i = tid; i < cf::PF_SLOTS * 32; i += WARPS * 32) tbl[i] = P.E[i >> 5];   // row h: 32 lane copies of T[h]
+  } else {
+    for (uint32_t i = tid; i < 256 * 32; i += WARPS * 32) {
+      const uint32_t e = P.E[i >> 5];
+      tbl[(i >> 5) * 64 + (i & 31)] = e | 0x3E000000u;            // E1
+      tbl[(i >> 5) * 64 + 32 + (i & 31)] = (e << 5) | 31u;        // F
+    }
   }
   __syncthreads();
 
@@ -487,7 +539,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
     if (++slot == STAGES) { slot = 0; phase ^= 1; }
 
     uint32_t h[NS];
-    if (NS == 4) {
+    if (PAIR) {
+      static_assert(!PAIR || NS == 4, "pair filter variant is written for 64 bytes per lane");
+      // two independent chains (bytes 0-31 and 32-63), one byte per step
+      uint32_t accA = 0, accB = 0;
+      h[0] = h[1] = h[2] = h[3] = 0;
+      QFEED_LB(accA, back)
+      QFEED_LB(accB, v[1].w)
+      QFEED4(accA, back, v[0].x, h[0]) QFEED4(accB, v[1].w, v[2].x, h[2])
+      QFEED4(accA, v[0].x, v[0].y, h[0]) QFEED4(accB, v[2].x, v[2].y, h[2])
+      QFEED4(accA, v[0].y, v[0].z, h[0]) QFEED4(accB, v[2].y, v[2].z, h[2])
+      QFEED4(accA, v[0].z, v[0].w, h[0]) QFEED4(accB, v[2].z, v[2].w, h[2])
+      QFEED4(accA, v[0].w, v[1].x, h[1]) QFEED4(accB, v[2].w, v[3].x, h[3])
+      QFEED4(accA, v[1].x, v[1].y, h[1]) QFEED4(accB, v[3].x, v[3].y, h[3])
+      QFEED4(accA, v[1].y, v[1].z, h[1]) QFEED4(accB, v[3].y, v[3].z, h[3])
+      QFEED4(accA, v[1].z, v[1].w, h[1]) QFEED4(accB, v[3].z, v[3].w, h[3])
+    } else if (NS == 4) {
       // two independent shift-AND chains per lane (bytes 0-31 and 32-63) for instruction-level
       // parallelism; the second chain re-feeds the last word of the first half as its look-back
       uint32_t accA = 0, accB = 0, dA = 0, dB = 0;
@@ -519,13 +586,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
     uint32_t hany = 0;
 #pragma unroll
     for (uint32_t j = 0; j < NS; ++j) hany |= h[j];
-    const bool anyhit = (hany & HIT2) != 0;
+    constexpr uint32_t HITM = PAIR ? cf::PF_HIT : HIT2;
+    const bool anyhit = (hany & HITM) != 0;
     if (__any_sync(0xFFFFFFFFu, anyhit)) {
       if (anyhit) {
         const uint64_t cpos = (uint64_t)t * TILE + chunk;   // stream offset of this lane's first byte
 #pragma unroll
         for (uint32_t j = 0; j < NS; ++j)
-          if (h[j] & HIT2) REGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
+          if (h[j] & HITM) {
+            if (PAIR) QREGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
+            else REGROUP((j ? v[j ? j - 1 : 0].w : back), v[j], cpos + 16 * j)
+          }
       }
       __syncwarp();
       if (sm.wq_n[warp] >= WQ / 2) flush_candidates<WARPS>(sm, P, warp, lane);
@@ -571,6 +642,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_kernel(const __grid_consta
 
 typedef void (*scan_fn_t)(const ScanParams, const CUtensorMap);
 struct ScanVariant { scan_fn_t fn; uint32_t warps, lane_bytes, acc, stages; };
+// pair-filter kernels (128 KiB table): same tile geometry as the byte-filter variant in use, two stages
+static scan_fn_t pair_variant(uint32_t warps, uint32_t lane_bytes) {
+  if (warps == 16 && lane_bytes == 64) return scan_kernel<16, 64, 1, 2, 1>;
+  if (warps == 20 && lane_bytes == 64) return scan_kernel<20, 64, 1, 2, 1>;
+  return nullptr;
+}
 #define SV(W, LB, A, S) {scan_kernel<W, LB, A, S>, W, LB, A, S}
 static const ScanVariant SCAN_VARIANTS[] = {
     SV(16, 64, 0, 3), SV(16, 64, 1, 3), SV(16, 64, 1, 4), SV(16, 64, 1, 2), SV(20, 64, 1, 3), SV(24, 64, 1, 3),
@@ -911,6 +988,8 @@ int cf_init(int device_ordinal, cf_ctx** out) {
   if (!scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages)) { ctx->err = "unsupported CF_SCAN_WARPS / CF_SCAN_LB / CF_SCAN_ACC / CF_SCAN_STAGES combination"; return CF_E_BADARG; }
   for (const auto& v : SCAN_VARIANTS)
     CF_CUDA(ctx, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
+  if (scan_fn_t pf = pair_variant(ctx->scan_warps, ctx->scan_lane_bytes))
+    CF_CUDA(ctx, cudaFuncSetAttribute(pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
   return CF_OK;
 }
 
@@ -944,8 +1023,14 @@ int cf_compile(cf_ctx* ctx, cf_builder* b, cf_prog** out) {
   p->W = b->out.search.W;
   *out = p;
   if ((rc = upload_dfa(ctx, b->out.search, p->search))) return rc;
-  CF_CUDA(ctx, cudaMalloc(&p->d_E, 256 * 4));
-  CF_CUDA(ctx, cudaMemcpy(p->d_E, b->out.filter.E, 256 * 4, cudaMemcpyHostToDevice));
+  p->use_pairs = b->out.filter.use_pairs && pair_variant(ctx->scan_warps, ctx->scan_lane_bytes) != nullptr;
+  if (p->use_pairs) {   // large rule set: the pair prefilter's table instead of the byte table (scan_core.h)
+    CF_CUDA(ctx, cudaMalloc(&p->d_E, cf::PF_SLOTS * 4));
+    CF_CUDA(ctx, cudaMemcpy(p->d_E, b->out.filter.pairT.data(), cf::PF_SLOTS * 4, cudaMemcpyHostToDevice));
+  } else {
+    CF_CUDA(ctx, cudaMalloc(&p->d_E, 256 * 4));
+    CF_CUDA(ctx, cudaMemcpy(p->d_E, b->out.filter.E, 256 * 4, cudaMemcpyHostToDevice));
+  }
   CF_CUDA(ctx, cudaMalloc(&p->d_always, p->W * 8));
   CF_CUDA(ctx, cudaMemcpy(p->d_always, b->out.always_bits.data(), p->W * 8, cudaMemcpyHostToDevice));
   for (uint64_t v : b->out.always_bits) if (v) p->any_always = true;
@@ -1096,13 +1181,14 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   P.dfa_bytes = p->search.stage_bytes < (1u << 30) ? (uint32_t)p->search.stage_bytes : 0;
   P.dfa_trans_bytes = (uint32_t)p->search.trans_bytes;
   P.dfa_acc_bytes = (uint32_t)p->search.acc_bytes;
-  P.mulc = 1024;
+  P.mulc = p->use_pairs ? 256 : 1024;
   const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages);
+  const scan_fn_t fn = p->use_pairs ? pair_variant(ctx->scan_warps, ctx->scan_lane_bytes) : sv->fn;
   uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM
   if (grid > ntiles) grid = ntiles;
   const bool prof = ctx->prof_on && (size_t)ctx->prof_used + 2 <= ctx->prof_ev.size();
   if (prof) cudaEventRecord(ctx->prof_ev[ctx->prof_used], st);
-  sv->fn<<<(unsigned)grid, sv->warps * 32, SCAN_SMEM, st>>>(P, b->tmap);
+  fn<<<(unsigned)grid, sv->warps * 32, SCAN_SMEM, st>>>(P, b->tmap);
   if (prof) { cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], st); ctx->prof_used += 2; }
   ctx->launches++;
   CF_CUDA(ctx, cudaGetLastError());

@@ -6,6 +6,8 @@
 #include <map>
 #include <deque>
 #include <queue>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "scan_core.h"
@@ -415,7 +417,15 @@ struct ByteSet {
   int union_count(const ByteSet& o) const { int c = 0; for (int i = 0; i < 4; ++i) c += __builtin_popcountll(w[i] | o.w[i]); return c; }
 };
 static const int NPOS = 4;   // match-byte positions covered by the prefilter
-struct PatFilter { ByteSet N, pos[NPOS]; };
+struct SlotSet {                      // subset of the cf::PF_SLOTS pair-hash slots
+  uint64_t w[cf::PF_SLOTS / 64];
+  SlotSet() { memset(w, 0, sizeof(w)); }
+  void set(uint32_t i) { w[i >> 6] |= 1ull << (i & 63); }
+  bool get(uint32_t i) const { return (w[i >> 6] >> (i & 63)) & 1; }
+  void all() { memset(w, 0xFF, sizeof(w)); }
+  void merge(const SlotSet& o) { for (size_t i = 0; i < cf::PF_SLOTS / 64; ++i) w[i] |= o.w[i]; }
+};
+struct PatFilter { ByteSet N, pos[NPOS]; SlotSet pair[NPOS]; };
 
 static void explore(const DfaBuilder& B, const Classes& C, uint32_t state, int bytepos,
                     std::vector<uint8_t>& seen, PatFilter& f) {
@@ -450,6 +460,94 @@ static bool alive(const DfaBuilder& B, const Classes& C, uint32_t state) {
   return false;
 }
 
+// Pair sets by forward data flow over the pattern's anchored DFA: reach[s] = bytes that can immediately
+// precede the transition out of state s at the current byte position.  Multi-byte characters are
+// over-approximated (any continuation byte may follow a lead or another continuation byte).
+static void add_pairs(SlotSet& ps, const ByteSet& prev, const ByteSet& cur) {
+  for (uint32_t x = 0; x < 256; ++x) {
+    if (!prev.get(x)) continue;
+    for (uint32_t y = 0; y < 256; ++y) if (cur.get(y)) ps.set(cf::pair_hash(x, y));
+  }
+}
+static void pattern_pairs(const DfaBuilder& B, const Classes& C, const uint32_t ss[4], const ByteSet ctxN[4], PatFilter& f) {
+  const uint32_t ncols = C.ncls + 1;
+  const size_t ns = B.states.size();
+  ByteSet conts;
+  for (uint32_t b = 0x80; b < 0xC0; ++b) conts.set(b);
+  // code points of every small non-ASCII class (empty = none or too many to enumerate)
+  std::vector<std::vector<uint32_t>> nonascii_cps(C.ncls);
+  {
+    std::vector<uint64_t> total(C.ncls, 0);
+    const size_t nr = C.range_start.size();
+    for (size_t i = 0; i < nr; ++i) {
+      const uint32_t lo = C.range_start[i], hi = i + 1 < nr ? C.range_start[i + 1] - 1 : 0x10FFFFu;
+      total[C.range_cls[i]] += (uint64_t)hi - lo + 1;
+    }
+    for (size_t i = 0; i < nr; ++i) {
+      const uint32_t cls = C.range_cls[i];
+      if (total[cls] > 256) continue;
+      const uint32_t lo = C.range_start[i], hi = i + 1 < nr ? C.range_start[i + 1] - 1 : 0x10FFFFu;
+      for (uint32_t cp = lo; cp <= hi; ++cp) nonascii_cps[cls].push_back(cp);
+    }
+  }
+  // reach[j][s]: possible previous bytes when state s is entered with j match bytes consumed
+  std::vector<std::vector<ByteSet>> reach(NPOS + 4, std::vector<ByteSet>(ns));
+  std::vector<std::vector<uint8_t>> live(NPOS + 4, std::vector<uint8_t>(ns, 0));
+  for (int P = 0; P < 4; ++P) {
+    if (ss[P] == cf::DEAD || ctxN[P].count() == 0) continue;
+    reach[0][ss[P]].merge(ctxN[P]);
+    live[0][ss[P]] = 1;
+  }
+  bool open_from[NPOS + 1] = {false, false, false, false, false};   // a match can be complete before byte j: anything follows
+  for (int j = 0; j < NPOS; ++j) {
+    for (size_t s = 0; s < ns; ++s) {
+      if (!live[j][s]) continue;
+      const ByteSet& R = reach[j][s];
+      for (uint32_t col = 0; col < ncols; ++col) {
+        const uint32_t e = B.trans[s * ncols + col];
+        if (e >> cf::ACC_SHIFT) open_from[j] = true;
+        const uint32_t t = e & 0xFFFF;
+        if (col == C.ncls || t == cf::DEAD) continue;
+        ByteSet asc;
+        bool any_ascii = false;
+        for (uint32_t b = 0; b < 128; ++b) if (C.ascii_members[col][b]) { asc.set(b); any_ascii = true; }
+        if (any_ascii) {
+          add_pairs(f.pair[j], R, asc);
+          reach[j + 1][t].merge(asc);
+          live[j + 1][t] = 1;
+        }
+        // non-ASCII members of the class: exact byte sequences when the class is small (the case-fold partners
+        // of ASCII letters: K, long s, dotless i ...), over-approximated continuation bytes otherwise
+        if (col < C.ncls && !nonascii_cps[col].empty()) {
+          for (uint32_t cp : nonascii_cps[col]) {
+            uint8_t u[4];
+            int L = 0;
+            if (cp < 0x800) { u[0] = 0xC0 | (cp >> 6); u[1] = 0x80 | (cp & 63); L = 2; }
+            else if (cp < 0x10000) { u[0] = 0xE0 | (cp >> 12); u[1] = 0x80 | ((cp >> 6) & 63); u[2] = 0x80 | (cp & 63); L = 3; }
+            else { u[0] = 0xF0 | (cp >> 18); u[1] = 0x80 | ((cp >> 12) & 63); u[2] = 0x80 | ((cp >> 6) & 63); u[3] = 0x80 | (cp & 63); L = 4; }
+            ByteSet one;
+            one.set(u[0]);
+            add_pairs(f.pair[j], R, one);
+            for (int k = 1; k < L && j + k < NPOS; ++k) f.pair[j + k].set(cf::pair_hash(u[k - 1], u[k]));
+            if (j + L < NPOS + 4) { reach[j + L][t].set(u[L - 1]); live[j + L][t] = 1; }
+          }
+          continue;
+        }
+        for (int L = 2; L <= 4; ++L) {
+          ByteSet leads;
+          bool any = false;
+          for (uint32_t b = 0xC0; b < 0x100; ++b) if (C.lead[L][col][b]) { leads.set(b); any = true; }
+          if (!any) continue;
+          add_pairs(f.pair[j], R, leads);
+          for (int k = 1; k < L && j + k < NPOS; ++k) add_pairs(f.pair[j + k], k == 1 ? leads : conts, conts);
+          if (j + L < NPOS + 4) { reach[j + L][t].merge(conts); live[j + L][t] = 1; }
+        }
+      }
+    }
+    if (open_from[j]) for (int k = j; k < NPOS; ++k) f.pair[k].all();
+  }
+}
+
 static int pattern_filter(const Prog& prog, const Classes& C, int pat, PatFilter& f, std::string* err) {
   DfaBuilder B2(prog, C, false, (uint32_t)pat + 1, 20000);
   uint32_t ss[4];
@@ -466,6 +564,12 @@ static int pattern_filter(const Prog& prog, const Classes& C, int pat, PatFilter
   if (al[cf::P_START]) f.N.set(cf::TERM);
   for (uint32_t b = 0; b < 128; ++b) if (al[C.cls_ctx[C.ascii_cls[b]]]) f.N.set(b);
   if (al[cf::P_WORD] || al[cf::P_OTHER]) for (uint32_t b = 0x80; b < 0xC0; ++b) f.N.set(b);
+  // the same "byte before the match" sets, per start context, for the pair filter
+  ByteSet ctxN[4];
+  if (al[cf::P_START]) ctxN[cf::P_START].set(cf::TERM);
+  for (uint32_t b = 0; b < 128; ++b) { const uint32_t cx = C.cls_ctx[C.ascii_cls[b]]; if (al[cx]) ctxN[cx].set(b); }
+  for (uint32_t b = 0x80; b < 0xC0; ++b) { if (al[cf::P_WORD]) ctxN[cf::P_WORD].set(b); if (al[cf::P_OTHER]) ctxN[cf::P_OTHER].set(b); }
+  pattern_pairs(B2, C, ss, ctxN, f);
   return 0;
 }
 
@@ -487,9 +591,11 @@ static const double* byte_prior() {
   return f;
 }
 
-static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
+// Partition the patterns into at most `nb` buckets minimising the expected candidates per byte of the BYTE
+// filter (sum over buckets of P(N) * prod P(pos_k) under the prior); the pair filter reuses the partition
+// logic with its own bucket count (patterns that share byte sets share pairs).  Returns the total cost.
+static double partition_patterns(const std::vector<PatFilter>& pf, size_t nb, std::vector<std::vector<int>>& groups) {
   size_t n = pf.size();
-  fo.bucket_of_pattern.assign(n, 0);
   const double* prior = byte_prior();
   auto mass = [&](const ByteSet& s) {
     double m = 0;
@@ -510,9 +616,23 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
   };
   struct Bk { PatFilter f; std::vector<int> pats; };
   std::vector<Bk> bks;
-  for (size_t i = 0; i < n; ++i) { Bk b; b.f = pf[i]; b.pats.push_back((int)i); bks.push_back(b); }
+  if (n <= 160) {
+    for (size_t i = 0; i < n; ++i) { Bk b; b.f = pf[i]; b.pats.push_back((int)i); bks.push_back(b); }
+  } else {
+    // very large rule sets: seed 64 groups by the smallest byte a match can start with (agglomeration is cubic)
+    std::vector<int> of_byte(256, -1);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t b0 = 0;
+      while (b0 < 255 && !pf[i].pos[0].get(b0)) ++b0;
+      const uint32_t key = b0 & 63;
+      if (of_byte[key] < 0) { of_byte[key] = (int)bks.size(); bks.push_back(Bk()); }
+      Bk& b = bks[of_byte[key]];
+      b.f = b.pats.empty() ? pf[i] : merged(b.f, pf[i]);
+      b.pats.push_back((int)i);
+    }
+  }
   // greedy agglomeration ...
-  while (bks.size() > cf::F_BUCKETS) {
+  while (bks.size() > nb) {
     size_t bi = 0, bj = 1; double best = 1e300;
     for (size_t i = 0; i < bks.size(); ++i)
       for (size_t j = i + 1; j < bks.size(); ++j) {
@@ -529,7 +649,7 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
     for (int p : b.pats) b.f = merged(b.f, pf[p]);
   };
   auto total = [&]() { double t = 0; for (auto& b : bks) if (!b.pats.empty()) t += cost(b.f); return t; };
-  const int rounds = n > 256 ? 2 : 16;   // bound compile time for very large rule sets
+  const int rounds = n > 160 ? 1 : 16;   // bound compile time for very large rule sets
   for (int round = 0; round < rounds; ++round) {
     bool moved = false;
     for (size_t from = 0; from < bks.size(); ++from)
@@ -559,17 +679,52 @@ static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo) {
       }
     if (!moved) break;
   }
+  groups.clear();
+  for (auto& b : bks) groups.push_back(b.pats);
+  return total();
+}
+
+// expected candidates per byte above which the pair filter (slower per byte, far more selective) takes over;
+// calibrated on B200: the byte filter scans at 4.6 TB/s plus ~0.12 ns per candidate, the pair filter at ~2 TB/s
+static const double PAIR_MODE_COST = 3e-3;
+
+static void assign_buckets(const std::vector<PatFilter>& pf, FilterOut& fo, bool allow_pairs) {
+  const size_t n = pf.size();
+  fo.bucket_of_pattern.assign(n, 0);
+  std::vector<std::vector<int>> groups;
+  fo.byte_cost = partition_patterns(pf, cf::F_BUCKETS, groups);
   memset(fo.E, 0, sizeof(fo.E));
-  for (size_t k = 0; k < bks.size(); ++k) {
-    for (int p : bks[k].pats) fo.bucket_of_pattern[p] = (int)k;
+  for (size_t k = 0; k < groups.size(); ++k) {
+    ByteSet N, pos[NPOS];
+    for (int p : groups[k]) {
+      fo.bucket_of_pattern[p] = (int)k;
+      N.merge(pf[p].N);
+      for (int j = 0; j < NPOS; ++j) pos[j].merge(pf[p].pos[j]);
+    }
     for (uint32_t b = 0; b < 256; ++b) {
       uint32_t e = 0;
-      if (bks[k].f.N.get(b)) e |= 1u << k;
+      if (N.get(b)) e |= 1u << k;
       for (int j = 0; j < NPOS; ++j)
-        if (bks[k].f.pos[j].get(b)) e |= 1u << ((j + 1) * cf::F_BITS + k);
+        if (pos[j].get(b)) e |= 1u << ((j + 1) * cf::F_BITS + k);
       fo.E[b] |= e;
     }
   }
+  fo.use_pairs = false;
+  fo.pairT.clear();
+  const char* force = getenv("CF_PAIR_FILTER");      // "1" / "0" force the choice (tests, measurements)
+  bool want = allow_pairs && fo.byte_cost > PAIR_MODE_COST;
+  if (allow_pairs && force && (force[0] == '0' || force[0] == '1')) want = force[0] == '1';
+  if (getenv("CF_DBG_FILTER")) fprintf(stderr, "byte filter cost %.3g (n=%zu) -> %s\n", fo.byte_cost, n, want ? "pairs" : "bytes");
+  if (!want) return;
+  std::vector<std::vector<int>> pg;
+  partition_patterns(pf, cf::PF_BUCKETS, pg);
+  fo.use_pairs = true;
+  fo.pairT.assign(cf::PF_SLOTS, 0);
+  for (size_t k = 0; k < pg.size(); ++k)
+    for (int p : pg[k])
+      for (int j = 0; j < NPOS; ++j)
+        for (uint32_t sl = 0; sl < cf::PF_SLOTS; ++sl)
+          if (pf[p].pair[j].get(sl)) fo.pairT[sl] |= 1u << (8 * j + k);
 }
 
 static bool nullable_no_assert(const Prog& prog, int start) {
@@ -660,7 +815,7 @@ int compile(const std::vector<PatternIn>& pats, const std::vector<uint8_t>& want
     rc = pattern_filter(prog, C, (int)i, pf[i], err);
     if (rc) return rc;
   }
-  assign_buckets(pf, out->filter);
+  assign_buckets(pf, out->filter, true);
 
   // ordered (leftmost-first) DFAs
   for (uint32_t i = 0; i < npat; ++i) {
@@ -676,7 +831,7 @@ int compile(const std::vector<PatternIn>& pats, const std::vector<uint8_t>& want
     std::vector<PatFilter> one(1);
     one[0] = pf[i];
     FilterOut fo;
-    assign_buckets(one, fo);
+    assign_buckets(one, fo, false);
     out->ordered_filter.push_back(fo);
   }
   return 0;

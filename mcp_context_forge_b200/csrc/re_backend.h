@@ -47,6 +47,10 @@ struct DfaOut {
 struct FilterOut {
   uint32_t E[256];           // P3<<20 | P2<<15 | P1<<10 | P0<<5 | N (five buckets per field; scan_core.h)
   std::vector<int> bucket_of_pattern;
+  // pair prefilter (scan_core.h), built when the byte filter's expected candidate rate is too high
+  bool use_pairs = false;
+  std::vector<uint32_t> pairT;          // [cf::PF_SLOTS] when use_pairs
+  double byte_cost = 0;                 // expected candidates per byte under the byte-frequency prior
 };
 
 struct PatternInfo {

@@ -143,4 +143,20 @@ static const uint32_t F_LOOKBACK = 4;   // bytes fed before the first owned posi
 static const uint32_t F_START_OFF = 3;  // candidate start = fed position - 3
 CF_HD uint32_t filter_step(uint32_t acc, uint32_t e) { return ((acc << F_BITS) | F_FILL) & e; }
 
+// Pair prefilter (large rule sets).  The byte filter admits a window when every position's byte is in
+// that position's SET; with many patterns per bucket the sets fill up and the filter stops filtering.
+// The pair filter keys each position on the byte AND its predecessor, hashed to PF_SLOTS table slots:
+//   T[h(x, y)] = P3<<24 | P2<<16 | P1<<8 | P0,  eight buckets per field,
+//   Pj bucket k : some pattern of bucket k has byte y at match position j preceded by byte x
+//                 (j = 0: x is the byte before the match; 0xFF = start of unit)
+//   acc' = ((acc << 8) | 0xFF) & T[h(prev, cur)];   (acc & PF_HIT) != 0 after feeding byte p
+//   <=> some bucket admits a match starting at p-3.  Same window (5 bytes), same candidate position,
+//   no false negatives (hash collisions only add admitted pairs).
+static const uint32_t PF_SLOTS = 1024, PF_BUCKETS = 8, PF_HIT = 0xFF000000u, PF_MULT = 0x9E3779B1u;
+CF_HD uint32_t pair_hash(uint32_t prev, uint32_t cur) {
+  const uint32_t u = (prev | (cur << 8)) * 0x00010001u;     // {prev, cur, prev, cur}: one PRMT on the GPU
+  return (u * PF_MULT) >> 22;
+}
+CF_HD uint32_t pair_step(uint32_t acc, uint32_t e) { return ((acc << 8) | 0xFFu) & e; }
+
 }  // namespace cf

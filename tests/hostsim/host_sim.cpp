@@ -40,10 +40,16 @@ int cfh_scan(cf_builder* b, const uint8_t* stream, uint64_t nbytes, const uint64
   const uint8_t* s = pad.data() + cf::FRONT_PAD;   // s[-FRONT_PAD..] valid
   uint32_t acc = 0;
   uint64_t ncand = 0, nsteps = 0;
+  const bool pairs = co.filter.use_pairs;
   // feed from LOOKBACK bytes before the stream to START_OFF bytes after (the last start is nbytes-1)
   for (int64_t p = -(int64_t)cf::F_LOOKBACK; p < (int64_t)nbytes + (int64_t)cf::F_START_OFF; ++p) {
-    acc = cf::filter_step(acc, co.filter.E[s[p]]);
-    if (!(acc & cf::F_HIT)) continue;
+    if (pairs) {
+      acc = cf::pair_step(acc, co.filter.pairT[cf::pair_hash(s[p - 1], s[p])]);
+      if (!(acc & cf::PF_HIT)) continue;
+    } else {
+      acc = cf::filter_step(acc, co.filter.E[s[p]]);
+      if (!(acc & cf::F_HIT)) continue;
+    }
     int64_t start = p - (int64_t)cf::F_START_OFF;
     if (start < 0 || start >= (int64_t)nbytes) continue;
     if ((s[start] & 0xC0) == 0x80) continue;   // not a character boundary

@@ -140,3 +140,63 @@ def test_unsupported_and_invalid():
     hp.add(r"x*", 0, ordered=True, repl="-")
     with pytest.raises(RuntimeError):
         hp.compile()  # empty-matching substitution rule -> CF_E_UNSUPPORTED
+
+
+def _big_rule_set(n_words, seed=0):
+    rng = random.Random(seed)
+    syll = ["ba", "co", "di", "fu", "ge", "ha", "ki", "lo", "mu", "ne", "pi", "qua", "ro", "su", "ty", "vo", "wi", "xe", "yo", "zu", "sch", "tion", "ing"]
+    words = set()
+    while len(words) < n_words:
+        words.add("".join(rng.choice(syll) for _ in range(rng.randint(2, 4))))
+    return sorted(words)
+
+
+@pytest.mark.parametrize("n_words", [40, 300])
+def test_large_rule_sets_switch_to_the_pair_prefilter_and_stay_exact(n_words):
+    """Large deny lists: the compiler must pick the pair prefilter (the byte filter would admit far too many
+    windows) and the verdicts must still equal CPython's, including case-insensitive and \\b rules mixed in."""
+    import re as _re
+    words = _big_rule_set(n_words)
+    p = HostProgram()
+    pats = []
+    for i, w in enumerate(words):
+        if i % 7 == 0:
+            pat, fl = r"\b" + w + r"\b", _re.I
+        elif i % 7 == 1:
+            pat, fl = w[:-1] + "[" + w[-1] + w[-1].upper() + "]s?", 0
+        else:
+            pat, fl = _re.escape(w), 0
+        pats.append((pat, fl))
+        p.add(pat, fl)
+    stats = p.compile()
+    if n_words >= 300:
+        assert stats[7] == 1, "pair prefilter expected for a large rule set"
+    rng = random.Random(1)
+    filler = "the quick brown fox jumps over the lazy dog while json payloads flow through gateways".split()
+    units = []
+    for u in range(400):
+        toks = []
+        for _ in range(rng.randint(0, 60)):
+            r = rng.random()
+            if r < 0.08:
+                w = rng.choice(words)
+                w = w.upper() if rng.random() < 0.3 else w
+                toks.append(w + ("s" if rng.random() < 0.2 else ""))
+            elif r < 0.12:
+                toks.append(rng.choice(words)[:-1])                 # near miss
+            elif r < 0.14:
+                toks.append("ſK" + rng.choice(words))       # long s / Kelvin sign next to a word
+            else:
+                toks.append(rng.choice(filler))
+        units.append((" " if rng.random() < 0.5 else "_").join(toks))
+    got, st = p.scan(units)
+    exp = []
+    comp = [_re.compile(pt, fl) for pt, fl in pats]
+    for u in units:
+        v = 0
+        for i, c in enumerate(comp):
+            if c.search(u):
+                v |= 1 << i
+        exp.append(v)
+    assert got == exp
+    assert sum(1 for v in exp if v) > 100

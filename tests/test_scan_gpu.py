@@ -140,3 +140,40 @@ def test_candidate_dense_input_overflows_queue():
     assert all(got[i] == exp[i % 16] for i in range(2048))
     cand, _ = engine.Context.get().scan_counters()
     assert cand > (1 << 20)          # really did exceed the queue capacity
+
+
+@pytest.mark.parametrize("n_extra", [40, 400])
+def test_large_rule_sets_pair_prefilter_kernel(n_extra, monkeypatch):
+    """The pair-prefilter variant of the scan kernel (forced, so that both table kinds are covered at both rule
+    set sizes) against the oracle: default rules + many more deny words, hits at tile / lane / pair boundaries."""
+    monkeypatch.setenv("CF_PAIR_FILTER", "1")
+    rng = random.Random(n_extra)
+    syll = ["ba", "co", "di", "fu", "ge", "ha", "ki", "lo", "mu", "ne", "pi", "qua", "ro", "su", "ty", "vo", "wi", "xe", "yo", "zu", "sch", "tion"]
+    words = set()
+    while len(words) < n_extra:
+        words.add("".join(rng.choice(syll) for _ in range(rng.randint(2, 4))))
+    words = sorted(words)
+    p = engine.Program()
+    for pat, f in HARMFUL:
+        p.add_search(pat, f)
+    for w in DENY + words:
+        p.add_literal(w)
+    for pat, f, r in SUBS:
+        p.add_sub(pat, f, r)
+    st = p.compile_host()
+    assert st.prefilter == 1
+    p.compile(engine.Context.get())
+    base = [synth.payload(s, 16384, seed=k, hit_rate=1e-3) for k, s in enumerate("ABCCAB")]
+    units = []
+    for i in range(600):
+        t = base[i % 6]
+        cut = rng.randrange(0, 4096)
+        w = rng.choice(words + DENY + ["kill him", "Kill yourself", "crap"])
+        units.append(t[:cut] + " " + w + " " + t[cut:cut + rng.randrange(100, 12000)])
+    # exact 64-byte / 2048-byte alignment sweeps of one hit
+    for off in range(0, 130):
+        units.append("x" * off + words[off % len(words)] + " tail")
+    got = engine.scan_units(p, units)
+    exp = ref.scan_bitmaps(units, HARMFUL, DENY + words, [(q, f) for q, f, _ in SUBS])
+    assert got == exp
+    assert sum(1 for v in exp if v) > 600
