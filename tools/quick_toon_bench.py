@@ -16,8 +16,12 @@ if len(sys.argv) > 2:
     a = sys.argv[2:]
     CASES = [(a[i], int(a[i + 1]), int(a[i + 2])) for i in range(0, len(a), 3)]
 for shape, size, n in CASES:
-    base = [synth.payload(shape, size, seed=s).encode() for s in range(64)]
-    texts = [base[i % 64] for i in range(n)]
+    if shape == "M":   # BASELINE configs[3]: mixed 2 / 16 / 256 KiB tabular payloads (by count 80 % / 19 % / 1 %)
+        pool = {k: [synth.payload("A", k, seed=s).encode() for s in range(8)] for k in (2048, 16384, 262144)}
+        texts = [pool[262144 if i % 100 == 0 else 16384 if i % 5 == 0 else 2048][i % 8] for i in range(n)]
+    else:
+        base = [synth.payload(shape, size, seed=s).encode() for s in range(64)]
+        texts = [base[i % 64] for i in range(n)]
     stream, offs = engine.pack_units(texts)
     batch = engine.Batch(b.ctx, len(stream), n)
     batch.upload(stream, offs)
