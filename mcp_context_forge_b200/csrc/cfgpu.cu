@@ -1127,10 +1127,8 @@ int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t st
   if (offsets[0] != 0 || offsets[n_units] != stream_bytes) { ctx->err = "offsets[0] must be 0 and offsets[n] the stream length"; return CF_E_BADARG; }
   cudaStream_t st = (cudaStream_t)cuda_stream;
   uint8_t* d_stream = b->d_buf + cf::FRONT_PAD;
-  CF_CUDA(ctx, cudaMemcpyAsync(d_stream, stream, stream_bytes, cudaMemcpyHostToDevice, st));
-  // re-arm the tail padding that a previous, longer upload may have overwritten
-  uint64_t end = (ntiles_for(b->nbytes > stream_bytes ? b->nbytes : stream_bytes, MAX_TILE) + 1) * (uint64_t)MAX_TILE;
-  CF_CUDA(ctx, cudaMemsetAsync(d_stream + stream_bytes, 0xFF, end - stream_bytes, st));
+  // small transfers first (offsets and the coarse index usually come from pageable memory: staged copies that
+  // would otherwise queue behind the big one), then the stream itself
   CF_CUDA(ctx, cudaMemcpyAsync(b->d_offsets, offsets, ((uint64_t)n_units + 1) * 8, cudaMemcpyHostToDevice, st));
   {  // coarse unit index (host sweep over offsets; tiny next to the stream copy)
     const uint64_t nc = (stream_bytes >> COARSE_SHIFT) + 1;
@@ -1143,6 +1141,10 @@ int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t st
     }
     CF_CUDA(ctx, cudaMemcpyAsync(b->d_coarse, b->h_coarse.data(), nc * 4, cudaMemcpyHostToDevice, st));
   }
+  // re-arm the tail padding that a previous, longer upload may have overwritten
+  const uint64_t end = (ntiles_for(b->nbytes > stream_bytes ? b->nbytes : stream_bytes, MAX_TILE) + 1) * (uint64_t)MAX_TILE;
+  CF_CUDA(ctx, cudaMemsetAsync(d_stream + stream_bytes, 0xFF, end - stream_bytes, st));
+  CF_CUDA(ctx, cudaMemcpyAsync(d_stream, stream, stream_bytes, cudaMemcpyHostToDevice, st));
   b->nbytes = stream_bytes;
   b->n = n_units;
   b->generation++;
@@ -1195,22 +1197,20 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   return CF_OK;
 }
 
+static int dev_reserve(cf_ctx* ctx, cf_ctx::DevBuf& b, size_t need);
+
 int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
                  const uint64_t* offsets, uint32_t n_units, uint64_t* h_bitmaps) {
   if (!h_bitmaps) return CF_E_BADARG;
   int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
   if (rc) return rc;
-  uint64_t* d_bm = nullptr;
-  size_t bytes = (size_t)n_units * p->W * 8;
-  CF_CUDA(ctx, cudaMallocAsync((void**)&d_bm, bytes, 0));
-  rc = cf_scan(ctx, p, b, d_bm, nullptr);
-  if (rc == CF_OK) {
-    cudaError_t e = cudaMemcpyAsync(h_bitmaps, d_bm, bytes, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = CF_E_CUDA; }
-  }
-  cudaFreeAsync(d_bm, 0);
-  return rc;
+  const size_t bytes = (size_t)n_units * p->W * 8;
+  if ((rc = dev_reserve(ctx, ctx->tmp[6], bytes))) return rc;
+  uint64_t* d_bm = (uint64_t*)ctx->tmp[6].p;
+  if ((rc = cf_scan(ctx, p, b, d_bm, nullptr))) return rc;
+  CF_CUDA(ctx, cudaMemcpyAsync(h_bitmaps, d_bm, bytes, cudaMemcpyDeviceToHost, 0));
+  CF_CUDA(ctx, cudaStreamSynchronize(0));
+  return CF_OK;
 }
 
 int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uint32_t n_sel, uint8_t* out_bytes,
