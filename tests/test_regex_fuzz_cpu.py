@@ -75,7 +75,12 @@ def run_round(seed):
     if not pats:
         return 0, []
     units = ["".join(rng.choice(ALPH) for _ in range(rng.randint(0, 30))) for _ in range(300)] + ["", "\n", "a\n"]
-    got, _ = hp.scan(units)
+    try:
+        got, _ = hp.scan(units)
+    except RuntimeError as exc:            # a loud, documented limit (automaton size) is not a mismatch
+        if "too large" in str(exc):
+            return 0, []
+        raise
     bad = []
     for u, g in zip(units, got):
         exp = 0
