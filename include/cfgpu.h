@@ -26,6 +26,10 @@
  *          what `orjson.loads` (toon_encoder.py:281), `serde_json::from_slice` (lib.rs:353) and the
  *          string walk `_iter_strings` (harmful_content_detector.py:110-139) each recompute per payload
  *
+ * Environment (read once per process; defaults are the measured best on B200):
+ *   CF_SCAN_WARPS / CF_SCAN_LB / CF_SCAN_ACC / CF_SCAN_STAGES   scan kernel variant (16 / 64 / 1 / 3)
+ *   CF_PAIR_FILTER=0|1   force the byte / pair prefilter instead of choosing per rule set (tests, measurements)
+ *
  * Conventions: every function returns CF_OK (0) or a negative CF_E_* code and never throws.
  * All buffers are caller-owned.  A cf_ctx belongs to one device; calls on one ctx must be
  * serialised by the caller (the Python host holds one ctx per process/GPU).
