@@ -795,7 +795,7 @@ __global__ void sub_compact_kernel(const uint8_t* __restrict__ stream, const uin
 // ------------------------------------------------------------------------------------------------
 static const uint32_t IDX_AHEAD = 8;     // chunks of 32 bytes in flight per warp
 __device__ __forceinline__ uint32_t warp_index(const uint8_t* __restrict__ s, uint32_t n, cfx::Tok* __restrict__ tk, bool* unterminated,
-                                               uint32_t lane) {
+                                               uint32_t lane, const uint8_t* __restrict__ cls) {
   cfx::IndexCarry cy;
   cy.init();
   uint32_t nt = 0;
@@ -811,11 +811,11 @@ __device__ __forceinline__ uint32_t warp_index(const uint8_t* __restrict__ s, ui
     for (uint32_t k = 0; k < IDX_AHEAD; ++k) {
       const uint32_t base = base0 + 32 * k;
       if (base >= n) break;
-      const uint32_t c = cs[k];
-      const uint32_t bs = __ballot_sync(0xFFFFFFFFu, c == '\\');
-      const uint32_t qm = __ballot_sync(0xFFFFFFFFu, c == '"');
-      const uint32_t st = __ballot_sync(0xFFFFFFFFu, cfx::is_structural(c));
-      const uint32_t ws = __ballot_sync(0xFFFFFFFFu, cfj::j_ws(c));
+      const uint32_t kc = cls[cs[k]];            // byte class from a 256-byte shared table: 1 LDS instead of ~14 compares
+      const uint32_t bs = __ballot_sync(0xFFFFFFFFu, (kc & 1u) != 0);
+      const uint32_t qm = __ballot_sync(0xFFFFFFFFu, (kc & 2u) != 0);
+      const uint32_t st = __ballot_sync(0xFFFFFFFFu, (kc & 4u) != 0);
+      const uint32_t ws = __ballot_sync(0xFFFFFFFFu, (kc & 8u) != 0);
       uint32_t esc = 0;
       if (bs | cy.bs_parity) {
         esc = __ballot_sync(0xFFFFFFFFu, cfx::escaped_bit(bs, lane, cy.bs_parity) != 0);
@@ -841,6 +841,10 @@ static const uint32_t NTOK_UNTERMINATED = 0x80000000u;
 __global__ void __launch_bounds__(128) json_index_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
                                                           cfx::Tok* __restrict__ toks, uint32_t* __restrict__ ntok, uint64_t max_len,
                                                           uint32_t flags) {
+  __shared__ uint8_t cls[256];       // bit 0 backslash, 1 quote, 2 structural, 3 JSON whitespace
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+    cls[i] = (uint8_t)((i == '\\' ? 1u : 0u) | (i == '"' ? 2u : 0u) | (cfx::is_structural(i) ? 4u : 0u) | (cfj::j_ws(i) ? 8u : 0u));
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= n_units) return;
@@ -850,7 +854,7 @@ __global__ void __launch_bounds__(128) json_index_kernel(const uint8_t* __restri
   const uint32_t len = (uint32_t)len64;
   cfx::Tok* tk = toks + b;
   bool unt;
-  const uint32_t nt = warp_index(stream + b, len, tk, &unt, lane);
+  const uint32_t nt = warp_index(stream + b, len, tk, &unt, lane, cls);
   __syncwarp();
   if (flags & CF_INDEX_CLASSIFY)
     for (uint32_t t = lane; t < nt; t += 32) tk[t].aux = cfx::classify_token(stream + b, len, tk[t].pos);
