@@ -18,98 +18,8 @@
 #include <string>
 #include <vector>
 
-#include "cf_host.h"
-#include "json_index.h"
-#include "json_mask.h"
-#include "json_toon.h"
-#include "scan_core.h"
 
-// ------------------------------------------------------------------------------------------------
-// host-side objects
-// ------------------------------------------------------------------------------------------------
-static const uint32_t LANE_BYTES = 64;
-static const uint32_t WARP_BYTES = 32 * LANE_BYTES;          // 2 KiB per warp per tile
-static const uint32_t MAX_WARPS = 32;   // padding granularity (>= every variant's tile)
-static const uint32_t MAX_TILE = MAX_WARPS * WARP_BYTES;     // buffers are padded for the largest tile
-
-struct cf_ctx {
-  int device = 0;
-  int sm_count = 0;
-  std::string err;
-  uint64_t launches = 0;
-  uint64_t* d_qstate = nullptr;     // two {candidates appended, verify steps} pairs, used alternately
-  uint32_t qphase = 0;
-  uint64_t* d_queue = nullptr;      // candidate start positions
-  uint32_t qcap = 1u << 20;
-  void* d_toon_scratch = nullptr;   // DOM node arrays for toon_kernel (grown on demand)
-  uint64_t toon_scratch_bytes = 0;
-  struct DevBuf { void* p = nullptr; size_t cap = 0; };
-  DevBuf tmp[8];                    // grow-only device scratch of the *_host entry points (no cudaMalloc per call)
-  DevBuf d_tok, d_ntok;             // structural index of the current batch (json_index_kernel)
-  void* h_stage = nullptr;          // pinned host staging for gathered results
-  size_t h_stage_bytes = 0;
-  // optional per-launch timing of the dominant kernel (bench.py roofline): event pairs
-  std::vector<cudaEvent_t> prof_ev;
-  uint32_t prof_used = 0;
-  bool prof_on = false;
-  // scan kernel configuration (CF_SCAN_WARPS / CF_SCAN_ACC override the defaults; experiments)
-  uint32_t scan_warps = 16;        // best of the measured variants (profiles/README.md)
-  uint32_t scan_lane_bytes = 64;
-  uint32_t scan_acc = 1;
-  uint32_t scan_stages = 3;
-  uint32_t tile() const { return scan_warps * 32 * scan_lane_bytes; }
-  uint32_t box_rows() const { uint32_t rows = tile() / 128, nbox = (rows + 255) / 256; return rows / nbox; }
-};
-
-struct DevDfa {
-  cf::DfaTables t;
-  std::vector<void*> allocs;
-  uint64_t trans_bytes = 0, acc_bytes = 0, stage_bytes = 0;   // sizes for staging in shared memory
-};
-
-struct cf_prog {
-  cf_ctx* ctx = nullptr;
-  uint32_t npat = 0, W = 1;
-  DevDfa search;
-  uint32_t* d_E = nullptr;         // byte prefilter E[256], or the pair prefilter's T[PF_SLOTS] when use_pairs
-  bool use_pairs = false;
-  uint64_t* d_always = nullptr;
-  bool any_always = false;
-  bool search_empty = false;       // every pattern is "always" -> no automaton work at all
-  std::vector<DevDfa> ordered;
-  std::vector<uint32_t*> d_ordered_E;
-  std::vector<int> ordered_pat;    // pattern index of each ordered rule
-  std::vector<uint8_t*> d_repl;
-  std::vector<uint32_t> repl_len;
-  std::vector<uint32_t> ordered_minlen;   // minimum match length (code points) of each ordered rule
-  std::vector<uint64_t> h_offsets;        // host copy of the last batch's offsets (cf_sub_host sizing)
-  const void* h_offsets_owner = nullptr;
-  uint64_t h_offsets_gen = 0;
-};
-
-struct cf_batch {
-  cf_ctx* ctx = nullptr;
-  uint8_t* d_buf = nullptr;        // FRONT_PAD + stream + tail pad
-  uint64_t* d_offsets = nullptr;
-  uint32_t* d_coarse = nullptr;    // unit index at every 4 KiB of stream (built on upload)
-  std::vector<uint32_t> h_coarse;
-  uint64_t cap_bytes = 0;
-  uint32_t cap_units = 0;
-  uint64_t nbytes = 0;
-  uint32_t n = 0;
-  uint64_t generation = 0;         // bumped by every upload
-  CUtensorMap tmap;                // 2-D view of d_buf: rows of 128 B, box = one scan tile, SWIZZLE_128B
-};
-
-
-#define CF_CUDA(ctx, call)                                                                  \
-  do {                                                                                      \
-    cudaError_t e_ = (call);                                                                \
-    if (e_ != cudaSuccess) {                                                                \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
-      return CF_E_CUDA;                                                                     \
-    }                                                                                       \
-  } while (0)
+#include "cf_internal.h"
 
 // ------------------------------------------------------------------------------------------------
 // device helpers: mbarrier + 1-D TMA bulk copy
@@ -782,158 +692,6 @@ __global__ void sub_compact_kernel(const uint8_t* __restrict__ stream, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// JSON structural index (csrc/json_index.h), one WARP per unit:
-//   stage 1   one ballot per byte class and 32 bytes (bytes prefetched eight chunks ahead): escape parity,
-//             in-string mask by prefix XOR, structural characters, scalar starts -> token positions
-//   stage 1b  (CF_INDEX_CLASSIFY) lane-parallel over the tokens: strings validated + their predicates/hash,
-//             scalars validated — the same functions the sequential parser uses
-// Measured as a front end of the TOON / masking kernels (index kernel + token-driven DOM build per lane)
-// it LOSES to the sequential per-lane parser on B200 at large batches (15.8 vs 10.1 ms for 32 768 x 16 KiB:
-// stage 1b is issue-bound at ~12 warp-instructions per byte and the tokens triple the memory traffic), so
-// those kernels keep json_parse; the index stands alone as a reusable op (string extraction, length
-// guards) and as the first stage of the token-parallel design the next round needs.
-// ------------------------------------------------------------------------------------------------
-static const uint32_t IDX_AHEAD = 8;     // chunks of 32 bytes in flight per warp
-__device__ __forceinline__ uint32_t warp_index(const uint8_t* __restrict__ s, uint32_t n, cfx::Tok* __restrict__ tk, bool* unterminated,
-                                               uint32_t lane, const uint8_t* __restrict__ cls) {
-  cfx::IndexCarry cy;
-  cy.init();
-  uint32_t nt = 0;
-  const uint32_t below = (1u << lane) - 1u;
-  for (uint32_t base0 = 0; base0 < n; base0 += 32 * IDX_AHEAD) {
-    uint32_t cs[IDX_AHEAD];
-#pragma unroll
-    for (uint32_t k = 0; k < IDX_AHEAD; ++k) {
-      const uint32_t p = base0 + 32 * k + lane;
-      cs[k] = p < n ? (uint32_t)s[p] : (uint32_t)' ';
-    }
-#pragma unroll
-    for (uint32_t k = 0; k < IDX_AHEAD; ++k) {
-      const uint32_t base = base0 + 32 * k;
-      if (base >= n) break;
-      const uint32_t kc = cls[cs[k]];            // byte class from a 256-byte shared table: 1 LDS instead of ~14 compares
-      const uint32_t bs = __ballot_sync(0xFFFFFFFFu, (kc & 1u) != 0);
-      const uint32_t qm = __ballot_sync(0xFFFFFFFFu, (kc & 2u) != 0);
-      const uint32_t st = __ballot_sync(0xFFFFFFFFu, (kc & 4u) != 0);
-      const uint32_t ws = __ballot_sync(0xFFFFFFFFu, (kc & 8u) != 0);
-      uint32_t esc = 0;
-      if (bs | cy.bs_parity) {
-        esc = __ballot_sync(0xFFFFFFFFu, cfx::escaped_bit(bs, lane, cy.bs_parity) != 0);
-        cy.bs_parity = cfx::next_bs_parity(bs, cy.bs_parity);
-      }
-      uint32_t close;
-      const uint32_t tm = cfx::index_chunk(qm & ~esc, st, ws, cy, &close);
-      if ((tm >> lane) & 1u) {
-        cfx::Tok t;
-        t.pos = (base + lane) | (((close >> lane) & 1u) ? cfx::T_CLOSE : 0u);
-        t.aux = 0;
-        tk[nt + __popc(tm & below)] = t;
-      }
-      nt += __popc(tm);
-    }
-  }
-  *unterminated = cy.in_string != 0;
-  return nt;
-}
-
-static const uint32_t NTOK_UNTERMINATED = 0x80000000u;
-// tokens of unit u at toks + offsets[u] (capacity len + 1: offsets count one terminator per unit); ntok[u] = count | flag
-__global__ void __launch_bounds__(128) json_index_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
-                                                          cfx::Tok* __restrict__ toks, uint32_t* __restrict__ ntok, uint64_t max_len,
-                                                          uint32_t flags) {
-  __shared__ uint8_t cls[256];       // bit 0 backslash, 1 quote, 2 structural, 3 JSON whitespace
-  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
-    cls[i] = (uint8_t)((i == '\\' ? 1u : 0u) | (i == '"' ? 2u : 0u) | (cfx::is_structural(i) ? 4u : 0u) | (cfj::j_ws(i) ? 8u : 0u));
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (u >= n_units) return;
-  const uint64_t b = offsets[u];
-  const uint64_t len64 = offsets[u + 1] - b - 1;
-  if (len64 > max_len) { if (lane == 0) ntok[u] = 0; return; }
-  const uint32_t len = (uint32_t)len64;
-  cfx::Tok* tk = toks + b;
-  bool unt;
-  const uint32_t nt = warp_index(stream + b, len, tk, &unt, lane, cls);
-  __syncwarp();
-  if (flags & CF_INDEX_CLASSIFY)
-    for (uint32_t t = lane; t < nt; t += 32) tk[t].aux = cfx::classify_token(stream + b, len, tk[t].pos);
-  if (lane == 0) ntok[u] = nt | (unt ? NTOK_UNTERMINATED : 0u);
-}
-
-// toon_encoder: output for unit i goes to out + offsets[i]; a conversion is only produced when it is strictly
-// smaller than the input (plugins/toon_encoder/toon_encoder.py:295-303).
-__global__ void __launch_bounds__(64) toon_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
-                                                   uint32_t n_units, cfj::JNode* __restrict__ nodes, uint8_t* __restrict__ out,
-                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t flags, uint32_t upw) {
-  const uint32_t lane = threadIdx.x & 31;
-  if (lane >= upw) return;
-  const uint32_t u = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * upw + lane;
-  if (u >= n_units) return;
-  const uint64_t b = offsets[u];
-  const uint64_t len64 = offsets[u + 1] - b - 1;
-  if (len64 > 0x7FFFFFFFull) { status[u] = cfj::TS_UNSUPPORTED; out_len[u] = 0; return; }
-  const uint32_t len = (uint32_t)len64;
-  cfj::JNode* my = nodes + (b >> 1) + 4ull * u;
-  if (flags & CF_TOON_PARSE_ONLY) {
-    uint32_t cnt = 0;
-    const int pr = cfj::json_parse(stream + b, len, my, len / 2 + 4, &cnt);
-    status[u] = pr; out_len[u] = cnt;
-    return;
-  }
-  cfj::Big big;
-  uint8_t digits[1240];
-  uint32_t ol = 0;
-  const int st = cfj::toon_process(stream + b, len, my, len / 2 + 4, out + b, len ? len - 1 : 0, &ol, &big, digits, sizeof(digits), (flags & 1u) == 0);
-  status[u] = st;
-  out_len[u] = st == cfj::TS_CONVERTED ? ol : 0;
-}
-
-// request_logging_masking: mask_sensitive_json_bytes per unit (csrc/json_mask.h), plus a key classifier
-// kernel for the object-level entry points of the drop-in module.
-__global__ void __launch_bounds__(64) mask_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
-                                                   cfj::JNode* __restrict__ nodes, uint32_t* __restrict__ idx, uint8_t* __restrict__ out,
-                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, int max_depth, uint32_t upw) {
-  const uint32_t lane = threadIdx.x & 31;
-  if (lane >= upw) return;
-  const uint32_t u = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * upw + lane;
-  if (u >= n_units) return;
-  const uint64_t b = offsets[u];
-  const uint64_t len64 = offsets[u + 1] - b - 1;
-  if (len64 > 0x30000000ull) { status[u] = cfm::MS_UNSUPPORTED; out_len[u] = 0; return; }
-  const uint32_t len = (uint32_t)len64;
-  cfj::JNode* my = nodes + (b >> 1) + 4ull * u;
-  uint32_t* myidx = idx + (b >> 1) + 4ull * u;
-  cfj::Big big;
-  uint8_t digits[1240];
-  cfm::NumWork w{&big, &big, digits, (uint32_t)sizeof(digits)};
-  uint32_t ol = 0;
-  const int st = cfm::mask_process(stream + b, len, my, len / 2 + 4, myidx, len / 2 + 4, out + 5 * b + 32ull * u, 5 * len + 32, &ol, max_depth, w);
-  status[u] = st;
-  out_len[u] = st == cfm::MS_OK ? ol : 0;
-}
-
-// gather per-unit results (unit u at src + mul*offsets[u] + add*u, out_len[u] bytes) into one contiguous buffer
-__global__ void compact_kernel(const uint8_t* __restrict__ src, uint32_t mul, uint32_t add, const uint64_t* __restrict__ offsets,
-                               const uint32_t* __restrict__ out_len, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out,
-                               uint32_t n_units) {
-  const uint32_t u = blockIdx.x;
-  if (u >= n_units) return;
-  const uint8_t* s = src + (uint64_t)mul * offsets[u] + (uint64_t)add * u;
-  uint8_t* dst = out + out_off[u];
-  for (uint32_t i = threadIdx.x; i < out_len[u]; i += blockDim.x) dst[i] = s[i];
-}
-
-__global__ void classify_keys_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
-                                     uint8_t* __restrict__ sensitive) {
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n_units) return;
-  const uint64_t b = offsets[u];
-  cfj::JNode k{cfj::J_KEY, 0, (uint32_t)(offsets[u + 1] - b - 1), 0};   // raw key text (no JSON escapes)
-  sensitive[u] = cfm::key_sensitive(stream + b, k) ? 1 : 0;
-}
-
-// ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -1201,7 +959,6 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   return CF_OK;
 }
 
-static int dev_reserve(cf_ctx* ctx, cf_ctx::DevBuf& b, size_t need);
 
 int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
                  const uint64_t* offsets, uint32_t n_units, uint64_t* h_bitmaps) {
@@ -1209,7 +966,7 @@ int cf_scan_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint8_t* stream, ui
   int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
   if (rc) return rc;
   const size_t bytes = (size_t)n_units * p->W * 8;
-  if ((rc = dev_reserve(ctx, ctx->tmp[6], bytes))) return rc;
+  if ((rc = cf_dev_reserve(ctx, ctx->tmp[6], bytes))) return rc;
   uint64_t* d_bm = (uint64_t*)ctx->tmp[6].p;
   if ((rc = cf_scan(ctx, p, b, d_bm, nullptr))) return rc;
   CF_CUDA(ctx, cudaMemcpyAsync(h_bitmaps, d_bm, bytes, cudaMemcpyDeviceToHost, 0));
@@ -1297,177 +1054,6 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
   } while (0);
   cudaFree(d_scratch); cudaFree(d_sel); cudaFree(d_soff); cudaFree(d_bound); cudaFree(d_rec); cudaFree(d_ooff); cudaFree(d_out);
   return rc;
-}
-
-static int dev_reserve(cf_ctx* ctx, cf_ctx::DevBuf& b, size_t need) {
-  if (need <= b.cap) return CF_OK;
-  cudaFree(b.p);
-  b.p = nullptr; b.cap = 0;
-  const size_t c = need + need / 4 + 256;
-  CF_CUDA(ctx, cudaMalloc(&b.p, c));
-  b.cap = c;
-  return CF_OK;
-}
-static int stage_reserve(cf_ctx* ctx, size_t need) {
-  if (need <= ctx->h_stage_bytes) return CF_OK;
-  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-  ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
-  const size_t c = need + need / 4 + 4096;
-  CF_CUDA(ctx, cudaHostAlloc(&ctx->h_stage, c, cudaHostAllocDefault));
-  ctx->h_stage_bytes = c;
-  return CF_OK;
-}
-// units per warp for the thread-per-unit JSON kernels: fill the GPU with warps first (about 12 resident
-// warps per SM at their register footprint), only then put several units into one warp
-static uint32_t units_per_warp(const cf_ctx* ctx, uint32_t n) {
-  const uint32_t warps = (uint32_t)ctx->sm_count * 12u;
-  uint32_t u = 1;
-  while (u < 32 && (n + u - 1) / u > warps) u <<= 1;
-  return u;
-}
-static uint32_t json_blocks(uint32_t n, uint32_t upw) { return ((n + upw - 1) / upw + 1) / 2; }   // two warps per block
-int cf_json_index(cf_ctx* ctx, cf_batch* b, uint32_t flags, cf_json_token* d_tokens, uint32_t* d_counts, void* cuda_stream) {
-  if (!ctx || !b || !d_tokens || !d_counts) return CF_E_BADARG;
-  if (b->n == 0) return CF_OK;
-  static_assert(sizeof(cf_json_token) == sizeof(cfx::Tok), "token layout");
-  json_index_kernel<<<(b->n + 3) / 4, 128, 0, (cudaStream_t)cuda_stream>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfx::Tok*)d_tokens, d_counts,
-                                                                            0x7FFFFFFFull, flags);
-  ctx->launches++;
-  CF_CUDA(ctx, cudaGetLastError());
-  return CF_OK;
-}
-
-int cf_json_index_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
-                       uint32_t n_units, cf_json_token* tokens, uint32_t* counts) {
-  if (!ctx || !b || !tokens || !counts) return CF_E_BADARG;
-  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
-  if (rc) return rc;
-  if ((rc = dev_reserve(ctx, ctx->d_tok, (size_t)(stream_bytes + 64) * sizeof(cfx::Tok)))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->d_ntok, (size_t)(n_units + 1) * 4))) return rc;
-  if ((rc = cf_json_index(ctx, b, flags, (cf_json_token*)ctx->d_tok.p, (uint32_t*)ctx->d_ntok.p, nullptr))) return rc;
-  CF_CUDA(ctx, cudaMemcpy(counts, ctx->d_ntok.p, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-  CF_CUDA(ctx, cudaMemcpy(tokens, ctx->d_tok.p, (size_t)stream_bytes * sizeof(cfx::Tok), cudaMemcpyDeviceToHost));
-  return CF_OK;
-}
-
-int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
-  if (!ctx || !b || !b->n || !d_out || !d_out_len || !d_status) return CF_E_BADARG;
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  const uint64_t need = (b->nbytes / 2 + 4ull * b->n + 8) * sizeof(cfj::JNode);
-  if (need > ctx->toon_scratch_bytes) {
-    CF_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaFree(ctx->d_toon_scratch);
-    ctx->d_toon_scratch = nullptr;
-    ctx->toon_scratch_bytes = 0;
-    CF_CUDA(ctx, cudaMalloc(&ctx->d_toon_scratch, need + need / 4));
-    ctx->toon_scratch_bytes = need + need / 4;
-  }
-  const uint32_t upw = units_per_warp(ctx, b->n);
-  toon_kernel<<<json_blocks(b->n, upw), 64, 0, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfj::JNode*)ctx->d_toon_scratch, d_out, d_out_len,
-                                                     d_status, flags, upw);
-  ctx->launches++;
-  CF_CUDA(ctx, cudaGetLastError());
-  return CF_OK;
-}
-
-int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
-                 uint32_t n_units, uint8_t* out_stream, uint32_t* out_len, int32_t* status) {
-  if (!out_stream || !out_len || !status) return CF_E_BADARG;
-  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
-  if (rc) return rc;
-  // device: encode in the input's layout, then gather the converted texts so that only they cross PCIe
-  if ((rc = dev_reserve(ctx, ctx->tmp[0], stream_bytes + 16))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[1], (size_t)n_units * 4))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[3], ((size_t)n_units + 1) * 8))) return rc;
-  uint8_t* d_out = (uint8_t*)ctx->tmp[0].p;
-  uint32_t* d_len = (uint32_t*)ctx->tmp[1].p;
-  int32_t* d_st = (int32_t*)ctx->tmp[2].p;
-  uint64_t* d_ooff = (uint64_t*)ctx->tmp[3].p;
-  rc = cf_toon(ctx, b, flags, d_out, d_len, d_st, nullptr);
-  if (rc) return rc;
-  CF_CUDA(ctx, cudaMemcpy(out_len, d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-  CF_CUDA(ctx, cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-  if (flags & CF_TOON_PARSE_ONLY) return CF_OK;
-  std::vector<uint64_t> ooff((size_t)n_units + 1);
-  uint64_t total = 0;
-  for (uint32_t i = 0; i < n_units; ++i) { ooff[i] = total; total += out_len[i]; }
-  ooff[n_units] = total;
-  if (!total) return CF_OK;
-  if ((rc = dev_reserve(ctx, ctx->tmp[4], total))) return rc;
-  if ((rc = stage_reserve(ctx, total))) return rc;
-  CF_CUDA(ctx, cudaMemcpy(d_ooff, ooff.data(), ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
-  compact_kernel<<<n_units, 128>>>(d_out, 1, 0, b->d_offsets, d_len, d_ooff, (uint8_t*)ctx->tmp[4].p, n_units);
-  ctx->launches++;
-  CF_CUDA(ctx, cudaGetLastError());
-  CF_CUDA(ctx, cudaMemcpy(ctx->h_stage, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
-  for (uint32_t i = 0; i < n_units; ++i)
-    if (out_len[i]) memcpy(out_stream + offsets[i], (const uint8_t*)ctx->h_stage + ooff[i], out_len[i]);
-  return CF_OK;
-}
-
-int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
-                 int max_depth, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, int32_t* status, uint64_t* out_needed) {
-  if (!ctx || !b || !out_offsets || !status) return CF_E_BADARG;
-  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
-  if (rc) return rc;
-  const uint64_t nnodes = stream_bytes / 2 + 4ull * n_units + 8;
-  const uint64_t need = nnodes * sizeof(cfj::JNode);
-  if (need > ctx->toon_scratch_bytes) {
-    cudaFree(ctx->d_toon_scratch);
-    ctx->d_toon_scratch = nullptr;
-    ctx->toon_scratch_bytes = 0;
-    CF_CUDA(ctx, cudaMalloc(&ctx->d_toon_scratch, need + need / 4));
-    ctx->toon_scratch_bytes = need + need / 4;
-  }
-  if ((rc = dev_reserve(ctx, ctx->tmp[0], 5 * stream_bytes + 32ull * n_units + 64))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[1], (size_t)n_units * 4))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[3], ((size_t)n_units + 1) * 8))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[5], nnodes * 4))) return rc;
-  uint8_t* d_arena = (uint8_t*)ctx->tmp[0].p;
-  uint32_t* d_len = (uint32_t*)ctx->tmp[1].p;
-  int32_t* d_st = (int32_t*)ctx->tmp[2].p;
-  uint64_t* d_ooff = (uint64_t*)ctx->tmp[3].p;
-  uint32_t* d_idx = (uint32_t*)ctx->tmp[5].p;
-  std::vector<uint32_t> lens(n_units);
-  const uint32_t upw = units_per_warp(ctx, n_units);
-  mask_kernel<<<json_blocks(n_units, upw), 64>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, (cfj::JNode*)ctx->d_toon_scratch, d_idx, d_arena, d_len,
-                                                 d_st, max_depth, upw);
-  ctx->launches++;
-  CF_CUDA(ctx, cudaGetLastError());
-  CF_CUDA(ctx, cudaMemcpy(lens.data(), d_len, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-  CF_CUDA(ctx, cudaMemcpy(status, d_st, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
-  uint64_t total = 0;
-  for (uint32_t i = 0; i < n_units; ++i) { out_offsets[i] = total; total += lens[i]; }
-  out_offsets[n_units] = total;
-  if (out_needed) *out_needed = total;
-  if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; return CF_E_CAPACITY; }
-  if (total) {
-    if ((rc = dev_reserve(ctx, ctx->tmp[4], total))) return rc;
-    if ((rc = stage_reserve(ctx, total))) return rc;
-    CF_CUDA(ctx, cudaMemcpy(d_ooff, out_offsets, ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
-    compact_kernel<<<n_units, 128>>>(d_arena, 5, 32, b->d_offsets, d_len, d_ooff, (uint8_t*)ctx->tmp[4].p, n_units);
-    ctx->launches++;
-    CF_CUDA(ctx, cudaGetLastError());
-    CF_CUDA(ctx, cudaMemcpy(ctx->h_stage, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
-    memcpy(out_bytes, ctx->h_stage, total);
-  }
-  return CF_OK;
-}
-
-int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
-                          uint8_t* sensitive) {
-  if (!ctx || !b || !sensitive) return CF_E_BADARG;
-  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
-  if (rc) return rc;
-  if ((rc = dev_reserve(ctx, ctx->tmp[6], n_units))) return rc;
-  uint8_t* d = (uint8_t*)ctx->tmp[6].p;
-  classify_keys_kernel<<<(n_units + 127) / 128, 128>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, n_units, d);
-  ctx->launches++;
-  CF_CUDA(ctx, cudaGetLastError());
-  CF_CUDA(ctx, cudaMemcpy(sensitive, d, n_units, cudaMemcpyDeviceToHost));
-  return CF_OK;
 }
 
 int cf_profile_begin(cf_ctx* ctx, uint32_t max_launches) {

@@ -192,3 +192,27 @@ extern "C" int cfh_mask_indexed(const uint8_t* text, uint32_t n, int max_depth, 
   const int pr = indexed_parse(text, n, nodes, &cnt);
   return cfm::mask_finish(pr, text, nodes.data(), idx.data(), (uint32_t)idx.size(), out, out_cap, out_len, max_depth, w);
 }
+
+// ---- token-parallel TOON (json_tp.h): the warp-per-unit kernel body, run on the 32-fibre warp emulator ----
+#include "../../mcp_context_forge_b200/csrc/json_tp.h"
+#include "warp_emu.h"
+// order: 0 ascending / 1 descending lane schedule.  Returns the TS_* status (7 = sequential fallback requested).
+extern "C" int cfh_toon_tp(const uint8_t* text, uint32_t n, uint8_t* out, uint32_t out_cap, uint32_t* out_len, int report_errors, int order,
+                           uint32_t* ntok_out) {
+  static uint16_t ctab[256];
+  if (!ctab[(int)'"']) for (uint32_t i = 0; i < 256; ++i) ctab[i] = (uint16_t)cftp::byte_class(i);
+  std::vector<cftp::GTok> toks(n / 2 + 64);
+  std::vector<cftp::Shared> sh(1);
+  int status[32];
+  uint32_t olen[32];
+  for (int i = 0; i < 32; ++i) { status[i] = -1; olen[i] = 0; }
+  wemu::run_warp([&](uint32_t lane) {
+    uint32_t ol = 0;
+    status[lane] = cftp::toon_unit(text, n, toks.data(), (uint32_t)toks.size(), out, out_cap, &ol, sh[0], ctab, report_errors != 0);
+    olen[lane] = ol;
+  }, order);
+  for (int i = 1; i < 32; ++i) if (status[i] != status[0] || olen[i] != olen[0]) return -100 - i;   // the status must be warp-uniform
+  *out_len = olen[0];
+  if (ntok_out) *ntok_out = (uint32_t)status[0] >> 8;   // fallback reason (diagnostics)
+  return status[0] & 0xFF;
+}

@@ -11,14 +11,15 @@ SRCS = [
     os.path.join(ROOT, "tests", "hostsim", "host_sim.cpp"),
     os.path.join(ROOT, "mcp_context_forge_b200", "csrc", "cf_host.cpp"),
     os.path.join(ROOT, "mcp_context_forge_b200", "csrc", "re_backend.cpp"),
+    os.path.join(ROOT, "tests", "hostsim", "warp_emu.cpp"),
 ]
 
 
 def build(force=False):
-    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h", "json_toon.h", "json_mask.h", "unicode_tables.h")]
+    deps = SRCS + [os.path.join(ROOT, "mcp_context_forge_b200", "csrc", h) for h in ("scan_core.h", "re_backend.h", "cf_host.h", "json_toon.h", "json_mask.h", "json_index.h", "json_tp.h", "warp_prims.h", "unicode_tables.h")] + [os.path.join(ROOT, "tests", "hostsim", "warp_emu.h")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", SO] + SRCS)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-DCF_WARP_EMU", "-o", SO] + SRCS)
     return SO
 
 
@@ -124,6 +125,19 @@ def toon_host(text: str, unlimited: bool = False, indexed: bool = False):
     n = ctypes.c_uint32()
     fn = lib().cfh_toon_indexed if indexed else lib().cfh_toon
     st = fn(b, len(b), out, cap, ctypes.byref(n))
+    return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)
+
+
+def toon_tp(text, unlimited: bool = False, report_errors: bool = True, order: int = 0):
+    """(status, toon_text_or_None) from the TOKEN-PARALLEL warp kernel body (json_tp.h) run on the 32-fibre warp
+    emulator.  status 7 = the unit is handed to the sequential encoder."""
+    b = text if isinstance(text, bytes) else text.encode("utf-8", "surrogatepass")
+    cap = len(b) * 6 + 4096 if unlimited else max(len(b) - 1, 0)
+    out = ctypes.create_string_buffer(max(cap, 1))
+    n = ctypes.c_uint32()
+    why = ctypes.c_uint32()
+    st = lib().cfh_toon_tp(b, len(b), out, cap, ctypes.byref(n), 1 if report_errors else 0, order, ctypes.byref(why))
+    toon_tp.last_reason = why.value
     return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)
 
 

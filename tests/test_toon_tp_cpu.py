@@ -1,0 +1,126 @@
+"""The token-parallel TOON kernel body (csrc/json_tp.h) on the CPU: the very source toon_tp_kernel compiles, executed
+lane for lane by the TEST-ONLY 32-fibre warp emulator (tests/hostsim/warp_emu.cpp), against
+  * the vectors recorded from the reference's own toon.py / toon_encoder.py (tests/golden/toon.json),
+  * the sequential encoder (csrc/json_toon.h, pinned to the same vectors) on a seeded differential fuzz,
+  * the oracle on the synthetic bench payloads.
+Status 7 means "handed to the sequential encoder" (a GPU path too): allowed, never wrong."""
+import json
+import os
+import random
+import sys
+
+import pytest
+
+import hostsim_util as hs
+from mcp_context_forge_b200 import synth
+from oracle import toon_ref
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import fuzz_toon_tp  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "toon.json")
+ST = {"converted": 0, "not_smaller": 1, "not_json": 2, "value_error": 3, "attr_error": 4, "fallback": 7}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD, encoding="utf-8") as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_reference_golden_encode_cases(gold, order):
+    n_ok = n_err = n_fb = 0
+    for c in gold["encode"]:
+        st, got = hs.toon_tp(c["json"], unlimited=True, order=order)
+        if st == ST["fallback"]:
+            n_fb += 1
+            continue
+        if "toon" in c:
+            assert st == 0 and got == c["toon"], (c["json"][:300], st, got, c["toon"])
+            n_ok += 1
+        else:
+            assert st == (ST["attr_error"] if c["error"] == "AttributeError" else ST["value_error"]), (c["json"][:200], st, c["error"])
+            n_err += 1
+    assert n_ok > 350 and n_err > 5, (n_ok, n_err, n_fb)
+
+
+def test_plugin_decisions_golden(gold):
+    n = conv = 0
+    for block in gold["plugin"]:
+        cfg = block["config"] or {}
+        if cfg.get("exclude_tools") or cfg.get("include_tools") or cfg.get("skip_on_error") is False:
+            continue
+        lo, hi = cfg.get("min_size_bytes", 100), cfg.get("max_size_bytes", 1 << 20)
+        for c in block["cases"]:
+            item = c["result"]["content"][0]
+            text = item["text"]
+            size = len(text.encode("utf-8"))
+            if size < lo or size > hi:
+                continue
+            new = (c["modified"] or c["result"])["content"][0]
+            st, got = hs.toon_tp(text, report_errors=False, order=n & 1)
+            if st == ST["fallback"]:
+                continue
+            if new == item:
+                assert st != 0, text[:200]
+            else:
+                assert st == 0 and got == new["text"], text[:200]
+                conv += 1
+            n += 1
+    assert n > 80 and conv > 15, (n, conv)
+
+
+def test_differential_fuzz_vs_sequential_encoder():
+    rng = random.Random(20260921)
+    case = fuzz_toon_tp.make_gen(rng)
+    bad = []
+    nfb = 0
+    for it in range(6000):
+        t = case()
+        r = fuzz_toon_tp.check(t, rng.random() < 0.5, rng.random() < 0.5, it & 1)
+        if r == "fallback":
+            nfb += 1
+        elif r:
+            bad.append((t[:300], r))
+    assert not bad, bad[:3]
+    assert nfb < 2000
+
+
+@pytest.mark.parametrize("shape,size", [("A", 600), ("A", 16384), ("B", 16384), ("A", 262144), ("C", 4096)])
+def test_synthetic_payloads_vs_oracle(shape, size):
+    for seed in range(4):
+        text = synth.payload(shape, size, seed=seed)
+        if shape == "C":
+            text = json.dumps({"doc": text, "n": seed})
+        exp = toon_ref.process_text(text, 0, 1 << 30)
+        st, got = hs.toon_tp(text, report_errors=False, order=seed & 1)
+        if st == ST["fallback"]:
+            continue
+        assert (got if st == 0 else None) == exp
+        if shape == "A":
+            assert st == 0          # the tabular shape must stay on the fast path
+
+
+def test_strict_json_rejections():
+    bad = ['{"a":1,}', "[1,]", "{'a':1}", "[01]", "[1.]", "[.5]", "[+1]", "NaN", "[Infinity]", '"\\x"', '"\\ud800"', '"\\udc00\\ud800"', '"a\tb"', "[1] x", "", "  ",
+           '{"a" 1}', "[1 2]", '"\\u12g4"', "tru", "nul", '{"a":}', "[", "{", '"abc', "{:1}", '{"a"::1}', '{"a":1 "b":2}', '{"a":"b":1}', "[,1]", "[1,,2]", '{"a":1}}',
+           "[]]", "1 2", '{"a":1,:2}', '["a":1]', "{1:2}", '[1}', '{"a":1]', "-", "1e", "--1", "[1" + "," * 300 + "2]", '"\x7f\xff"']
+    for t in bad:
+        for order in (0, 1):
+            st, _ = hs.toon_tp(t.encode("latin1") if "\xff" in t else t, unlimited=True, order=order)
+            assert st in (ST["not_json"],), (t, st)
+    deep = "[" * 70 + "]" * 70
+    assert hs.toon_tp(deep, unlimited=True)[0] == 6
+    ok64 = "[" * 64 + "]" * 64
+    assert hs.toon_tp(ok64, unlimited=True) == hs.toon_host(ok64, unlimited=True)
+
+
+def test_long_strings_and_chunk_boundaries():
+    """Strings, scalars and separators that straddle the 32-byte front-end chunks and the 32-token batches."""
+    rng = random.Random(5)
+    for pad in range(0, 70):
+        doc = json.dumps({"p" * (pad % 7 + 1): "x" * pad, "rows": [{"id": i, "v": "y" * (pad + i), "f": i * 1.5, "t": i % 2 == 0} for i in range(40)],
+                          "long": " ".join("w%d" % rng.randint(0, 999) for _ in range(60 + pad)), "esc": "a\\nb" * (pad % 5), "n": -pad}, separators=(",", ":"))
+        for order in (0, 1):
+            assert hs.toon_tp(doc, unlimited=True, order=order) == hs.toon_host(doc, unlimited=True), pad
