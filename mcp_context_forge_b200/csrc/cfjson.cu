@@ -102,9 +102,6 @@ __global__ void __launch_bounds__(TP_WARPS * 32) toon_tp_kernel(const uint8_t* _
                                                                  cftp::GTok* __restrict__ toks, uint8_t* __restrict__ out, uint32_t* __restrict__ out_len,
                                                                  int32_t* __restrict__ status, uint32_t flags) {
   __shared__ cftp::Shared sh[TP_WARPS];
-  __shared__ uint16_t ctab[256];
-  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) ctab[i] = (uint16_t)cftp::byte_class(i);
-  __syncthreads();
   const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const uint32_t u = blockIdx.x * TP_WARPS + wic;
   if (u >= n_units) return;
@@ -114,7 +111,7 @@ __global__ void __launch_bounds__(TP_WARPS * 32) toon_tp_kernel(const uint8_t* _
   const uint32_t len = (uint32_t)len64;
   cftp::GTok* my = toks + (b >> 1) + (uint64_t)TP_TOK_SLACK * u;
   uint32_t ol = 0;
-  const int st = cftp::toon_unit(stream + b, len, my, len / 2 + TP_TOK_SLACK, out + b, len ? len - 1 : 0, &ol, sh[wic], ctab, (flags & 1u) != 0);
+  const int st = cftp::toon_unit(stream + b, len, my, len / 2 + TP_TOK_SLACK, out + b, len ? len - 1 : 0, &ol, sh[wic], (flags & 1u) != 0);
   if (lane == 0) {
     status[u] = st & 0xFF;
     out_len[u] = (st & 0xFF) == cfj::TS_CONVERTED ? ol : (uint32_t)st >> 8;

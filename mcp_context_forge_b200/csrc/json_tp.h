@@ -4,19 +4,21 @@
 //   orjson.loads + toon.encode + "keep only if strictly smaller"   plugins/toon_encoder/toon_encoder.py:277-303
 //   encoder rules                                                    plugins/toon_encoder/toon.py:82-565
 //
-// Shape of the computation:
-//   pass 1  front end   32 bytes per step, lane i <-> byte i: byte classes by ballot, escape parity, in-string mask by
-//                       prefix XOR -> SIGNIFICANT tokens (brackets, strings at their closing quote, scalar starts); commas
-//                       and colons are not tokens, each token carries how many of them precede it.  Tokens go through a
-//                       ring in shared memory.
-//           batch       32 tokens at a time, lane i <-> token i: scalars / strings validated and classified in parallel
-//                       (orjson's accept set), then ONE warp-uniform walk over the batch's brackets maintains the container
-//                       stack (grammar, child counts, duplicate-key screen, columnar-table detection against the first row)
-//                       and patches every opener's token with {child count, layout mode} when its closer arrives.
-//                       Tokens are stored to HBM scratch (8 bytes each).
-//   pass 2  emit        32 tokens at a time: the same bracket walk now carries the TOON frames (layout mode, prefix width,
-//                       indent level); every token's output piece length is known locally, a warp prefix sum gives its
-//                       offset, pieces are written in parallel (long spans by the whole warp).
+// Shape of the computation.  Everything is written so that each LANE runs sequential code over
+// data it owns (its 32 bytes, its token, its table row): the first version put lane i on byte i of one 32-byte chunk
+// and paid ~16 warp-instructions per input byte (profiles/r02_toon_tp_v1_lines.txt).
+//   tokenize   1 KiB per step, lane l owns bytes [32 l, 32 l + 32) as eight 32-bit words: SWAR byte-class flags ->
+//              per-lane 32-bit masks (quote, backslash, brackets, comma, colon, blank, ...), escape parity and the
+//              in-string state carried across lanes by ballots / warp scans -> SIGNIFICANT tokens (brackets, strings at
+//              their closing quote, scalar starts; commas and colons are only counted in front of the next token).
+//              32 tokens at a time, lane i <-> token i: scalars / strings validated and classified (orjson's accept
+//              set), 8-byte tokens stored to HBM scratch.
+//   analyze    over the token array.  Generic mode: 32 tokens, ONE warp-uniform walk over the batch's brackets keeps the
+//              container stack (grammar, child counts, duplicate-key screen, table detection against the first row) and
+//              patches each opener with {child count, layout mode}.  Table mode: once the first row of an array of
+//              objects is known, every later row is checked by its own lane against the first row's token pattern.
+//   emit       over the token array.  Generic mode: the bracket walk carries the TOON frames (layout mode, prefix width,
+//              indent level), piece lengths -> warp prefix sum -> parallel writes.  Table mode: one lane per table row.
 // Whatever the fast path does not cover (duplicate keys, escaped keys, permuted table rows, numbers that need the exact
 // big-integer formatter, ...) is reported as TS_FALLBACK and re-done by the sequential per-thread encoder (json_toon.h) —
 // still on the GPU, never on the CPU.
@@ -36,31 +38,35 @@ using cfj::TS_NOT_SMALLER;
 using cfj::TS_UNSUPPORTED;
 using cfj::TS_VALUE_ERROR;
 enum : int { TS_FALLBACK = 7 };      // internal: bits 8.. carry the reason (FB_*), stripped at the ABI
-enum : uint32_t { FB_NUM_EXACT = 1, FB_KEY_ESCAPE = 2, FB_TOK_CAP = 3, FB_KH_CAP = 4, FB_DUP_HASH = 5, FB_ROW_ORDER = 6, FB_MIXED_ITEM = 7 };
+enum : uint32_t { FB_NUM_EXACT = 1, FB_KEY_ESCAPE = 2, FB_TOK_CAP = 3, FB_KH_CAP = 4, FB_DUP_HASH = 5, FB_ROW_ORDER = 6, FB_MIXED_ITEM = 7, FB_TOO_LONG = 8 };
 
 // ---- tokens --------------------------------------------------------------------------------------------------------
 enum : uint32_t { K_OPEN_OBJ = 0, K_OPEN_ARR = 1, K_CLOSE_OBJ = 2, K_CLOSE_ARR = 3, K_STR = 4, K_KEY = 5, K_NUM = 6, K_LIT = 7 };
-struct GTok { uint32_t pos, w; };                 // w = kind | flags << 3 | len << 8
-static const uint32_t GT_MAXLEN = (1u << 24) - 1;
+struct GTok { uint32_t pos, w; };                 // w = kind:3 | flags:5 | commas:2 | colons:2 | len:20
+static const uint32_t GT_MAXLEN = (1u << 20) - 1;
 // flags (5 bits)
 enum : uint32_t { SF_Q = 1, SF_ESCX = 2, SF_CTRLERR = 4 };        // K_STR: needs quotes / needs transcoding / holds a char TOON cannot quote
 enum : uint32_t { KF_KEYOK = 1 };                                 // K_KEY: valid unquoted key
-enum : uint32_t { AM_EMPTY = 0, AM_COLUMNAR = 1, AM_INLINE = 2, AM_ITEMS = 3, AF_MIXED = 4 };   // K_OPEN_ARR (patched at its closer)
+enum : uint32_t { AM_EMPTY = 0, AM_COLUMNAR = 1, AM_INLINE = 2, AM_ITEMS = 3, AF_MIXED = 4 /* first element an object, some later one not, verdict unknown */,
+                  AF_CRASH = 8 /* toon._try_columnar_encoding(arr) raises AttributeError */ };   // K_OPEN_ARR (patched at its closer)
 TP_FN uint32_t gt_kind(uint32_t w) { return w & 7u; }
 TP_FN uint32_t gt_flags(uint32_t w) { return (w >> 3) & 31u; }
-TP_FN uint32_t gt_len(uint32_t w) { return w >> 8; }
-TP_FN uint32_t gt_make(uint32_t kind, uint32_t fl, uint32_t len) { return kind | (fl << 3) | (len << 8); }
+TP_FN uint32_t gt_nc(uint32_t w) { return (w >> 8) & 3u; }        // commas in front of the token (saturating at 3)
+TP_FN uint32_t gt_nk(uint32_t w) { return (w >> 10) & 3u; }       // colons in front of the token
+TP_FN uint32_t gt_len(uint32_t w) { return w >> 12; }
+TP_FN uint32_t gt_make(uint32_t kind, uint32_t fl, uint32_t nc, uint32_t nk, uint32_t len) { return kind | (fl << 3) | (nc << 8) | (nk << 10) | (len << 12); }
+TP_FN uint32_t gt_patch(uint32_t w, uint32_t kind, uint32_t fl, uint32_t len) { return (w & 0xF00u) | kind | (fl << 3) | (len << 12); }
 
-// ring record meta (front end -> batch)
+// ring record meta (tokenizer -> classification batch)
 enum : uint32_t { RM_KIND = 7u, RM_NCOMMA_SH = 3, RM_NCOLON_SH = 5, RM_SPECIAL = 1u << 7, RM_NONKEY = 1u << 8, RM_HI = 1u << 9, RM_BS = 1u << 10,
-                  RM_OPENEND = 1u << 11 /* scalar run reaches the end of its 32-byte chunk: length still unknown */ };
+                  RM_OPENEND = 1u << 11 /* scalar run reaches the end of its lane's 32 bytes: length still unknown */ };
 
 // ---- per-warp shared memory ----------------------------------------------------------------------------------------
 static const uint32_t RING = 128, MAXD = 64, KH_CAP = 256;
 static const uint32_t UNSET = 0xFFFFFFFFu;
 struct Shared {
   uint32_t ring_pos[RING], ring_len[RING], ring_meta[RING];
-  // pass 1: container stack            | pass 2: frame stack (same storage)
+  // analyze: container stack            | emit: frame stack (same storage)
   uint32_t open_idx[MAXD];             // token index of the opener      | frame mode
   uint32_t cnt[MAXD];                  // children (values) so far       | children so far
   uint32_t cfl[MAXD];                  // C_* flags                      | prefix width
@@ -69,28 +75,81 @@ struct Shared {
   uint32_t row0_n[MAXD];               // arrays: member count of that first object once it closed
   uint32_t kh[KH_CAP];                 // key hashes of the open objects (stack)
 };
-enum : uint32_t { C_OBJ = 1, C_ALL_SIMPLE = 2, C_ALL_OBJ = 4, C_COL_OK = 8, C_ALIGNED = 16, C_VALS_SIMPLE = 32 };
+enum : uint32_t {
+  C_OBJ = 1,
+  // arrays
+  C_ALL_SIMPLE = 2,      // no element is a container
+  C_ALL_OBJ = 4,         // every element is an object
+  C_KEYSET_OK = 8,       // every object element so far has the first one's key set (toon.py:487-490)
+  C_ROWS_SIMPLE = 64,    // every member value of every object element so far is a primitive (toon.py:493-495)
+  C_ND_SEEN = 128,       // a non-object element followed an object first element (the unchecked .keys() of toon.py:488)
+  C_CRASH = 256,         // ... and arrived before any key-set mismatch: _try_columnar_encoding raises AttributeError
+  C_PERMUTED = 512,      // some row lists the first row's keys in another order (columnar output needs a gather)
+  C_ROW0_SIMPLE = 1024,  // the first row's values are primitives: its j-th key is token row0 + 1 + 2j
+  // objects
+  C_ALIGNED = 16,        // keys equal the first row's, position by position
+  C_VALS_SIMPLE = 32,    // all member values are primitives
+  C_DIFFSET = 4096       // some key does not occur in the first row at all
+};
 
-// byte classes of the front end
-enum : uint32_t { BC_BS = 1, BC_QUOTE = 2, BC_STRUCT = 4, BC_COMMA = 8, BC_COLON = 16, BC_WS = 32, BC_CTRL = 64, BC_SPECIAL = 128, BC_NONKEY = 256, BC_HI = 512 };
+// byte classes (scalar-run scan of the rare paths; the tokenizer itself uses SWAR flag words)
+enum : uint32_t { BC_QUOTE = 2, BC_STRUCT = 4, BC_WS = 32 };
 TP_FN uint32_t byte_class(uint32_t b) {
   uint32_t k = 0;
-  if (b == '\\') k |= BC_BS;
   if (b == '"') k |= BC_QUOTE;
   if (b == '{' || b == '}' || b == '[' || b == ']' || b == ':' || b == ',') k |= BC_STRUCT;
-  if (b == ',') k |= BC_COMMA;
-  if (b == ':') k |= BC_COLON;
   if (b == ' ' || b == '\t' || b == '\n' || b == '\r') k |= BC_WS;
-  if (b < 0x20) k |= BC_CTRL;
-  if (b == ',' || b == ':' || b == '[' || b == ']' || b == '{' || b == '}' || b == '-') k |= BC_SPECIAL;
-  if (!((b >= 'A' && b <= 'Z') || (b >= 'a' && b <= 'z') || (b >= '0' && b <= '9') || b == '_' || b == '.')) k |= BC_NONKEY;
-  if (b >= 0x80) k |= BC_HI;
   return k;
 }
 
 TP_FN uint32_t bits_below(uint32_t i) { return i >= 32 ? 0xFFFFFFFFu : ((1u << i) - 1u); }   // bits 0..i-1
 TP_FN uint32_t range_mask(uint32_t lo, uint32_t hi) { return bits_below(hi) & ~bits_below(lo); }   // bits lo..hi-1
 TP_FN uint32_t sat3(uint32_t v) { return v > 3u ? 3u : v; }
+
+// ---- SWAR over 4 bytes of a 32-bit word: the result has 0x80 in every byte that satisfies the predicate ----
+TP_FN uint32_t swar_eq(uint32_t w, uint32_t c) { const uint32_t x = w ^ (c * 0x01010101u); return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+// lo <= byte <= hi for bytes below 0x80 (x7 = w & 0x7F7F7F7F; bytes >= 0x80 must be masked out by the caller)
+TP_FN uint32_t swar_range7(uint32_t x7, uint32_t lo, uint32_t hi) { return (x7 + (0x80u - lo) * 0x01010101u) & ~(x7 + (0x7Fu - hi) * 0x01010101u) & 0x80808080u; }
+TP_FN uint32_t gather4(uint32_t f) { return (((f >> 7) * 0x00204081u) >> 21) & 15u; }   // flags at bits 7,15,23,31 -> nibble
+
+struct LaneMasks { uint32_t q, bs, ob, cb, curly, cm, co, ws, ctrl, hi, special, nonkey; };   // bit j <-> byte j of the lane's 32 bytes
+TP_FN void build_masks(const uint32_t* w, LaneMasks& M) {
+  M.q = M.bs = M.ob = M.cb = M.curly = M.cm = M.co = M.ws = M.ctrl = M.hi = M.special = M.nonkey = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; ++k) {
+    const uint32_t x = w[k], sh = 4 * k;
+    const uint32_t hi = x & 0x80808080u, x7 = x & 0x7F7F7F7Fu;
+    const uint32_t q = swar_eq(x, '"'), bs = swar_eq(x, '\\'), cm = swar_eq(x, ','), co = swar_eq(x, ':'), sp = swar_eq(x, ' ');
+    const uint32_t x20 = x | 0x20202020u;
+    const uint32_t ob = swar_eq(x20, '{'), cb = swar_eq(x20, '}');                    // '[' | 0x20 == '{', ']' | 0x20 == '}'
+    const uint32_t br = ob | cb;
+    const uint32_t curly = br & (x << 2);                                             // bit 5 of the byte: '{' '}' have it, '[' ']' do not
+    const uint32_t ctrl = ~((x7 + 0x60606060u) | x) & 0x80808080u;                    // byte < 0x20
+    uint32_t ws = sp;
+    if (ctrl) ws |= ctrl & (swar_eq(x, '\t') | swar_eq(x, '\n') | swar_eq(x, '\r'));
+    const uint32_t st = br | cm | co;
+    const uint32_t special = st | swar_eq(x, '-');
+    // [A-Za-z0-9_.]: folding to lower case maps '@' to '`' (below 'a') and '[' '\\' ']' '^' '_' to '{' '|' '}' '~' 0x7F (above 'z')
+    const uint32_t x7l = x20 & 0x7F7F7F7Fu;
+    const uint32_t keych = (swar_range7(x7l, 'a', 'z') | swar_range7(x7, '0', '9') | swar_eq(x, '_') | swar_eq(x, '.')) & ~hi;
+    M.q |= gather4(q) << sh; M.bs |= gather4(bs) << sh; M.ob |= gather4(ob) << sh; M.cb |= gather4(cb) << sh; M.curly |= gather4(curly) << sh;
+    M.cm |= gather4(cm) << sh; M.co |= gather4(co) << sh; M.ws |= gather4(ws) << sh; M.ctrl |= gather4(ctrl) << sh; M.hi |= gather4(hi) << sh;
+    M.special |= gather4(special) << sh; M.nonkey |= gather4(keych ^ 0x80808080u) << sh;
+  }
+}
+
+// Which bytes are escaped (preceded by an odd-length run of backslashes)?  simdjson's carry trick on the lane's 32-bit
+// backslash mask; e_in = the lane's first byte is escaped; *e_out = the first byte after the lane is.
+TP_FN uint32_t find_escaped(uint32_t bs, uint32_t e_in, uint32_t* e_out) {
+  bs &= ~e_in;
+  const uint32_t follows = (bs << 1) | e_in;
+  const uint32_t EVEN = 0x55555555u;
+  const uint32_t odd_starts = bs & ~EVEN & ~follows;
+  const uint32_t sum = odd_starts + bs;
+  *e_out = sum < bs ? 1u : 0u;                      // carry out of bit 31
+  const uint32_t invert = sum << 1;
+  return (EVEN ^ invert) & follows;
+}
 
 // ---- scalars ---------------------------------------------------------------------------------------------------------
 // Number literal t[0..len) (already grammar-checked, flags from cfj::scan_number): the text toon._encode_float / str(int)
@@ -166,7 +225,10 @@ struct Emit {
   uint8_t* out;
   uint32_t cap, o;
   TP_FN void put(uint32_t c) { if (o < cap) out[o] = (uint8_t)c; ++o; }
-  TP_FN void span(const uint8_t* b, uint32_t len) { for (uint32_t i = 0; i < len; ++i) put(b[i]); }
+  TP_FN void span(const uint8_t* b, uint32_t len) {
+    if (o + len <= cap) { uint8_t* d = out + o; for (uint32_t i = 0; i < len; ++i) d[i] = b[i]; o += len; }
+    else for (uint32_t i = 0; i < len; ++i) put(b[i]);
+  }
   TP_FN void spaces(uint32_t k) { for (uint32_t i = 0; i < k; ++i) put(' '); }
   TP_FN void uint_dec(uint32_t v) {
     uint8_t b[10]; int k = 0;
@@ -196,20 +258,33 @@ struct Emit {
 };
 TP_FN uint32_t dec_digits(uint32_t v) { uint32_t d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
 
-// frame modes of pass 2
+// frame modes of emit
 enum : uint32_t { M_ROOT = 0, M_OBJ = 1, M_LIST_ITEM = 2, M_ROW = 3, M_ARR_ITEMS = 4, M_ARR_INLINE = 5, M_ARR_COL = 6, M_DEAD = 7 /* empty container */ };
 
-struct P1State {
-  uint32_t sp, root_cnt, ntok, last_was_key;
-  int status;          // 0 while everything is fine
-};
+// A non-object element arrives in an array whose first element is an object (row0 = 1 + its token index, row0_n its member
+// count).  toon._try_columnar_encoding would call .keys() on it unless an earlier row already returned None.
+TP_FN uint32_t nondict_element(uint32_t afl, uint32_t row0, uint32_t row0_n) {
+  afl &= ~C_ALL_OBJ;
+  if (row0 && !(afl & C_ND_SEEN)) {
+    afl |= C_ND_SEEN;
+    if ((afl & C_KEYSET_OK) && (afl & C_ROW0_SIMPLE) && row0_n != 0 && row0_n != UNSET) afl |= C_CRASH;
+  }
+  return afl;
+}
+TP_FN bool key_equals(const uint8_t* s, const GTok r, const uint8_t* b, uint32_t len) {
+  if (gt_kind(r.w) != K_KEY || gt_len(r.w) != len) return false;
+  const uint8_t* a = s + r.pos;
+  for (uint32_t i = 0; i < len; ++i) if (a[i] != b[i]) return false;
+  return true;
+}
 
 // ----------------------------------------------------------------------------------------------------------------------
-// pass 1, one batch: tokens ring[head .. head+m), la_ncolon = colons in front of the token that follows the batch
+// tokenize, classification batch: raw tokens ring[head .. head+m) -> validated GTok toks[ntok ..); la_ncolon = colons in
+// front of the token that follows the batch (a string followed by a colon is a key)
 // ----------------------------------------------------------------------------------------------------------------------
-TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, P1State& st, uint32_t head, uint32_t m, uint32_t la_ncolon) {
+struct TokState { uint32_t ntok; int status; };
+TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, TokState& st, uint32_t head, uint32_t m, uint32_t la_ncolon) {
   const uint32_t l = tpw::lane();
-  const uint32_t ltm = tpw::lt_mask();
   const bool act = l < m;
   uint32_t pos = 0, len = 0, meta = 0;
   if (act) { const uint32_t r = (head + l) & (RING - 1); pos = sh.ring_pos[r]; len = sh.ring_len[r]; meta = sh.ring_meta[r]; }
@@ -218,13 +293,10 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
   uint32_t nxt_ncolon = tpw::shfl_down(ncolon, 1);
   if (l + 1 >= m) nxt_ncolon = la_ncolon;
   bool bad = false, unsup = false;
-  uint32_t fb = 0;                                   // fallback reason (FB_*), 0 = none
-  uint32_t fl = 0, hash = 0;
+  uint32_t fb = 0, fl = 0;
   const bool isK = act && kind == K_STR && ncolon == 0 && nxt_ncolon >= 1;
-
-  // ---- phase 0: every token on its own lane
   if (act && kind == K_NUM) {                       // scalar run starting at pos
-    if (meta & RM_OPENEND) {                        // the run left its chunk: find its end
+    if (meta & RM_OPENEND) {                        // the run left its lane: find its end
       uint32_t e = pos + len;
       while (e < n) { const uint32_t k = byte_class(s[e]); if (k & (BC_STRUCT | BC_WS | BC_QUOTE)) break; ++e; }
       len = e - pos;
@@ -244,19 +316,16 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
     } else bad = true;
   } else if (act && kind == K_STR) {
     const uint8_t* b = s + pos;
-    if (len > GT_MAXLEN) unsup = true;
+    if (len > GT_MAXLEN) fb = FB_TOO_LONG;
     else if ((meta & (RM_BS | RM_HI)) || (len && b[0] >= '0' && b[0] <= '9')) {
       // escapes, non-ASCII or number-like candidates: the sequential validator decides (same function as json_toon.h)
       uint32_t p = pos - 1, sf = 0, h = 0;
       if (!cfj::parse_string(s, n, &p, &sf, &h) || p != pos + len + 1) bad = true;
+      else if (isK) { if (sf & cfj::JF_ESC) fb = FB_KEY_ESCAPE; if (sf & cfj::JF_KEYOK) fl |= KF_KEYOK; }
       else {
-        hash = h;
-        if (isK) { if (sf & cfj::JF_ESC) fb = FB_KEY_ESCAPE; if (sf & cfj::JF_KEYOK) fl |= KF_KEYOK; }
-        else {
-          if (sf & cfj::JF_Q) fl |= SF_Q;
-          if (sf & cfj::JF_CTRLERR) fl |= SF_CTRLERR;
-          if ((sf & cfj::JF_ESC) && has_complex_escape(b, len)) fl |= SF_ESCX;
-        }
+        if (sf & cfj::JF_Q) fl |= SF_Q;
+        if (sf & cfj::JF_CTRLERR) fl |= SF_CTRLERR;
+        if ((sf & cfj::JF_ESC) && has_complex_escape(b, len)) fl |= SF_ESCX;
       }
     } else {
       const bool res = is_reserved(b, len);
@@ -264,19 +333,227 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
         const uint32_t f0 = len ? b[0] : 0u;
         const bool al = (f0 >= 'A' && f0 <= 'Z') || (f0 >= 'a' && f0 <= 'z') || f0 == '_';
         if (len && al && !(meta & RM_NONKEY) && !res) fl |= KF_KEYOK;
-        hash = fnv1a(b, len);
       } else if (len == 0 || res || (meta & RM_SPECIAL) || b[0] == ' ' || b[len - 1] == ' ') fl |= SF_Q;
     }
     if (isK) kind = K_KEY;
   }
-  if (len > GT_MAXLEN) unsup = true;
-  // store the tokens (openers are patched when their closer arrives)
-  const uint32_t idx = st.ntok + l;
+  if (len > GT_MAXLEN) { if (kind == K_NUM || kind == K_LIT) unsup = true; else if (!fb) fb = FB_TOO_LONG; len = 0; }
   if (st.ntok + m > tok_cap) fb = FB_TOK_CAP;
-  else if (act) { GTok t; t.pos = pos; t.w = gt_make(kind, fl, kind <= K_CLOSE_ARR ? 0u : len); toks[idx] = t; }
-  tpw::sync();
+  else if (act) { GTok t; t.pos = pos; t.w = gt_make(kind, fl, ncomma, ncolon, kind <= K_CLOSE_ARR ? 0u : len); toks[st.ntok + l] = t; }
+  st.ntok += m;
+  const bool any_bad = tpw::any(bad), any_unsup = tpw::any(unsup);
+  const uint32_t fbm = tpw::ballot(fb != 0);
+  if (any_bad) st.status = TS_NOT_JSON;
+  else if (any_unsup) st.status = TS_UNSUPPORTED;
+  else if (fbm) st.status = TS_FALLBACK | (int)(tpw::shfl(fb, tpw::ffs(fbm) - 1) << 8);
+}
 
-  // ---- phase 1: one walk over the brackets of the batch
+// ----------------------------------------------------------------------------------------------------------------------
+// tokenize: s[0..n) -> toks[0..*ntok_out).  Returns 0 or a TS_* status (warp-uniform).
+// The unit is walked in 1 KiB steps on a 16-byte-aligned grid (the bytes in front of s and behind s+n that fall into the
+// first / last step count as blanks; the caller guarantees 15 readable bytes in front and 1 KiB behind).
+// ----------------------------------------------------------------------------------------------------------------------
+TP_FN int tokenize(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, uint32_t* ntok_out) {
+  const uint32_t l = tpw::lane();
+  const uint32_t ltm = tpw::lt_mask();
+  TokState st; st.ntok = 0; st.status = 0;
+  const uint32_t lead = (uint32_t)((uintptr_t)s & 15u);
+  const uint8_t* s0 = s - lead;                       // 16-byte aligned
+  const uint32_t vend = n + lead;
+  // carries between steps (warp-uniform)
+  uint32_t c_instr = 0, c_esc = 0, c_other = 0, c_sep = 0 /* commas | colons << 16 since the last token */;
+  uint32_t c_open = 0, c_cls = 0;                     // string open across steps: position of its opening quote, classes seen so far
+  uint32_t head = 0, rcount = 0;
+  for (uint32_t vb = 0; vb < vend; vb += 1024) {
+    const uint32_t v = vb + 32 * l;                   // virtual offset of this lane's first byte
+    uint32_t w[8];
+    uint32_t valid = 0xFFFFFFFFu;
+    if (v < vend) {
+      const uint4 a = *reinterpret_cast<const uint4*>(s0 + v), b = *reinterpret_cast<const uint4*>(s0 + v + 16);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+      if (v < lead) valid &= ~bits_below(lead - v);
+      if (v + 32 > vend) valid &= bits_below(vend - v);
+    } else {
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) w[k] = 0x20202020u;
+      valid = 0;
+    }
+    LaneMasks M;
+    build_masks(w, M);
+    if (valid != 0xFFFFFFFFu) {
+      M.q &= valid; M.bs &= valid; M.ob &= valid; M.cb &= valid; M.curly &= valid; M.cm &= valid; M.co &= valid; M.ctrl &= valid; M.hi &= valid;
+      M.special &= valid; M.nonkey &= valid; M.ws |= ~valid;
+    }
+    // ---- escapes: which quotes are real
+    uint32_t quotes = M.q;
+    if (tpw::any(M.bs != 0) || c_esc) {
+      uint32_t eo;
+      find_escaped(M.bs, 0, &eo);
+      uint32_t e_in = tpw::shfl_up(eo, 1);
+      if (l == 0) e_in = c_esc;
+      if (tpw::any(M.bs == 0xFFFFFFFFu)) {            // a whole lane of backslashes: its carry-out depends on its carry-in
+        uint32_t e = c_esc;
+        for (uint32_t k = 0; k < 32; ++k) {
+          const uint32_t bk = tpw::shfl(M.bs, k);
+          uint32_t ek;
+          find_escaped(bk, e, &ek);
+          if (l == k) e_in = e;
+          e = ek;
+        }
+      }
+      uint32_t eo2;
+      const uint32_t escaped = find_escaped(M.bs, e_in, &eo2);
+      quotes &= ~escaped;
+      c_esc = tpw::shfl(eo2, 31);
+    }
+    // ---- in-string state
+    const uint32_t par = tpw::ballot(tpw::popc(quotes) & 1u);
+    const uint32_t is_in = (c_instr ^ (tpw::popc(par & ltm) & 1u)) ? 0xFFFFFFFFu : 0u;   // this lane starts inside a string
+    c_instr ^= tpw::popc(par) & 1u;
+    uint32_t x = quotes;
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+    const uint32_t instr = x ^ is_in;                 // opening quote included, closing quote excluded
+    const uint32_t openq = quotes & instr, closeq = quotes & ~instr;
+    const uint32_t content = instr & ~openq;
+    const bool ctl_bad = (M.ctrl & content) != 0;      // raw control character inside a string
+    const uint32_t outside = ~instr & ~closeq;
+    const uint32_t st_all = M.ob | M.cb | M.cm | M.co;
+    const uint32_t comma_out = M.cm & outside, colon_out = M.co & outside;
+    const uint32_t other = outside & ~st_all & ~M.ws;
+    uint32_t prev_other = tpw::shfl_up(other >> 31, 1);
+    if (l == 0) prev_other = c_other;
+    c_other = tpw::shfl(other >> 31, 31);
+    const uint32_t starts = other & ~((other << 1) | prev_other);
+    const uint32_t brackets = (M.ob | M.cb) & outside;
+    const uint32_t T = brackets | closeq | starts;
+    if (tpw::any(ctl_bad)) { st.status = TS_NOT_JSON; break; }
+    const uint32_t m_special = M.special & content, m_nonkey = M.nonkey & content, m_hi = M.hi & content, m_bs = M.bs & content;
+    // ---- separators in front of each lane's first token: segmented scan over the lanes
+    uint32_t sep_in;
+    {
+      const uint32_t after = T ? ~bits_below(32 - tpw::clz(T)) : 0xFFFFFFFFu;
+      uint32_t r = T ? 1u : 0u, vv = tpw::popc(comma_out & after) | (tpw::popc(colon_out & after) << 16);
+#pragma unroll
+      for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t r2 = tpw::shfl_up(r, d), v2 = tpw::shfl_up(vv, d);
+        if (l >= d) { if (!r) vv += v2; r |= r2; }
+      }
+      uint32_t rin = tpw::shfl_up(r, 1), vin = tpw::shfl_up(vv, 1);
+      if (l == 0) { rin = 0; vin = 0; }
+      sep_in = vin + (rin ? 0u : c_sep);
+      const uint32_t r31 = tpw::shfl(r, 31), v31 = tpw::shfl(vv, 31);
+      c_sep = v31 + (r31 ? 0u : c_sep);
+      if ((c_sep & 0xFFFFu) > 3u) c_sep = (c_sep & 0xFFFF0000u) | 3u;
+      if ((c_sep >> 16) > 3u) c_sep = (c_sep & 0xFFFFu) | (3u << 16);
+    }
+    // ---- the string that is open at each lane's start: position of its opening quote + classes seen so far
+    uint32_t so_pos, so_cls;
+    {
+      uint32_t r = quotes ? 1u : 0u, pp = 0, cc;
+      if (quotes) {                                    // only meaningful when the lane ends inside a string it opened
+        const uint32_t ob = 31 - tpw::clz(quotes), after = ~bits_below(ob + 1);
+        pp = v + ob;
+        cc = ((m_special & after) ? 1u : 0u) | ((m_nonkey & after) ? 2u : 0u) | ((m_hi & after) ? 4u : 0u) | ((m_bs & after) ? 8u : 0u);
+      } else cc = (m_special ? 1u : 0u) | (m_nonkey ? 2u : 0u) | (m_hi ? 4u : 0u) | (m_bs ? 8u : 0u);
+#pragma unroll
+      for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t r2 = tpw::shfl_up(r, d), p2 = tpw::shfl_up(pp, d), c2 = tpw::shfl_up(cc, d);
+        if (l >= d && !r) { pp = p2; cc |= c2; r = r2; }
+      }
+      uint32_t rin = tpw::shfl_up(r, 1), pin = tpw::shfl_up(pp, 1), cin = tpw::shfl_up(cc, 1);
+      if (l == 0) { rin = 0; pin = 0; cin = 0; }
+      so_pos = rin ? pin : c_open;
+      so_cls = rin ? cin : (cin | c_cls);
+      const uint32_t r31 = tpw::shfl(r, 31), p31 = tpw::shfl(pp, 31), c31 = tpw::shfl(cc, 31);
+      if (!r31) c_cls |= c31; else { c_open = p31; c_cls = c31; }
+    }
+    // ---- tokens of this lane, in windows through the ring
+    const uint32_t cntT = tpw::popc(T);
+    const uint32_t incl = tpw::scan_incl(cntT);
+    const uint32_t lane_off = incl - cntT, total = tpw::shfl(incl, 31);
+    uint32_t Tm = T, k = 0, prevj = 32;               // prevj = bit of this lane's previous token (32 = none yet)
+    for (uint32_t done = 0; done < total && !st.status; done += 64) {
+      const uint32_t win = total - done > 64 ? 64u : total - done;
+      while (Tm && lane_off + k < done + win) {
+        const uint32_t j = tpw::ffs(Tm) - 1;
+        Tm &= Tm - 1;
+        const uint32_t below = bits_below(j);
+        uint32_t between, nc, nk;
+        if (prevj < 32) { between = below & ~bits_below(prevj + 1); nc = 0; nk = 0; }
+        else { between = below; nc = sep_in & 0xFFFFu; nk = sep_in >> 16; }
+        nc = sat3(nc + tpw::popc(comma_out & between));
+        nk = sat3(nk + tpw::popc(colon_out & between));
+        uint32_t meta = (nc << RM_NCOMMA_SH) | (nk << RM_NCOLON_SH), tpos = v + j - lead, tlen = 0;
+        if ((brackets >> j) & 1u) meta |= ((M.ob >> j) & 1u) ? (((M.curly >> j) & 1u) ? K_OPEN_OBJ : K_OPEN_ARR) : (((M.curly >> j) & 1u) ? K_CLOSE_OBJ : K_CLOSE_ARR);
+        else if ((closeq >> j) & 1u) {
+          const uint32_t qb = quotes & below;
+          uint32_t span, cls, op;
+          if (qb) { const uint32_t ob = 31 - tpw::clz(qb); op = v + ob; span = below & ~bits_below(ob + 1); cls = 0; }
+          else { op = so_pos; span = below; cls = so_cls; }
+          tpos = op + 1 - lead; tlen = (v + j) - op - 1;
+          meta |= K_STR;
+          if ((cls & 1u) | (m_special & span)) meta |= RM_SPECIAL;
+          if ((cls & 2u) | (m_nonkey & span)) meta |= RM_NONKEY;
+          if ((cls & 4u) | (m_hi & span)) meta |= RM_HI;
+          if ((cls & 8u) | (m_bs & span)) meta |= RM_BS;
+        } else {
+          meta |= K_NUM;
+          const uint32_t e = ~other & ~bits_below(j + 1);          // first byte after the run, within the lane
+          if (e) tlen = tpw::ffs(e) - 1 - j; else { tlen = 32 - j; meta |= RM_OPENEND; }
+        }
+        const uint32_t r = (head + rcount + (lane_off + k - done)) & (RING - 1);
+        sh.ring_pos[r] = tpos; sh.ring_len[r] = tlen; sh.ring_meta[r] = meta;
+        prevj = j;
+        ++k;
+      }
+      rcount += win;
+      tpw::sync();
+      while (rcount >= 33 && !st.status) {
+        const uint32_t la = (sh.ring_meta[(head + 32) & (RING - 1)] >> RM_NCOLON_SH) & 3u;
+        tok_batch(s, n, toks, tok_cap, sh, st, head, 32, la);
+        head += 32; rcount -= 32;
+      }
+      tpw::sync();
+    }
+    if (st.status) break;
+  }
+  if (!st.status) {
+    if (c_instr || (c_sep & 0xFFFFu) || (c_sep >> 16)) st.status = TS_NOT_JSON;     // unterminated string / separators after the last token
+    while (rcount && !st.status) {
+      const uint32_t m = rcount > 32 ? 32u : rcount;
+      const uint32_t la = rcount > 32 ? ((sh.ring_meta[(head + 32) & (RING - 1)] >> RM_NCOLON_SH) & 3u) : 0u;
+      tok_batch(s, n, toks, tok_cap, sh, st, head, m, la);
+      head += m; rcount -= m;
+    }
+  }
+  *ntok_out = st.ntok;
+  return st.status;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// analyze: grammar + container stack over the token array; patches every opener with {child count, layout mode}
+// ----------------------------------------------------------------------------------------------------------------------
+struct AnState {
+  uint32_t sp, root_cnt, last_was_key;
+  int status;
+};
+TP_FN bool table_candidate(const Shared& sh, uint32_t top) {
+  const uint32_t tfl = sh.cfl[top];
+  return !(tfl & C_OBJ) && sh.cnt[top] > 0 && (tfl & C_KEYSET_OK) && (tfl & C_ROW0_SIMPLE) && !(tfl & C_ND_SEEN) && sh.row0_n[top] != UNSET && sh.row0_n[top] != 0;
+}
+
+// Generic mode: tokens [i, i+m) with one walk over their brackets.  Returns the number of tokens consumed: the walk stops in
+// front of a row opener `{` of a table candidate (unless it is the batch's first token and `force`), so that table mode can
+// take over.
+TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& sh, AnState& st, uint32_t i, uint32_t m, bool force) {
+  const uint32_t l = tpw::lane();
+  const uint32_t ltm = tpw::lt_mask();
+  const bool act = l < m;
+  GTok t; t.pos = 0; t.w = K_CLOSE_ARR;
+  if (act) t = toks[i + l];
+  const uint32_t kind = gt_kind(t.w), ncomma = gt_nc(t.w), ncolon = gt_nk(t.w), len = gt_len(t.w), pos = t.pos;
+  bool bad = false;
+  uint32_t fb = 0;
   const bool isV = act && kind >= K_STR && kind != K_KEY;           // value that is not a container
   uint32_t evm = tpw::ballot(act && kind <= K_CLOSE_ARR);
   const uint32_t Km = tpw::ballot(act && kind == K_KEY), Vm = tpw::ballot(isV);
@@ -285,7 +562,7 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
   uint32_t sp = st.sp, root_cnt = st.root_cnt;
   bool ubad = false, uunsup = false;
   uint32_t ufb = 0;                  // warp-uniform verdicts of the walk
-  uint32_t cur = 0;
+  uint32_t cur = 0, consumed = m;
   while (true) {
     const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
     const uint32_t run = range_mask(cur, e);
@@ -308,30 +585,32 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
         tpw::sync();
         if (l == 0) {
           sh.cnt[top] = c0 + tpw::popc(Vr);
-          if (!isobj && Vr) sh.cfl[top] = tfl & ~C_ALL_OBJ;
+          if (!isobj && Vr) sh.cfl[top] = nondict_element(tfl, sh.row0_idx[top], sh.row0_n[top]);
         }
         if (isobj && Kr) {
           // duplicate-key screen on the hashes (a repeated hash, real duplicate or not, goes to the sequential encoder)
           const uint32_t kb = sh.khbase[top];
           const bool mine = inrun && kind == K_KEY;
-          if (mine) { if (kb + ord >= KH_CAP) fb = FB_KH_CAP; else sh.kh[kb + ord] = hash; }
+          uint32_t hash = 0;
+          if (mine) { hash = fnv1a(s + pos, len); if (kb + ord >= KH_CAP) fb = FB_KH_CAP; else sh.kh[kb + ord] = hash; }
           tpw::sync();
           if (mine && kb + ord < KH_CAP) for (uint32_t j = kb; j < kb + ord; ++j) if (sh.kh[j] == hash) { fb = FB_DUP_HASH; break; }
           // table detection: the keys of every later row against the first row's, position by position
           if (sp >= 2) {
             const uint32_t par = sp - 2, pfl = sh.cfl[par];
-            if (!(pfl & C_OBJ) && (pfl & C_COL_OK) && sh.row0_n[par] != UNSET && sh.open_idx[top] + 1 != sh.row0_idx[par]) {
+            if (!(pfl & C_OBJ) && (pfl & C_KEYSET_OK) && (pfl & C_ROW0_SIMPLE) && !(pfl & C_ND_SEEN) && sh.row0_n[par] != UNSET &&
+                sh.open_idx[top] + 1 != sh.row0_idx[par]) {
               const uint32_t r0 = sh.row0_idx[par] - 1, rn = sh.row0_n[par];
-              bool mism = false;
+              bool mism = false, diff = false;
               if (mine) {
-                if (ord >= rn) mism = true;
-                else {
-                  const GTok r = toks[r0 + 1 + 2 * ord];
-                  if (gt_kind(r.w) != K_KEY || gt_len(r.w) != len) mism = true;
-                  else { const uint8_t* a = s + r.pos; const uint8_t* b = s + pos; for (uint32_t i = 0; i < len; ++i) if (a[i] != b[i]) { mism = true; break; } }
+                if (ord >= rn || !key_equals(s, toks[r0 + 1 + 2 * ord], s + pos, len)) {
+                  mism = true;
+                  diff = true;                               // out of place: does the first row have this key at all?
+                  for (uint32_t j = 0; j < rn; ++j) if (key_equals(s, toks[r0 + 1 + 2 * j], s + pos, len)) { diff = false; break; }
                 }
               }
-              if (tpw::any(mism) && l == 0) sh.cfl[top] = sh.cfl[top] & ~C_ALIGNED;
+              const bool anym = tpw::any(mism), anyd = tpw::any(diff);
+              if (anym && l == 0) sh.cfl[top] = (sh.cfl[top] & ~C_ALIGNED) | (anyd ? C_DIFFSET : 0u);
             }
           }
         }
@@ -341,7 +620,7 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
     if (e >= m) break;
     // ---- the bracket at lane e
     const uint32_t ek = tpw::shfl(kind, e), ecomma = tpw::shfl(ncomma, e), ecolon = tpw::shfl(ncolon, e), eprevK = tpw::shfl(prevK, e);
-    const uint32_t eidx = st.ntok + e;
+    const uint32_t eidx = i + e;
     if (ek <= K_OPEN_ARR) {
       uint32_t newkb = 0;
       if (sp == 0) { if (ecomma || ecolon || root_cnt) ubad = true; ++root_cnt; }
@@ -350,11 +629,12 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
         uint32_t tfl = sh.cfl[top];
         const uint32_t ord = sh.cnt[top];
         const bool isobj = (tfl & C_OBJ) != 0;
+        if (ek == K_OPEN_OBJ && (e > 0 || !force) && table_candidate(sh, top)) { consumed = e; break; }   // a table row: table mode takes it from here
         if (isobj) { if (ecolon != 1 || ecomma != 0 || !eprevK) ubad = true; }
         else if (ecolon != 0 || ecomma != (ord > 0 ? 1u : 0u)) ubad = true;
         tfl &= ~C_ALL_SIMPLE;
-        if (ek == K_OPEN_ARR) tfl &= ~C_ALL_OBJ;
         if (isobj) tfl &= ~C_VALS_SIMPLE;
+        else if (ek == K_OPEN_ARR) tfl = nondict_element(tfl, sh.row0_idx[top], sh.row0_n[top]);
         newkb = sh.khbase[top] + (isobj ? ord + 1 : 0u);
         tpw::sync();
         if (l == 0) {
@@ -366,7 +646,7 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
       if (sp >= MAXD) { uunsup = true; break; }
       if (l == 0) {
         sh.open_idx[sp] = eidx; sh.cnt[sp] = 0; sh.khbase[sp] = newkb < KH_CAP ? newkb : KH_CAP;
-        sh.cfl[sp] = ek == K_OPEN_OBJ ? (C_OBJ | C_ALIGNED | C_VALS_SIMPLE) : (C_ALL_SIMPLE | C_ALL_OBJ | C_COL_OK);
+        sh.cfl[sp] = ek == K_OPEN_OBJ ? (C_OBJ | C_ALIGNED | C_VALS_SIMPLE) : (C_ALL_SIMPLE | C_ALL_OBJ | C_KEYSET_OK | C_ROWS_SIMPLE);
         sh.row0_idx[sp] = 0; sh.row0_n[sp] = UNSET;
       }
       ++sp;
@@ -376,32 +656,39 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
       const uint32_t top = sp - 1, tfl = sh.cfl[top], nn = sh.cnt[top], oi = sh.open_idx[top];
       const bool isobj = (tfl & C_OBJ) != 0;
       if ((ek == K_CLOSE_OBJ) != isobj || ecomma || ecolon) ubad = true;
-      if (nn > GT_MAXLEN) uunsup = true;
-      uint32_t w;
-      if (isobj) w = gt_make(K_OPEN_OBJ, 0, nn & GT_MAXLEN);
+      if (nn > GT_MAXLEN) ufb = FB_TOO_LONG;
+      uint32_t pk, pf;
+      if (isobj) { pk = K_OPEN_OBJ; pf = 0; }
       else {
-        const uint32_t mode = nn == 0 ? AM_EMPTY : ((tfl & C_ALL_OBJ) && (tfl & C_COL_OK)) ? AM_COLUMNAR : (tfl & C_ALL_SIMPLE) ? AM_INLINE : AM_ITEMS;
-        const uint32_t mixed = (sh.row0_idx[top] && !(tfl & C_ALL_OBJ)) ? AF_MIXED : 0u;
-        w = gt_make(K_OPEN_ARR, mode | mixed, nn & GT_MAXLEN);
+        const bool col = (tfl & C_ALL_OBJ) && (tfl & C_KEYSET_OK) && (tfl & C_ROWS_SIMPLE) && sh.row0_n[top] != 0;
+        const uint32_t mode = nn == 0 ? AM_EMPTY : col ? AM_COLUMNAR : (tfl & C_ALL_SIMPLE) ? AM_INLINE : AM_ITEMS;
+        if (col && (tfl & C_PERMUTED)) ufb = FB_ROW_ORDER;          // the rows need a gather: sequential encoder
+        uint32_t xf = 0;
+        if (sh.row0_idx[top] && !(tfl & C_ALL_OBJ)) xf = (tfl & C_CRASH) ? AF_CRASH : (!(tfl & C_ROW0_SIMPLE) && sh.row0_n[top] != 0) ? AF_MIXED : 0u;
+        pk = K_OPEN_ARR; pf = mode | xf;
       }
       if (sp >= 2 && isobj) {
         const uint32_t par = sp - 2;
         uint32_t pfl = sh.cfl[par];
         if (!(pfl & C_OBJ)) {
-          if (oi + 1 == sh.row0_idx[par]) {
-            if (nn == 0 || !(tfl & C_VALS_SIMPLE)) pfl &= ~C_COL_OK;
+          if (!(tfl & C_VALS_SIMPLE)) pfl &= ~C_ROWS_SIMPLE;
+          if (oi + 1 == sh.row0_idx[par]) {                          // the first row
+            if (tfl & C_VALS_SIMPLE) pfl |= C_ROW0_SIMPLE;
             tpw::sync();
             if (l == 0) { sh.row0_n[par] = nn; sh.cfl[par] = pfl; }
-          } else if (pfl & C_COL_OK) {
+          } else {
             const uint32_t rn = sh.row0_n[par];
-            if (rn == UNSET || nn != rn || !(tfl & C_VALS_SIMPLE)) pfl &= ~C_COL_OK;
-            else if (!(tfl & C_ALIGNED)) ufb = FB_ROW_ORDER;      // same size, other key order or other keys: the sequential encoder sorts it out
+            if (rn != UNSET && (pfl & C_KEYSET_OK) && !(pfl & C_ND_SEEN)) {
+              // same key set?  (no duplicate keys here — those went to the sequential encoder — so equal counts + every key found = equal sets)
+              if (nn != rn || (tfl & C_DIFFSET)) pfl &= ~C_KEYSET_OK;
+              else if (!(tfl & C_ALIGNED)) pfl |= C_PERMUTED;
+            }
             tpw::sync();
             if (l == 0) sh.cfl[par] = pfl;
           }
         }
       }
-      if (l == 0 && oi < tok_cap) toks[oi].w = w;
+      if (l == 0 && oi < tok_cap) toks[oi].w = gt_patch(toks[oi].w, pk, pf, nn & GT_MAXLEN);
       --sp;
       tpw::sync();
     }
@@ -409,130 +696,78 @@ TP_FN void p1_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, 
     evm &= evm - 1;
   }
   st.sp = sp; st.root_cnt = root_cnt;
-  st.last_was_key = tpw::shfl(kind == K_KEY ? 1u : 0u, m - 1);
-  st.ntok += m;
-  const bool any_bad = tpw::any(bad) || ubad, any_unsup = tpw::any(unsup) || uunsup;
-  const uint32_t fbm = tpw::ballot(fb != 0);
+  if (consumed) st.last_was_key = tpw::shfl(kind == K_KEY ? 1u : 0u, consumed - 1);
+  // verdicts of lanes past the stop point do not count (their tokens are walked again)
+  const uint32_t live = bits_below(consumed);
+  const bool any_bad = (tpw::ballot(bad) & live) != 0 || ubad;
+  const uint32_t fbm = tpw::ballot(fb != 0) & live;
   if (any_bad) st.status = TS_NOT_JSON;
-  else if (any_unsup) st.status = TS_UNSUPPORTED;
+  else if (uunsup) st.status = TS_UNSUPPORTED;
   else if (fbm) st.status = TS_FALLBACK | (int)(tpw::shfl(fb, tpw::ffs(fbm) - 1) << 8);
   else if (ufb) st.status = TS_FALLBACK | (int)(ufb << 8);
+  return consumed;
 }
 
-// ----------------------------------------------------------------------------------------------------------------------
-// pass 1: front end + batches.  Returns 0 or a TS_* status (warp-uniform); *ntok_out = tokens stored.
-// ----------------------------------------------------------------------------------------------------------------------
-TP_FN int pass1(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, const uint16_t* ctab, uint32_t* ntok_out) {
+// Table mode: token i opens a row of the array on top of the stack whose first row (rn members, primitives only) closed.
+// Lane r checks row r against the first row's token pattern; returns the number of leading rows that conform (each of
+// S = 2 + 2 rn tokens) after patching their openers and counting them as children.
+TP_FN uint32_t an_rows(const uint8_t* s, GTok* toks, uint32_t ntok, Shared& sh, AnState& st, uint32_t i) {
   const uint32_t l = tpw::lane();
-  const uint32_t ltm = tpw::lt_mask();
-  P1State st;
-  st.sp = 0; st.root_cnt = 0; st.ntok = 0; st.last_was_key = 0; st.status = 0;
-  uint32_t in_string = 0, bs_parity = 0, prev_other = 0, c_ncomma = 0, c_ncolon = 0, open_pos = 0;
-  uint32_t c_special = 0, c_nonkey = 0, c_hi = 0, c_bs = 0;     // classes seen so far in the string that is open across chunks
-  uint32_t head = 0, rcount = 0;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t p = base + l;
-    const uint32_t c = p < n ? (uint32_t)s[p] : (uint32_t)' ';
-    const uint32_t kc = ctab[c];                                // byte_class(c) from a 256-entry table (shared memory on the GPU)
-    const uint32_t bs = tpw::ballot(kc & BC_BS), qm = tpw::ballot(kc & BC_QUOTE), stc = tpw::ballot(kc & BC_STRUCT);
-    const uint32_t cm = tpw::ballot(kc & BC_COMMA), co = tpw::ballot(kc & BC_COLON), ws = tpw::ballot(kc & BC_WS), ctl = tpw::ballot(kc & BC_CTRL);
-    uint32_t esc = 0;
-    if (bs | bs_parity) {
-      esc = tpw::ballot(cfx::escaped_bit(bs, l, bs_parity) != 0);
-      bs_parity = cfx::next_bs_parity(bs, bs_parity);
+  const uint32_t top = st.sp - 1;
+  const uint32_t rn = sh.row0_n[top], r0 = sh.row0_idx[top] - 1, S = 2 + 2 * rn;
+  const uint32_t avail = (ntok - i) / S;
+  const uint32_t R = avail > 32 ? 32u : avail;
+  bool ok = l < R;
+  const uint32_t t0 = i + l * S;
+  if (ok) {
+    const uint32_t w0 = toks[t0].w, wc = toks[t0 + S - 1].w;
+    ok = gt_kind(w0) == K_OPEN_OBJ && gt_nc(w0) == 1 && gt_nk(w0) == 0 && gt_kind(wc) == K_CLOSE_OBJ && gt_nc(wc) == 0 && gt_nk(wc) == 0;
+    for (uint32_t k = 0; k < rn && ok; ++k) {
+      const GTok a = toks[t0 + 1 + 2 * k];
+      const uint32_t vw = toks[t0 + 2 + 2 * k].w;
+      ok = gt_nc(a.w) == (k ? 1u : 0u) && gt_nk(a.w) == 0 && gt_kind(vw) >= K_STR && gt_kind(vw) != K_KEY && gt_nc(vw) == 0 && gt_nk(vw) == 1 &&
+           key_equals(s, toks[r0 + 1 + 2 * k], s + a.pos, gt_len(a.w)) && gt_kind(a.w) == K_KEY;
     }
-    const uint32_t quotes = qm & ~esc;
-    uint32_t x = quotes;
-    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
-    const uint32_t instr = x ^ in_string;                       // opening quote included, closing quote excluded
-    in_string = (instr & 0x80000000u) ? ~0u : 0u;
-    const uint32_t openq = quotes & instr, closeq = quotes & ~instr;
-    const uint32_t content = instr & ~openq;
-    if (ctl & content) { st.status = TS_NOT_JSON; break; }      // raw control character inside a string
-    const uint32_t outside = ~instr & ~closeq;
-    const uint32_t st_out = stc & outside, comma_out = cm & outside, colon_out = co & outside;
-    const uint32_t other = outside & ~stc & ~ws;
-    const uint32_t starts = other & ~((other << 1) | prev_other);
-    prev_other = other >> 31;
-    const uint32_t brackets = st_out & ~comma_out & ~colon_out;
-    const uint32_t T = brackets | closeq | starts;
-    // string classes (only bytes inside strings matter)
-    uint32_t m_special = 0, m_nonkey = 0, m_hi = 0;
-    if (content) {
-      m_special = tpw::ballot(kc & BC_SPECIAL) & content;
-      m_nonkey = tpw::ballot(kc & BC_NONKEY) & content;
-      m_hi = tpw::ballot(kc & BC_HI) & content;
-    }
-    const uint32_t m_bs = bs & content;
-    if ((T >> l) & 1u) {
-      const uint32_t prevT = T & ltm;
-      uint32_t between, nc, nk;
-      if (prevT) { between = ltm & ~bits_below(32 - tpw::clz(prevT)); nc = 0; nk = 0; }
-      else { between = ltm; nc = c_ncomma; nk = c_ncolon; }
-      nc = sat3(nc + tpw::popc(comma_out & between));
-      nk = sat3(nk + tpw::popc(colon_out & between));
-      uint32_t meta = (nc << RM_NCOMMA_SH) | (nk << RM_NCOLON_SH), tpos = p, tlen = 0;
-      if ((brackets >> l) & 1u) meta |= c == '{' ? K_OPEN_OBJ : c == '[' ? K_OPEN_ARR : c == '}' ? K_CLOSE_OBJ : K_CLOSE_ARR;
-      else if ((closeq >> l) & 1u) {
-        const uint32_t qb = quotes & ltm;
-        uint32_t span, sp_ = 0, nk_ = 0, hi_ = 0, b_ = 0, op;
-        if (qb) { const uint32_t ob = 31 - tpw::clz(qb); op = base + ob; span = ltm & ~bits_below(ob + 1); }
-        else { op = open_pos; span = ltm; sp_ = c_special; nk_ = c_nonkey; hi_ = c_hi; b_ = c_bs; }
-        tpos = op + 1; tlen = p - op - 1;
-        meta |= K_STR;
-        if (sp_ | (m_special & span)) meta |= RM_SPECIAL;
-        if (nk_ | (m_nonkey & span)) meta |= RM_NONKEY;
-        if (hi_ | (m_hi & span)) meta |= RM_HI;
-        if (b_ | (m_bs & span)) meta |= RM_BS;
-      } else {
-        meta |= K_NUM;
-        const uint32_t e = ~other & ~bits_below(l + 1);           // first byte after the run, within the chunk
-        if (e) tlen = tpw::ffs(e) - 1 - l; else { tlen = 32 - l; meta |= RM_OPENEND; }
-      }
-      const uint32_t r = (head + rcount + tpw::popc(prevT)) & (RING - 1);
-      sh.ring_pos[r] = tpos; sh.ring_len[r] = tlen; sh.ring_meta[r] = meta;
-    }
-    // carries
-    if (T) {
-      const uint32_t after = ~bits_below(32 - tpw::clz(T));
-      c_ncomma = sat3(tpw::popc(comma_out & after)); c_ncolon = sat3(tpw::popc(colon_out & after));
-    } else { c_ncomma = sat3(c_ncomma + tpw::popc(comma_out)); c_ncolon = sat3(c_ncolon + tpw::popc(colon_out)); }
-    if (in_string) {
-      if (openq) {                                               // the string still open was opened in this chunk
-        const uint32_t ob = 31 - tpw::clz(openq), after = ~bits_below(ob + 1);
-        open_pos = base + ob;
-        c_special = m_special & after; c_nonkey = m_nonkey & after; c_hi = m_hi & after; c_bs = m_bs & after;
-      } else { c_special |= m_special; c_nonkey |= m_nonkey; c_hi |= m_hi; c_bs |= m_bs; }
-    }
-    rcount += tpw::popc(T);
+  }
+  const uint32_t good = tpw::ballot(ok);
+  const uint32_t ngood = good == 0xFFFFFFFFu ? 32u : tpw::ffs(~good) - 1;
+  if (l < ngood) toks[t0].w = gt_patch(toks[t0].w, K_OPEN_OBJ, 0, rn);
+  if (ngood) {
     tpw::sync();
-    while (rcount >= 33 && !st.status) {
-      const uint32_t la = (sh.ring_meta[(head + 32) & (RING - 1)] >> RM_NCOLON_SH) & 3u;
-      p1_batch(s, n, toks, tok_cap, sh, st, head, 32, la);
-      head += 32; rcount -= 32;
-    }
-    if (st.status) break;
+    if (l == 0) sh.cnt[top] = sh.cnt[top] + ngood;
+    tpw::sync();
+    st.last_was_key = 0;
   }
-  if (!st.status) {
-    if (in_string || c_ncomma || c_ncolon) st.status = TS_NOT_JSON;     // unterminated string / separators after the last token
-    while (rcount && !st.status) {
-      const uint32_t m = rcount > 32 ? 32u : rcount;
-      const uint32_t la = rcount > 32 ? ((sh.ring_meta[(head + 32) & (RING - 1)] >> RM_NCOLON_SH) & 3u) : 0u;
-      p1_batch(s, n, toks, tok_cap, sh, st, head, m, la);
-      head += m; rcount -= m;
+  return ngood;
+}
+
+TP_FN int analyze(const uint8_t* s, GTok* toks, uint32_t ntok, uint32_t tok_cap, Shared& sh) {
+  AnState st; st.sp = 0; st.root_cnt = 0; st.last_was_key = 0; st.status = 0;
+  uint32_t i = 0;
+  bool force = false;
+  while (i < ntok && !st.status) {
+    if (!force && st.sp > 0 && table_candidate(sh, st.sp - 1) && gt_kind(toks[i].w) == K_OPEN_OBJ) {
+      const uint32_t S = 2 + 2 * sh.row0_n[st.sp - 1];
+      const uint32_t g = an_rows(s, toks, ntok, sh, st, i);
+      i += g * S;
+      if (g < 32) force = true;                       // the next row (if it is one) does not conform: generic walk
+      continue;
     }
-    if (!st.status && (st.sp != 0 || st.root_cnt != 1)) st.status = TS_NOT_JSON;
+    const uint32_t m = ntok - i > 32 ? 32u : ntok - i;
+    const uint32_t c = an_batch(s, toks, tok_cap, sh, st, i, m, force);
+    force = false;
+    i += c;
   }
-  *ntok_out = st.ntok;
+  if (!st.status && (st.sp != 0 || st.root_cnt != 1)) st.status = TS_NOT_JSON;
   return st.status;
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
-// pass 2: tokens -> TOON text
+// emit: tokens -> TOON text
 // ----------------------------------------------------------------------------------------------------------------------
 struct Piece {
   uint32_t l0;        // literal before the line break: 0 or ':'
-  uint32_t nl;        // 1 = line break + `spaces` blanks
+  uint32_t nl;        // 1 = line break + `spaces` blanks, 2 = blanks only (first line of the document)
   uint32_t spaces;
   uint32_t l1, l1n;   // literal after the indentation (up to 2 chars, low byte first)
   uint32_t body;      // B_*
@@ -542,201 +777,284 @@ enum : uint32_t { B_NONE = 0, B_SPAN = 1, B_QSPAN = 2, B_ESCX = 3, B_QESCX = 4, 
 enum : uint32_t { T_COLON = 0, T_COLON_SP = 1, T_COLUMNAR = 2 };
 TP_FN uint32_t lit2(char a, char b) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8); }
 
-TP_FN int pass2(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Shared& sh, bool report_errors) {
+struct EmState {
+  uint32_t sp, ocur;
+  int status;
+  bool over;
+  uint32_t col_first, col_rows, col_rn;    // set when a batch stopped behind a table header: first row token, rows, members per row
+};
+
+// text of one primitive value token (string / number / literal) as a table cell: length, then bytes
+TP_FN uint32_t cell_len(const uint8_t* s, const GTok t, uint32_t* err) {
+  const uint32_t kind = gt_kind(t.w), fl = gt_flags(t.w), len = gt_len(t.w);
+  if (kind != K_STR) return len;
+  const bool q = (fl & SF_Q) != 0;
+  if (q && (fl & SF_CTRLERR)) *err = TS_VALUE_ERROR;
+  if (fl & SF_ESCX) return escx_len(s + t.pos, len, q);
+  return len + (q ? 2u : 0u);
+}
+TP_FN void cell_put(Emit& em, const uint8_t* s, const GTok t) {
+  const uint32_t kind = gt_kind(t.w), fl = gt_flags(t.w), len = gt_len(t.w);
+  if (kind != K_STR) { em.span(s + t.pos, len); return; }
+  const bool q = (fl & SF_Q) != 0;
+  if (fl & SF_ESCX) { em.escx(s + t.pos, len, q); return; }
+  if (q) em.put('"');
+  em.span(s + t.pos, len);
+  if (q) em.put('"');
+}
+
+// Generic mode: tokens [i, i+m).  Returns the number consumed: the batch ends right behind the header of a table.
+TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8_t* out, uint32_t out_cap, Shared& sh, EmState& st, uint32_t i, uint32_t m,
+                        bool report_errors) {
   const uint32_t l = tpw::lane();
   const uint32_t ltm = tpw::lt_mask();
   uint32_t* f_mode = sh.open_idx; uint32_t* f_cnt = sh.cnt; uint32_t* f_pre = sh.cfl; uint32_t* f_ind = sh.khbase;
-  uint32_t sp = 0, root_cnt = 0, ocur = 0;
-  int status = 0;
-  bool over = false;
-  for (uint32_t base = 0; base < ntok; base += 32) {
-    const uint32_t m = ntok - base > 32 ? 32u : ntok - base;
-    const bool act = l < m;
-    GTok t; t.pos = 0; t.w = K_CLOSE_ARR;
-    if (act) t = toks[base + l];
-    const uint32_t kind = gt_kind(t.w), fl = gt_flags(t.w), len = gt_len(t.w);
-    uint32_t nk = tpw::shfl_down(kind, 1);                         // kind of the following token
-    if (l + 1 >= m) nk = base + m < ntok ? gt_kind(toks[base + m].w) : (uint32_t)K_CLOSE_ARR;
-    Piece pc; pc.l0 = 0; pc.nl = 0; pc.spaces = 0; pc.l1 = 0; pc.l1n = 0; pc.body = B_NONE; pc.tail = T_COLON;
-    uint32_t err = 0;                                             // per-lane TS_* error of this token
-    const bool isV = act && kind >= K_STR && kind != K_KEY;
-    uint32_t evm = tpw::ballot(act && kind <= K_CLOSE_ARR);
-    const uint32_t Vm = tpw::ballot(isV);
-    uint32_t cur = 0;
-    while (true) {
-      const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
-      const uint32_t run = range_mask(cur, e);
-      if (run) {
-        const bool inrun = (run >> l) & 1u;
-        if (sp == 0) { root_cnt += tpw::popc(run); if (inrun) pc.body = B_SPAN; }
-        else {
-          const uint32_t top = sp - 1, mode = f_mode[top], pre = f_pre[top], ind = f_ind[top], c0 = f_cnt[top];
-          const uint32_t Vr = Vm & run;
-          const uint32_t ord = c0 + tpw::popc(Vr & ltm);
-          if (inrun) {
-            if (kind == K_KEY) {
-              if (mode == M_OBJ) { pc.nl = (pre == 0 && ord == 0 && sp == 1) ? 2u : 1u; pc.spaces = pre; pc.body = B_SPAN; }
-              else if (mode == M_LIST_ITEM) {
-                pc.nl = 1; pc.spaces = pre + (ord == 0 ? 2 * ind : 2 * (ind + 1));
-                if (ord == 0) { pc.l1 = lit2('-', ' '); pc.l1n = 2; }
-                pc.body = B_SPAN;
-              }
-            } else {
+  uint32_t sp = st.sp;
+  bool act = l < m;
+  GTok t; t.pos = 0; t.w = K_CLOSE_ARR;
+  if (act) t = toks[i + l];
+  const uint32_t kind = gt_kind(t.w), fl = gt_flags(t.w), len = gt_len(t.w);
+  uint32_t nk = tpw::shfl_down(kind, 1);                         // kind of the following token
+  if (l + 1 >= m) nk = i + m < ntok ? gt_kind(toks[i + m].w) : (uint32_t)K_CLOSE_ARR;
+  Piece pc; pc.l0 = 0; pc.nl = 0; pc.spaces = 0; pc.l1 = 0; pc.l1n = 0; pc.body = B_NONE; pc.tail = T_COLON;
+  uint32_t err = 0;                                             // per-lane TS_* error of this token
+  const bool isV = act && kind >= K_STR && kind != K_KEY;
+  uint32_t evm = tpw::ballot(act && kind <= K_CLOSE_ARR);
+  const uint32_t Vm = tpw::ballot(isV);
+  uint32_t cur = 0, consumed = m;
+  st.col_rows = 0;
+  while (true) {
+    const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
+    const uint32_t run = range_mask(cur, e);
+    if (run) {
+      const bool inrun = (run >> l) & 1u;
+      if (sp == 0) { if (inrun) pc.body = B_SPAN; }
+      else {
+        const uint32_t top = sp - 1, mode = f_mode[top], pre = f_pre[top], ind = f_ind[top], c0 = f_cnt[top];
+        const uint32_t Vr = Vm & run;
+        const uint32_t ord = c0 + tpw::popc(Vr & ltm);
+        if (inrun) {
+          if (kind == K_KEY) {
+            if (mode == M_OBJ) { pc.nl = (pre == 0 && ord == 0 && sp == 1) ? 2u : 1u; pc.spaces = pre; pc.body = B_SPAN; }
+            else if (mode == M_LIST_ITEM) {
+              pc.nl = 1; pc.spaces = pre + (ord == 0 ? 2 * ind : 2 * (ind + 1));
+              if (ord == 0) { pc.l1 = lit2('-', ' '); pc.l1n = 2; }
               pc.body = B_SPAN;
-              if (mode == M_OBJ || mode == M_LIST_ITEM) { pc.l1 = lit2(':', ' '); pc.l1n = 2; }
-              else if (mode == M_ROW || mode == M_ARR_INLINE) { if (ord > 0) { pc.l1 = ','; pc.l1n = 1; } }
-              else if (mode == M_ARR_ITEMS) { pc.nl = 1; pc.spaces = pre + 2 * (ind + 1); pc.l1 = lit2('-', ' '); pc.l1n = 2; }
             }
+          } else {
+            pc.body = B_SPAN;
+            if (mode == M_OBJ || mode == M_LIST_ITEM) { pc.l1 = lit2(':', ' '); pc.l1n = 2; }
+            else if (mode == M_ROW || mode == M_ARR_INLINE) { if (ord > 0) { pc.l1 = ','; pc.l1n = 1; } }
+            else if (mode == M_ARR_ITEMS) { pc.nl = 1; pc.spaces = pre + 2 * (ind + 1); pc.l1 = lit2('-', ' '); pc.l1n = 2; }
           }
-          tpw::sync();
-          if (l == 0) f_cnt[top] = c0 + tpw::popc(Vr);
-          tpw::sync();
         }
+        tpw::sync();
+        if (l == 0) f_cnt[top] = c0 + tpw::popc(Vr);
+        tpw::sync();
       }
-      if (e >= m) break;
-      const uint32_t ek = tpw::shfl(kind, e);
-      if (ek <= K_OPEN_ARR) {
-        const uint32_t en = tpw::shfl(len, e), efl = tpw::shfl(fl, e), enk = tpw::shfl(nk, e);
-        uint32_t pmode = M_ROOT, pre = 0, ind = 0, ord = 0;
-        if (sp == 0) ++root_cnt;
-        else { const uint32_t top = sp - 1; pmode = f_mode[top]; pre = f_pre[top]; ind = f_ind[top]; ord = f_cnt[top]; tpw::sync(); if (l == 0) f_cnt[top] = ord + 1; }
-        uint32_t nmode = M_DEAD, npre = 0, nind = 0;
-        Piece q; q.l0 = 0; q.nl = 0; q.spaces = 0; q.l1 = 0; q.l1n = 0; q.body = B_NONE; q.tail = T_COLON;
-        uint32_t eerr = 0;
-        if (ek == K_OPEN_OBJ) {
-          if (pmode == M_ROOT) { nmode = M_OBJ; npre = 0; nind = 0; }
-          else if (pmode == M_OBJ) { q.l1 = ':'; q.l1n = 1; nmode = M_OBJ; npre = pre + 2; nind = ind + 1; }
-          else if (pmode == M_ARR_ITEMS) {
-            if (en == 0) { q.nl = 1; q.spaces = pre + 2 * (ind + 1); q.l1 = '-'; q.l1n = 1; }
-            else { nmode = M_LIST_ITEM; npre = pre; nind = ind + 1; }
-          } else if (pmode == M_LIST_ITEM) {
-            if (en == 0) { q.l1 = lit2(':', ' '); q.l1n = 2; }
-            else { q.l1 = ':'; q.l1n = 1; nmode = M_OBJ; npre = pre + 2 * (ind + 1) + 2; nind = ind + 2; }
-          } else if (pmode == M_ARR_COL) { q.nl = 1; q.spaces = pre; nmode = M_ROW; }
-          if (en == 0) nmode = M_DEAD;
-        } else {
-          const uint32_t amode = efl & 3u;
-          uint32_t apre = pre, aind = ind;                           // arguments of begin_array
-          bool col_on_hyphen = false;
-          q.body = B_ARR;
-          if (pmode == M_ARR_ITEMS) { const uint32_t ci = 2 * (ind + 1); q.nl = 1; q.spaces = pre + ci; q.l1 = lit2('-', ' '); q.l1n = 2; apre = pre + ci + 2; aind = ind + 2; }
-          else if (pmode == M_LIST_ITEM) {
-            const uint32_t fi = 2 * (ind + 1);
-            if (en == 0) { q.l1 = lit2(':', ' '); q.l1n = 2; }
-            else {
-              if (ord == 0) {                                       // toon.py:400-404: columnar attempt without a type check
-                if (enk != K_OPEN_OBJ) eerr = TS_ATTR_ERROR;
-                else if (efl & AF_MIXED) eerr = TS_FALLBACK | (FB_MIXED_ITEM << 8);
-                else if (amode == AM_COLUMNAR) col_on_hyphen = true;
-              }
-              apre = pre + fi + 2; aind = ind + 2;
-              if (!col_on_hyphen) { q.l0 = ':'; q.nl = 1; q.spaces = apre; }
-            }
-          }
-          if (amode == AM_EMPTY) q.tail = T_COLON;
-          else if (amode == AM_COLUMNAR) { q.tail = T_COLUMNAR; nmode = M_ARR_COL; npre = apre + 2; nind = aind; }
-          else if (amode == AM_INLINE) { q.tail = T_COLON_SP; nmode = M_ARR_INLINE; }
-          else { q.tail = T_COLON; nmode = M_ARR_ITEMS; npre = apre; nind = aind; }
-          if (col_on_hyphen) npre = apre;
-        }
-        if (l == e) { pc = q; err = eerr; }
-        if (sp >= MAXD) { status = TS_UNSUPPORTED; break; }
-        tpw::sync();
-        if (l == 0) { f_mode[sp] = nmode; f_pre[sp] = npre; f_ind[sp] = nind; f_cnt[sp] = 0; }
-        ++sp;
-        tpw::sync();
+    }
+    if (e >= m) break;
+    const uint32_t ek = tpw::shfl(kind, e);
+    if (ek <= K_OPEN_ARR) {
+      const uint32_t en = tpw::shfl(len, e), efl = tpw::shfl(fl, e), enk = tpw::shfl(nk, e);
+      uint32_t pmode = M_ROOT, pre = 0, ind = 0, ord = 0;
+      if (sp > 0) { const uint32_t top = sp - 1; pmode = f_mode[top]; pre = f_pre[top]; ind = f_ind[top]; ord = f_cnt[top]; tpw::sync(); if (l == 0) f_cnt[top] = ord + 1; }
+      uint32_t nmode = M_DEAD, npre = 0, nind = 0;
+      Piece q; q.l0 = 0; q.nl = 0; q.spaces = 0; q.l1 = 0; q.l1n = 0; q.body = B_NONE; q.tail = T_COLON;
+      uint32_t eerr = 0;
+      bool table = false;
+      if (ek == K_OPEN_OBJ) {
+        if (pmode == M_ROOT) { nmode = M_OBJ; npre = 0; nind = 0; }
+        else if (pmode == M_OBJ) { q.l1 = ':'; q.l1n = 1; nmode = M_OBJ; npre = pre + 2; nind = ind + 1; }
+        else if (pmode == M_ARR_ITEMS) {
+          if (en == 0) { q.nl = 1; q.spaces = pre + 2 * (ind + 1); q.l1 = '-'; q.l1n = 1; }
+          else { nmode = M_LIST_ITEM; npre = pre; nind = ind + 1; }
+        } else if (pmode == M_LIST_ITEM) {
+          if (en == 0) { q.l1 = lit2(':', ' '); q.l1n = 2; }
+          else { q.l1 = ':'; q.l1n = 1; nmode = M_OBJ; npre = pre + 2 * (ind + 1) + 2; nind = ind + 2; }
+        } else if (pmode == M_ARR_COL) { q.nl = 1; q.spaces = pre; nmode = M_ROW; }
+        if (en == 0) nmode = M_DEAD;
       } else {
-        --sp;
-      }
-      cur = e + 1;
-      evm &= evm - 1;
-    }
-    if (status) break;
-
-    // ---- piece lengths
-    uint32_t blen = 0;
-    const uint8_t* src = s + t.pos;
-    if (act && pc.body == B_SPAN) {
-      if (kind == K_KEY) { if (!(fl & KF_KEYOK)) pc.body = B_QSPAN; }
-      else if (kind == K_STR) {
-        const bool q = (fl & SF_Q) != 0;
-        if (q && (fl & SF_CTRLERR)) err = TS_VALUE_ERROR;
-        pc.body = (fl & SF_ESCX) ? (q ? B_QESCX : B_ESCX) : (q ? B_QSPAN : B_SPAN);
-      }
-    }
-    uint32_t hk = 0;                                              // columnar header: number of keys
-    if (act) {
-      if (pc.body == B_SPAN) blen = len;
-      else if (pc.body == B_QSPAN) blen = len + 2;
-      else if (pc.body == B_ESCX || pc.body == B_QESCX) blen = escx_len(src, len, pc.body == B_QESCX);
-      else if (pc.body == B_ARR) {
-        blen = 2 + dec_digits(len) + (pc.tail == T_COLON_SP ? 2u : 1u);
-        if (pc.tail == T_COLUMNAR) {
-          hk = gt_len(toks[base + l + 1].w);                      // members of the first row
-          blen += 2 + (hk - 1);
-          for (uint32_t j = 0; j < hk; ++j) blen += gt_len(toks[base + l + 2 + 2 * j].w);
+        const uint32_t amode = efl & 3u;
+        uint32_t apre = pre, aind = ind;                           // arguments of begin_array
+        bool col_on_hyphen = false;
+        q.body = B_ARR;
+        if (pmode == M_ARR_ITEMS) { const uint32_t ci = 2 * (ind + 1); q.nl = 1; q.spaces = pre + ci; q.l1 = lit2('-', ' '); q.l1n = 2; apre = pre + ci + 2; aind = ind + 2; }
+        else if (pmode == M_LIST_ITEM) {
+          const uint32_t fi = 2 * (ind + 1);
+          if (en == 0) { q.l1 = lit2(':', ' '); q.l1n = 2; }
+          else {
+            if (ord == 0) {                                       // toon.py:400-404: columnar attempt without a type check
+              if (enk != K_OPEN_OBJ) eerr = TS_ATTR_ERROR;
+              else if (efl & AF_CRASH) eerr = TS_ATTR_ERROR;
+              else if (efl & AF_MIXED) eerr = TS_FALLBACK | (FB_MIXED_ITEM << 8);
+              else if (amode == AM_COLUMNAR) col_on_hyphen = true;
+            }
+            apre = pre + fi + 2; aind = ind + 2;
+            if (!col_on_hyphen) { q.l0 = ':'; q.nl = 1; q.spaces = apre; }
+          }
         }
+        if (amode == AM_EMPTY) q.tail = T_COLON;
+        else if (amode == AM_COLUMNAR) { q.tail = T_COLUMNAR; nmode = M_ARR_COL; npre = apre + 2; nind = aind; table = true; }
+        else if (amode == AM_INLINE) { q.tail = T_COLON_SP; nmode = M_ARR_INLINE; }
+        else { q.tail = T_COLON; nmode = M_ARR_ITEMS; npre = apre; nind = aind; }
+        if (col_on_hyphen) npre = apre;
+      }
+      if (l == e) { pc = q; err = eerr; }
+      if (sp >= MAXD) { st.status = TS_UNSUPPORTED; break; }
+      tpw::sync();
+      if (l == 0) { f_mode[sp] = nmode; f_pre[sp] = npre; f_ind[sp] = nind; f_cnt[sp] = 0; }
+      ++sp;
+      tpw::sync();
+      if (table && !eerr) {                                        // rows are written one lane per row (em_rows)
+        consumed = e + 1;
+        st.col_first = i + e + 1; st.col_rows = en; st.col_rn = gt_len(toks[i + e + 1].w);
+        break;
+      }
+    } else {
+      --sp;
+    }
+    cur = e + 1;
+    evm &= evm - 1;
+  }
+  st.sp = sp;
+  if (st.status) return consumed;
+  if (l >= consumed) { act = false; pc.l0 = 0; pc.nl = 0; pc.l1n = 0; pc.body = B_NONE; err = 0; }
+
+  // ---- piece lengths
+  uint32_t blen = 0;
+  const uint8_t* src = s + t.pos;
+  if (act && pc.body == B_SPAN) {
+    if (kind == K_KEY) { if (!(fl & KF_KEYOK)) pc.body = B_QSPAN; }
+    else if (kind == K_STR) {
+      const bool q = (fl & SF_Q) != 0;
+      if (q && (fl & SF_CTRLERR)) err = TS_VALUE_ERROR;
+      pc.body = (fl & SF_ESCX) ? (q ? B_QESCX : B_ESCX) : (q ? B_QSPAN : B_SPAN);
+    }
+  }
+  uint32_t hk = 0;                                              // columnar header: number of keys
+  if (act) {
+    if (pc.body == B_SPAN) blen = len;
+    else if (pc.body == B_QSPAN) blen = len + 2;
+    else if (pc.body == B_ESCX || pc.body == B_QESCX) blen = escx_len(src, len, pc.body == B_QESCX);
+    else if (pc.body == B_ARR) {
+      blen = 2 + dec_digits(len) + (pc.tail == T_COLON_SP ? 2u : 1u);
+      if (pc.tail == T_COLUMNAR) {
+        hk = gt_len(toks[i + l + 1].w);                         // members of the first row
+        blen += 2 + (hk - 1);
+        for (uint32_t j = 0; j < hk; ++j) blen += gt_len(toks[i + l + 2 + 2 * j].w);
       }
     }
-    const uint32_t plen = act ? ((pc.l0 ? 1u : 0u) + (pc.nl == 1 ? 1u : 0u) + (pc.nl ? pc.spaces : 0u) + pc.l1n + blen) : 0u;
+  }
+  const uint32_t plen = act ? ((pc.l0 ? 1u : 0u) + (pc.nl == 1 ? 1u : 0u) + (pc.nl ? pc.spaces : 0u) + pc.l1n + blen) : 0u;
+  const uint32_t incl = tpw::scan_incl(plen);
+  const uint32_t off = st.ocur + incl - plen;
+  const uint32_t total = tpw::shfl(incl, 31);
+  // first error / first overflow in token order
+  const uint32_t errm = tpw::ballot(err != 0), ovm = tpw::ballot(plen && off + plen > out_cap);
+  if (errm) {
+    const uint32_t fe = tpw::ffs(errm) - 1;
+    const bool ov_first = ovm && (tpw::ffs(ovm) - 1) < fe;
+    if (report_errors || !(st.over || ov_first)) { st.status = (int)tpw::shfl(err, fe); return consumed; }
+  }
+  if (ovm) { st.over = true; if (!report_errors) { st.status = TS_NOT_SMALLER; return consumed; } }
+  // ---- write
+  const bool longspan = act && (pc.body == B_SPAN || pc.body == B_QSPAN) && len >= 64;
+  if (act && plen) {
+    Emit em; em.out = out; em.cap = out_cap; em.o = off;
+    if (pc.l0) em.put(pc.l0);
+    if (pc.nl == 1) em.put('\n');
+    if (pc.nl) em.spaces(pc.spaces);
+    if (pc.l1n >= 1) em.put(pc.l1 & 0xFF);
+    if (pc.l1n >= 2) em.put((pc.l1 >> 8) & 0xFF);
+    if (pc.body == B_SPAN) { if (!longspan) em.span(src, len); }
+    else if (pc.body == B_QSPAN) { em.put('"'); if (!longspan) em.span(src, len); else em.o += len; em.put('"'); }
+    else if (pc.body == B_ESCX || pc.body == B_QESCX) em.escx(src, len, pc.body == B_QESCX);
+    else if (pc.body == B_ARR) {
+      em.put('['); em.uint_dec(len); em.put(']');
+      if (pc.tail == T_COLUMNAR) {
+        em.put('{');
+        for (uint32_t j = 0; j < hk; ++j) { const GTok k = toks[i + l + 2 + 2 * j]; if (j) em.put(','); em.span(s + k.pos, gt_len(k.w)); }
+        em.put('}'); em.put(':');
+      } else { em.put(':'); if (pc.tail == T_COLON_SP) em.put(' '); }
+    }
+  }
+  uint32_t lm = tpw::ballot(longspan);
+  while (lm) {                                                  // long spans: the whole warp copies
+    const uint32_t j = tpw::ffs(lm) - 1;
+    lm &= lm - 1;
+    const uint32_t jpos = tpw::shfl(t.pos, j), jlen = tpw::shfl(len, j);
+    const uint32_t jdst = tpw::shfl(off + plen - blen + (pc.body == B_QSPAN ? 1u : 0u), j);
+    for (uint32_t k = l; k < jlen; k += 32) if (jdst + k < out_cap) out[jdst + k] = s[jpos + k];
+  }
+  st.ocur += total;
+  return consumed;
+}
+
+// Table mode: `rows` rows of rn members each (2 + 2 rn tokens per row, primitives only) starting at token `first`;
+// every lane writes one row per round: line break, prefix, cells joined by commas.
+TP_FN void em_rows(const uint8_t* s, const GTok* toks, uint8_t* out, uint32_t out_cap, Shared& sh, EmState& st, bool report_errors) {
+  const uint32_t l = tpw::lane();
+  const uint32_t rn = st.col_rn, S = 2 + 2 * rn, pre = sh.cfl[st.sp - 1];     // f_pre of the table frame = row prefix
+  for (uint32_t rb = 0; rb < st.col_rows; rb += 32) {
+    const uint32_t r = rb + l;
+    const bool act = r < st.col_rows;
+    const uint32_t t0 = st.col_first + r * S;
+    uint32_t plen = 0, err = 0;
+    if (act) {
+      plen = 1 + pre + (rn - 1);
+      for (uint32_t k = 0; k < rn; ++k) plen += cell_len(s, toks[t0 + 2 + 2 * k], &err);
+    }
     const uint32_t incl = tpw::scan_incl(plen);
-    const uint32_t off = ocur + incl - plen;
+    const uint32_t off = st.ocur + incl - plen;
     const uint32_t total = tpw::shfl(incl, 31);
-    // first error / first overflow in token order
     const uint32_t errm = tpw::ballot(err != 0), ovm = tpw::ballot(plen && off + plen > out_cap);
     if (errm) {
       const uint32_t fe = tpw::ffs(errm) - 1;
       const bool ov_first = ovm && (tpw::ffs(ovm) - 1) < fe;
-      if (report_errors || !(over || ov_first)) { status = (int)tpw::shfl(err, fe); break; }
+      if (report_errors || !(st.over || ov_first)) { st.status = (int)tpw::shfl(err, fe); return; }
     }
-    if (ovm) { over = true; if (!report_errors) { status = TS_NOT_SMALLER; break; } }
-    // ---- write
-    const bool longspan = act && (pc.body == B_SPAN || pc.body == B_QSPAN) && len >= 64;
-    if (act && plen) {
+    if (ovm) { st.over = true; if (!report_errors) { st.status = TS_NOT_SMALLER; return; } }
+    if (act) {
       Emit em; em.out = out; em.cap = out_cap; em.o = off;
-      if (pc.l0) em.put(pc.l0);
-      if (pc.nl == 1) em.put('\n');
-      if (pc.nl) em.spaces(pc.spaces);
-      if (pc.l1n >= 1) em.put(pc.l1 & 0xFF);
-      if (pc.l1n >= 2) em.put((pc.l1 >> 8) & 0xFF);
-      if (pc.body == B_SPAN) { if (!longspan) em.span(src, len); }
-      else if (pc.body == B_QSPAN) { em.put('"'); if (!longspan) em.span(src, len); else em.o += len; em.put('"'); }
-      else if (pc.body == B_ESCX || pc.body == B_QESCX) em.escx(src, len, pc.body == B_QESCX);
-      else if (pc.body == B_ARR) {
-        em.put('['); em.uint_dec(len); em.put(']');
-        if (pc.tail == T_COLUMNAR) {
-          em.put('{');
-          for (uint32_t j = 0; j < hk; ++j) { const GTok k = toks[base + l + 2 + 2 * j]; if (j) em.put(','); em.span(s + k.pos, gt_len(k.w)); }
-          em.put('}'); em.put(':');
-        } else { em.put(':'); if (pc.tail == T_COLON_SP) em.put(' '); }
-      }
+      em.put('\n');
+      em.spaces(pre);
+      for (uint32_t k = 0; k < rn; ++k) { if (k) em.put(','); cell_put(em, s, toks[t0 + 2 + 2 * k]); }
     }
-    uint32_t lm = tpw::ballot(longspan);
-    while (lm) {                                                  // long spans: the whole warp copies
-      const uint32_t j = tpw::ffs(lm) - 1;
-      lm &= lm - 1;
-      const uint32_t jpos = tpw::shfl(t.pos, j), jlen = tpw::shfl(len, j);
-      const uint32_t jdst = tpw::shfl(off + plen - blen + (pc.body == B_QSPAN ? 1u : 0u), j);
-      for (uint32_t i = l; i < jlen; i += 32) if (jdst + i < out_cap) out[jdst + i] = s[jpos + i];
-    }
-    ocur += total;
+    st.ocur += total;
   }
-  if (status) return status;
-  if (over || ocur > out_cap) return TS_NOT_SMALLER;
-  *out_len = ocur;
+}
+
+TP_FN int emit(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Shared& sh, bool report_errors) {
+  EmState st; st.sp = 0; st.ocur = 0; st.status = 0; st.over = false; st.col_first = 0; st.col_rows = 0; st.col_rn = 0;
+  uint32_t i = 0;
+  while (i < ntok && !st.status) {
+    const uint32_t m = ntok - i > 32 ? 32u : ntok - i;
+    i += em_batch(s, toks, ntok, out, out_cap, sh, st, i, m, report_errors);
+    if (!st.status && st.col_rows) {
+      em_rows(s, toks, out, out_cap, sh, st, report_errors);
+      i = st.col_first + st.col_rows * (2 + 2 * st.col_rn);       // the table's closing bracket comes next
+    }
+  }
+  if (st.status) return st.status;
+  if (st.over || st.ocur > out_cap) return TS_NOT_SMALLER;
+  *out_len = st.ocur;
   return TS_CONVERTED;
 }
 
 // Whole per-unit pipeline (all 32 lanes call it with the same arguments).  out_cap = n - 1 in the product (a
-// conversion is only kept when strictly smaller).  Returns a TS_* status, TS_FALLBACK when the sequential encoder has
-// to redo the unit.
+// conversion is only kept when strictly smaller).  Returns a TS_* status, TS_FALLBACK (| reason << 8) when the sequential
+// encoder has to redo the unit.
 TP_FN int toon_unit(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Shared& sh,
-                    const uint16_t* ctab, bool report_errors) {
+                    bool report_errors) {
   uint32_t ntok = 0;
-  const int st = pass1(s, n, toks, tok_cap, sh, ctab, &ntok);
+  int st = tokenize(s, n, toks, tok_cap, sh, &ntok);
   if (st) return st;
   tpw::sync();
-  return pass2(s, toks, ntok, out, out_cap, out_len, sh, report_errors);
+  st = analyze(s, toks, ntok, tok_cap, sh);
+  if (st) return st;
+  tpw::sync();
+  return emit(s, toks, ntok, out, out_cap, out_len, sh, report_errors);
 }
 
 }  // namespace cftp

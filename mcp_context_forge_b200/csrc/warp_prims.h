@@ -24,6 +24,7 @@ TP_FN uint32_t ffs(uint32_t v) { return (uint32_t)__ffs((int)v); }   // 1-based,
 #else
 #define TP_FN inline
 #define TP_SLOW inline
+struct uint4 { uint32_t x, y, z, w; };
 namespace tpw {
 static const uint32_t FULL = 0xFFFFFFFFu;
 uint32_t lane();

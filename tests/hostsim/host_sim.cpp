@@ -199,8 +199,14 @@ extern "C" int cfh_mask_indexed(const uint8_t* text, uint32_t n, int max_depth, 
 // order: 0 ascending / 1 descending lane schedule.  Returns the TS_* status (7 = sequential fallback requested).
 extern "C" int cfh_toon_tp(const uint8_t* text, uint32_t n, uint8_t* out, uint32_t out_cap, uint32_t* out_len, int report_errors, int order,
                            uint32_t* ntok_out) {
-  static uint16_t ctab[256];
-  if (!ctab[(int)'"']) for (uint32_t i = 0; i < 256; ++i) ctab[i] = (uint16_t)cftp::byte_class(i);
+  // the kernel reads whole 1 KiB steps on a 16-byte grid: give it the padding the device buffers have; `order` bits 4.. shift the
+  // unit's alignment inside the 16-byte grid
+  std::vector<uint8_t> buf(64 + n + 2048, 0xFF);
+  const uint32_t shift = ((uint32_t)order >> 4) & 15u;
+  uint8_t* base = buf.data() + 32;
+  base += (16 - ((uintptr_t)base & 15u)) & 15u;
+  uint8_t* s = base + shift;
+  memcpy(s, text, n);
   std::vector<cftp::GTok> toks(n / 2 + 64);
   std::vector<cftp::Shared> sh(1);
   int status[32];
@@ -208,9 +214,9 @@ extern "C" int cfh_toon_tp(const uint8_t* text, uint32_t n, uint8_t* out, uint32
   for (int i = 0; i < 32; ++i) { status[i] = -1; olen[i] = 0; }
   wemu::run_warp([&](uint32_t lane) {
     uint32_t ol = 0;
-    status[lane] = cftp::toon_unit(text, n, toks.data(), (uint32_t)toks.size(), out, out_cap, &ol, sh[0], ctab, report_errors != 0);
+    status[lane] = cftp::toon_unit(s, n, toks.data(), (uint32_t)toks.size(), out, out_cap, &ol, sh[0], report_errors != 0);
     olen[lane] = ol;
-  }, order);
+  }, order & 1);
   for (int i = 1; i < 32; ++i) if (status[i] != status[0] || olen[i] != olen[0]) return -100 - i;   // the status must be warp-uniform
   *out_len = olen[0];
   if (ntok_out) *ntok_out = (uint32_t)status[0] >> 8;   // fallback reason (diagnostics)

@@ -127,7 +127,7 @@ def main():
     nfb = nbad = 0
     for it in range(n):
         t = case()
-        r = check(t, rng.random() < 0.5, rng.random() < 0.5, it & 1)
+        r = check(t, rng.random() < 0.5, rng.random() < 0.5, (it & 1) | (rng.randrange(16) << 4))
         if r == "fallback":
             nfb += 1
         elif r:
