@@ -98,20 +98,24 @@ __global__ void __launch_bounds__(128) json_index_kernel(const uint8_t* __restri
 // ------------------------------------------------------------------------------------------------
 static const uint32_t TP_WARPS = 8;
 static const uint32_t TP_TOK_SLACK = 64;               // token capacity of unit u: len/2 + TP_TOK_SLACK
-__global__ void __launch_bounds__(TP_WARPS * 32) toon_tp_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
-                                                                 cftp::GTok* __restrict__ toks, uint8_t* __restrict__ out, uint32_t* __restrict__ out_len,
-                                                                 int32_t* __restrict__ status, uint32_t flags) {
-  __shared__ cftp::Shared sh[TP_WARPS];
+static const uint32_t TP_WARP_SMEM = (uint32_t)sizeof(cftp::Shared) + cftp::STAGE;   // container stack + token ring | staging buffer
+static const uint32_t TP_SMEM = TP_WARPS * TP_WARP_SMEM;                              // 110 592 B: two CTAs per SM
+__global__ void __launch_bounds__(TP_WARPS * 32, 2) toon_tp_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
+                                                                    cftp::GTok* __restrict__ toks, uint8_t* __restrict__ out, uint32_t* __restrict__ out_len,
+                                                                    int32_t* __restrict__ status, uint32_t flags) {
+  extern __shared__ __align__(16) uint8_t tp_smem[];
   const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const uint32_t u = blockIdx.x * TP_WARPS + wic;
   if (u >= n_units) return;
+  cftp::Shared& sh = *reinterpret_cast<cftp::Shared*>(tp_smem + (size_t)wic * TP_WARP_SMEM);
+  uint8_t* stage = tp_smem + (size_t)wic * TP_WARP_SMEM + sizeof(cftp::Shared);
   const uint64_t b = offsets[u];
   const uint64_t len64 = offsets[u + 1] - b - 1;
   if (len64 > 0x7FFFFFFFull) { if (lane == 0) { status[u] = cfj::TS_UNSUPPORTED; out_len[u] = 0; } return; }
   const uint32_t len = (uint32_t)len64;
   cftp::GTok* my = toks + (b >> 1) + (uint64_t)TP_TOK_SLACK * u;
   uint32_t ol = 0;
-  const int st = cftp::toon_unit(stream + b, len, my, len / 2 + TP_TOK_SLACK, out + b, len ? len - 1 : 0, &ol, sh[wic], (flags & 1u) != 0);
+  const int st = cftp::toon_unit(stream + b, len, my, len / 2 + TP_TOK_SLACK, out + b, len ? len - 1 : 0, &ol, sh, stage, (flags & 1u) != 0);
   if (lane == 0) {
     status[u] = st & 0xFF;
     out_len[u] = (st & 0xFF) == cfj::TS_CONVERTED ? ol : (uint32_t)st >> 8;
@@ -200,7 +204,9 @@ int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* 
   const bool prof = ctx->prof_on && (size_t)ctx->prof_used + 2 <= ctx->prof_ev.size();
   if (prof) cudaEventRecord(ctx->prof_ev[ctx->prof_used], st);
   if (!(flags & (CF_TOON_PARSE_ONLY | CF_TOON_SEQUENTIAL))) {
-    toon_tp_kernel<<<(b->n + TP_WARPS - 1) / TP_WARPS, TP_WARPS * 32, 0, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cftp::GTok*)ctx->d_toon_scratch,
+    static bool smem_set = false;
+    if (!smem_set) { CF_CUDA(ctx, cudaFuncSetAttribute(toon_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM)); smem_set = true; }
+    toon_tp_kernel<<<(b->n + TP_WARPS - 1) / TP_WARPS, TP_WARPS * 32, TP_SMEM, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cftp::GTok*)ctx->d_toon_scratch,
                                                                             d_out, d_out_len, d_status, flags);
     ctx->launches++;
     CF_CUDA(ctx, cudaGetLastError());

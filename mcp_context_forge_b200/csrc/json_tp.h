@@ -59,10 +59,12 @@ TP_FN uint32_t gt_patch(uint32_t w, uint32_t kind, uint32_t fl, uint32_t len) { 
 
 // ring record meta (tokenizer -> classification batch)
 enum : uint32_t { RM_KIND = 7u, RM_NCOMMA_SH = 3, RM_NCOLON_SH = 5, RM_SPECIAL = 1u << 7, RM_NONKEY = 1u << 8, RM_HI = 1u << 9, RM_BS = 1u << 10,
-                  RM_OPENEND = 1u << 11 /* scalar run reaches the end of its lane's 32 bytes: length still unknown */ };
+                  RM_OPENEND = 1u << 11 /* scalar run reaches past the next lane's 32 bytes: length still unknown */,
+                  RM_ALLDIGIT = 1u << 12 /* scalar run consists of ASCII digits only */ };
 
 // ---- per-warp shared memory ----------------------------------------------------------------------------------------
-static const uint32_t RING = 128, MAXD = 64, KH_CAP = 256;
+static const uint32_t RING = 256, MAXD = 64, KH_CAP = 256;
+static const uint32_t TOK_WIN = 192;      // tokens of one 1 KiB step pushed through the ring at a time (a window never overtakes the 32-token batches)
 static const uint32_t UNSET = 0xFFFFFFFFu;
 struct Shared {
   uint32_t ring_pos[RING], ring_len[RING], ring_meta[RING];
@@ -92,6 +94,47 @@ enum : uint32_t {
   C_DIFFSET = 4096       // some key does not occur in the first row at all
 };
 
+// Per-warp staging buffer (shared memory on the GPU): lane-strided byte accesses to global memory cost one L1 wavefront per
+// lane (profiles/r02_toon_tp_v2_ncu.txt: the kernel was bound by exactly that), so whatever a lane reads byte by byte is
+// first brought in with coalesced 16-byte loads, and table rows are written to global memory through it the same way.
+static const uint32_t STAGE = 8192;          // bytes per warp
+static const uint32_t WIN = 2048;            // tokenizer: the last two 1 KiB steps of source text
+static const uint32_t ROW_SRC = 5120, ROW_OUT = STAGE - ROW_SRC;   // table rows: source bytes of a round | its output
+
+// stage[0..) <- s[a0 .. a1) where a0 is rounded down to the 16-byte grid; returns the unit position of stage[0] (can be negative)
+TP_FN int64_t stage_load(uint8_t* stage, const uint8_t* s, uint32_t a0, uint32_t a1) {
+  const uint32_t lead = (uint32_t)((uintptr_t)(s + a0) & 15u);
+  const uint8_t* g = s + a0 - lead;
+  const uint32_t bytes = a1 - a0 + lead;
+  for (uint32_t o = tpw::lane() * 16; o < bytes; o += 512) *reinterpret_cast<uint4*>(stage + o) = *reinterpret_cast<const uint4*>(g + o);
+  tpw::sync();
+  return (int64_t)a0 - (int64_t)lead;
+}
+// out[dst .. dst+len) <- stage[0 .. len), coalesced (16-byte stores on the aligned middle)
+TP_FN void stage_flush(uint8_t* out, uint32_t dst, const uint8_t* stage, uint32_t len) {
+  const uint32_t l = tpw::lane();
+  uint8_t* g = out + dst;
+  const uint32_t head = (uint32_t)((16u - ((uintptr_t)g & 15u)) & 15u);
+  const uint32_t h = head < len ? head : len;
+  if (l < h) g[l] = stage[l];
+  if ((h & 15u) == 0 || true) {
+    // stage + h is not 16-byte aligned in general: assemble each 16-byte store from byte reads of shared memory
+    const uint32_t mid = (len - h) & ~15u;
+    for (uint32_t o = l * 16; o < mid; o += 512) {
+      const uint8_t* p = stage + h + o;
+      uint4 v;
+      v.x = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+      v.y = (uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
+      v.z = (uint32_t)p[8] | ((uint32_t)p[9] << 8) | ((uint32_t)p[10] << 16) | ((uint32_t)p[11] << 24);
+      v.w = (uint32_t)p[12] | ((uint32_t)p[13] << 8) | ((uint32_t)p[14] << 16) | ((uint32_t)p[15] << 24);
+      *reinterpret_cast<uint4*>(g + h + o) = v;
+    }
+    const uint32_t t0 = h + mid;
+    if (t0 + l < len) g[t0 + l] = stage[t0 + l];
+  }
+  tpw::sync();
+}
+
 // byte classes (scalar-run scan of the rare paths; the tokenizer itself uses SWAR flag words)
 enum : uint32_t { BC_QUOTE = 2, BC_STRUCT = 4, BC_WS = 32 };
 TP_FN uint32_t byte_class(uint32_t b) {
@@ -112,9 +155,10 @@ TP_FN uint32_t swar_eq(uint32_t w, uint32_t c) { const uint32_t x = w ^ (c * 0x0
 TP_FN uint32_t swar_range7(uint32_t x7, uint32_t lo, uint32_t hi) { return (x7 + (0x80u - lo) * 0x01010101u) & ~(x7 + (0x7Fu - hi) * 0x01010101u) & 0x80808080u; }
 TP_FN uint32_t gather4(uint32_t f) { return (((f >> 7) * 0x00204081u) >> 21) & 15u; }   // flags at bits 7,15,23,31 -> nibble
 
-struct LaneMasks { uint32_t q, bs, ob, cb, curly, cm, co, ws, ctrl, hi, special, nonkey; };   // bit j <-> byte j of the lane's 32 bytes
+struct LaneMasks { uint32_t q, bs, ob, cb, curly, cm, co, ws, ctrl, hi, special, nonkey, digit; };   // bit j <-> byte j of the lane's 32 bytes
 TP_FN void build_masks(const uint32_t* w, LaneMasks& M) {
-  M.q = M.bs = M.ob = M.cb = M.curly = M.cm = M.co = M.ws = M.ctrl = M.hi = M.special = M.nonkey = 0;
+  M.q = M.bs = M.ob = M.cb = M.curly = M.cm = M.co = M.ws = M.ctrl = M.hi = M.special = M.nonkey = M.digit = 0;
+  uint32_t f_bs[8], f_ctrl[8], any_bs = 0, any_ctrl = 0, any_hi = 0;
 #pragma unroll
   for (uint32_t k = 0; k < 8; ++k) {
     const uint32_t x = w[k], sh = 4 * k;
@@ -127,14 +171,28 @@ TP_FN void build_masks(const uint32_t* w, LaneMasks& M) {
     const uint32_t ctrl = ~((x7 + 0x60606060u) | x) & 0x80808080u;                    // byte < 0x20
     uint32_t ws = sp;
     if (ctrl) ws |= ctrl & (swar_eq(x, '\t') | swar_eq(x, '\n') | swar_eq(x, '\r'));
-    const uint32_t st = br | cm | co;
-    const uint32_t special = st | swar_eq(x, '-');
+    const uint32_t special = br | cm | co | swar_eq(x, '-');
     // [A-Za-z0-9_.]: folding to lower case maps '@' to '`' (below 'a') and '[' '\\' ']' '^' '_' to '{' '|' '}' '~' 0x7F (above 'z')
     const uint32_t x7l = x20 & 0x7F7F7F7Fu;
-    const uint32_t keych = (swar_range7(x7l, 'a', 'z') | swar_range7(x7, '0', '9') | swar_eq(x, '_') | swar_eq(x, '.')) & ~hi;
-    M.q |= gather4(q) << sh; M.bs |= gather4(bs) << sh; M.ob |= gather4(ob) << sh; M.cb |= gather4(cb) << sh; M.curly |= gather4(curly) << sh;
-    M.cm |= gather4(cm) << sh; M.co |= gather4(co) << sh; M.ws |= gather4(ws) << sh; M.ctrl |= gather4(ctrl) << sh; M.hi |= gather4(hi) << sh;
-    M.special |= gather4(special) << sh; M.nonkey |= gather4(keych ^ 0x80808080u) << sh;
+    const uint32_t digit = swar_range7(x7, '0', '9') & ~hi;
+    const uint32_t keych = ((swar_range7(x7l, 'a', 'z') & ~hi) | digit | swar_eq(x, '_') | swar_eq(x, '.'));
+    f_bs[k] = bs; f_ctrl[k] = ctrl; any_bs |= bs; any_ctrl |= ctrl; any_hi |= hi;
+    M.q |= gather4(q) << sh; M.ob |= gather4(ob) << sh; M.cb |= gather4(cb) << sh; M.curly |= gather4(curly) << sh;
+    M.cm |= gather4(cm) << sh; M.co |= gather4(co) << sh; M.ws |= gather4(ws) << sh;
+    M.special |= gather4(special) << sh; M.nonkey |= gather4(keych ^ 0x80808080u) << sh; M.digit |= gather4(digit) << sh;
+  }
+  // rare classes: only gathered when the lane has any such byte
+  if (any_bs) {
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) M.bs |= gather4(f_bs[k]) << (4 * k);
+  }
+  if (any_ctrl) {
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) M.ctrl |= gather4(f_ctrl[k]) << (4 * k);
+  }
+  if (any_hi) {
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) M.hi |= gather4(w[k] & 0x80808080u) << (4 * k);
   }
 }
 
@@ -226,8 +284,17 @@ struct Emit {
   uint32_t cap, o;
   TP_FN void put(uint32_t c) { if (o < cap) out[o] = (uint8_t)c; ++o; }
   TP_FN void span(const uint8_t* b, uint32_t len) {
-    if (o + len <= cap) { uint8_t* d = out + o; for (uint32_t i = 0; i < len; ++i) d[i] = b[i]; o += len; }
-    else for (uint32_t i = 0; i < len; ++i) put(b[i]);
+    if (o + len <= cap) {
+      // eight independent loads in flight, then the stores: a lone lane cannot hide the load latency any other way
+      uint8_t* d = out + o;
+      uint32_t i = 0;
+      for (; i + 8 <= len; i += 8) {
+        const uint8_t a0 = b[i], a1 = b[i + 1], a2 = b[i + 2], a3 = b[i + 3], a4 = b[i + 4], a5 = b[i + 5], a6 = b[i + 6], a7 = b[i + 7];
+        d[i] = a0; d[i + 1] = a1; d[i + 2] = a2; d[i + 3] = a3; d[i + 4] = a4; d[i + 5] = a5; d[i + 6] = a6; d[i + 7] = a7;
+      }
+      for (; i < len; ++i) d[i] = b[i];
+      o += len;
+    } else for (uint32_t i = 0; i < len; ++i) put(b[i]);
   }
   TP_FN void spaces(uint32_t k) { for (uint32_t i = 0; i < k; ++i) put(' '); }
   TP_FN void uint_dec(uint32_t v) {
@@ -278,12 +345,28 @@ TP_FN bool key_equals(const uint8_t* s, const GTok r, const uint8_t* b, uint32_t
   return true;
 }
 
+// rare paths of the classification batch, kept out of line (instruction-cache footprint of the hot loop)
+TP_SLOW uint32_t scalar_end(const uint8_t* s, uint32_t n, uint32_t e) {
+  while (e < n) { const uint32_t k = byte_class(s[e]); if (k & (BC_STRUCT | BC_WS | BC_QUOTE)) break; ++e; }
+  return e;
+}
+TP_SLOW bool string_slow(const uint8_t* s, uint32_t n, uint32_t pos, uint32_t len, uint32_t* sf) {
+  uint32_t p = pos - 1, h = 0;
+  return cfj::parse_string(s, n, &p, sf, &h) && p == pos + len + 1;
+}
+
 // ----------------------------------------------------------------------------------------------------------------------
 // tokenize, classification batch: raw tokens ring[head .. head+m) -> validated GTok toks[ntok ..); la_ncolon = colons in
 // front of the token that follows the batch (a string followed by a colon is a key)
 // ----------------------------------------------------------------------------------------------------------------------
 struct TokState { uint32_t ntok; int status; };
-TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, TokState& st, uint32_t head, uint32_t m, uint32_t la_ncolon) {
+// win[0..WIN) holds the unit's bytes [wlo, wlo + WIN) (unit positions; wlo may be "negative" = wrapped, see in_window)
+TP_FN const uint8_t* in_window(const uint8_t* s, const uint8_t* win, uint32_t wlo, uint32_t pos, uint32_t len) {
+  const uint32_t d = pos - wlo;                       // wraps to a huge value when pos < wlo
+  return (d < WIN && len <= WIN - d) ? win + d : s + pos;
+}
+TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, TokState& st, uint32_t head, uint32_t m, uint32_t la_ncolon,
+                     const uint8_t* win, uint32_t wlo) {
   const uint32_t l = tpw::lane();
   const bool act = l < m;
   uint32_t pos = 0, len = 0, meta = 0;
@@ -296,36 +379,35 @@ TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap,
   uint32_t fb = 0, fl = 0;
   const bool isK = act && kind == K_STR && ncolon == 0 && nxt_ncolon >= 1;
   if (act && kind == K_NUM) {                       // scalar run starting at pos
-    if (meta & RM_OPENEND) {                        // the run left its lane: find its end
-      uint32_t e = pos + len;
-      while (e < n) { const uint32_t k = byte_class(s[e]); if (k & (BC_STRUCT | BC_WS | BC_QUOTE)) break; ++e; }
-      len = e - pos;
-    }
-    const uint32_t c0 = s[pos];
-    if (c0 == 't') { if (len == 4 && s[pos + 1] == 'r' && s[pos + 2] == 'u' && s[pos + 3] == 'e') kind = K_LIT; else bad = true; }
-    else if (c0 == 'f') { if (len == 5 && s[pos + 1] == 'a' && s[pos + 2] == 'l' && s[pos + 3] == 's' && s[pos + 4] == 'e') kind = K_LIT; else bad = true; }
-    else if (c0 == 'n') { if (len == 4 && s[pos + 1] == 'u' && s[pos + 2] == 'l' && s[pos + 3] == 'l') kind = K_LIT; else bad = true; }
+    if (meta & RM_OPENEND) len = scalar_end(s, n, pos + len) - pos;        // the run left its lane and the next: find its end
+    const uint8_t* b = in_window(s, win, wlo, pos, len);
+    const uint32_t c0 = b[0];
+    if (c0 == 't') { if (len == 4 && b[1] == 'r' && b[2] == 'u' && b[3] == 'e') kind = K_LIT; else bad = true; }
+    else if (c0 == 'f') { if (len == 5 && b[1] == 'a' && b[2] == 'l' && b[3] == 's' && b[4] == 'e') kind = K_LIT; else bad = true; }
+    else if (c0 == 'n') { if (len == 4 && b[1] == 'u' && b[2] == 'l' && b[3] == 'l') kind = K_LIT; else bad = true; }
+    else if ((meta & RM_ALLDIGIT) && len < 19 && (len == 1 || c0 != '0')) { /* plain integer: the text is its own TOON form */ }
     else if (c0 == '-' || (c0 >= '0' && c0 <= '9')) {
-      uint32_t p = pos, nf = 0;
-      if (!cfj::scan_number(s, pos + len, &p, &nf) || p != pos + len) bad = true;
+      uint32_t p = 0, nf = 0;
+      if (!cfj::scan_number(b, len, &p, &nf) || p != len) bad = true;
       else {
         uint32_t eoff, elen;
-        if (num_canon(s + pos, len, nf, &eoff, &elen)) { pos += eoff; len = elen; }
+        if (num_canon(b, len, nf, &eoff, &elen)) { pos += eoff; len = elen; }
         else fb = FB_NUM_EXACT;                     // exact formatter: sequential encoder
       }
     } else bad = true;
   } else if (act && kind == K_STR) {
-    const uint8_t* b = s + pos;
+    // only the first / last bytes (and up to five for the reserved words) are looked at on the fast path
+    const uint8_t* b = in_window(s, win, wlo, pos, len);
     if (len > GT_MAXLEN) fb = FB_TOO_LONG;
     else if ((meta & (RM_BS | RM_HI)) || (len && b[0] >= '0' && b[0] <= '9')) {
       // escapes, non-ASCII or number-like candidates: the sequential validator decides (same function as json_toon.h)
-      uint32_t p = pos - 1, sf = 0, h = 0;
-      if (!cfj::parse_string(s, n, &p, &sf, &h) || p != pos + len + 1) bad = true;
+      uint32_t sf = 0;
+      if (!string_slow(s, n, pos, len, &sf)) bad = true;
       else if (isK) { if (sf & cfj::JF_ESC) fb = FB_KEY_ESCAPE; if (sf & cfj::JF_KEYOK) fl |= KF_KEYOK; }
       else {
         if (sf & cfj::JF_Q) fl |= SF_Q;
         if (sf & cfj::JF_CTRLERR) fl |= SF_CTRLERR;
-        if ((sf & cfj::JF_ESC) && has_complex_escape(b, len)) fl |= SF_ESCX;
+        if ((sf & cfj::JF_ESC) && has_complex_escape(s + pos, len)) fl |= SF_ESCX;
       }
     } else {
       const bool res = is_reserved(b, len);
@@ -353,7 +435,7 @@ TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap,
 // The unit is walked in 1 KiB steps on a 16-byte-aligned grid (the bytes in front of s and behind s+n that fall into the
 // first / last step count as blanks; the caller guarantees 15 readable bytes in front and 1 KiB behind).
 // ----------------------------------------------------------------------------------------------------------------------
-TP_FN int tokenize(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, uint32_t* ntok_out) {
+TP_FN int tokenize(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, Shared& sh, uint8_t* stage, uint32_t* ntok_out) {
   const uint32_t l = tpw::lane();
   const uint32_t ltm = tpw::lt_mask();
   TokState st; st.ntok = 0; st.status = 0;
@@ -378,11 +460,22 @@ TP_FN int tokenize(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, S
       for (uint32_t k = 0; k < 8; ++k) w[k] = 0x20202020u;
       valid = 0;
     }
+    // source window for the classification batches: [previous step | this step]
+    {
+      const uint4 p0 = *reinterpret_cast<const uint4*>(stage + 1024 + 32 * l), p1 = *reinterpret_cast<const uint4*>(stage + 1024 + 32 * l + 16);
+      tpw::sync();
+      *reinterpret_cast<uint4*>(stage + 32 * l) = p0; *reinterpret_cast<uint4*>(stage + 32 * l + 16) = p1;
+      uint4 c0, c1;
+      c0.x = w[0]; c0.y = w[1]; c0.z = w[2]; c0.w = w[3]; c1.x = w[4]; c1.y = w[5]; c1.z = w[6]; c1.w = w[7];
+      *reinterpret_cast<uint4*>(stage + 1024 + 32 * l) = c0; *reinterpret_cast<uint4*>(stage + 1024 + 32 * l + 16) = c1;
+      tpw::sync();
+    }
+    const uint32_t wlo = vb - 1024 - lead;             // unit position of stage[0] (wraps for the first step: nothing lies there)
     LaneMasks M;
     build_masks(w, M);
     if (valid != 0xFFFFFFFFu) {
       M.q &= valid; M.bs &= valid; M.ob &= valid; M.cb &= valid; M.curly &= valid; M.cm &= valid; M.co &= valid; M.ctrl &= valid; M.hi &= valid;
-      M.special &= valid; M.nonkey &= valid; M.ws |= ~valid;
+      M.special &= valid; M.nonkey &= valid; M.digit &= valid; M.ws |= ~valid;
     }
     // ---- escapes: which quotes are real
     uint32_t quotes = M.q;
@@ -467,50 +560,60 @@ TP_FN int tokenize(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, S
       const uint32_t r31 = tpw::shfl(r, 31), p31 = tpw::shfl(pp, 31), c31 = tpw::shfl(cc, 31);
       if (!r31) c_cls |= c31; else { c_open = p31; c_cls = c31; }
     }
-    // ---- tokens of this lane, in windows through the ring
+    // ---- tokens of this lane through the ring (TOK_WIN at a time), one pass per token kind so that the lanes of a pass
+    // run the same code: slot = rank of the token in text order, separators = commas / colons since the previous token
     const uint32_t cntT = tpw::popc(T);
     const uint32_t incl = tpw::scan_incl(cntT);
     const uint32_t lane_off = incl - cntT, total = tpw::shfl(incl, 31);
-    uint32_t Tm = T, k = 0, prevj = 32;               // prevj = bit of this lane's previous token (32 = none yet)
-    for (uint32_t done = 0; done < total && !st.status; done += 64) {
-      const uint32_t win = total - done > 64 ? 64u : total - done;
-      while (Tm && lane_off + k < done + win) {
-        const uint32_t j = tpw::ffs(Tm) - 1;
-        Tm &= Tm - 1;
-        const uint32_t below = bits_below(j);
-        uint32_t between, nc, nk;
-        if (prevj < 32) { between = below & ~bits_below(prevj + 1); nc = 0; nk = 0; }
-        else { between = below; nc = sep_in & 0xFFFFu; nk = sep_in >> 16; }
-        nc = sat3(nc + tpw::popc(comma_out & between));
-        nk = sat3(nk + tpw::popc(colon_out & between));
-        uint32_t meta = (nc << RM_NCOMMA_SH) | (nk << RM_NCOLON_SH), tpos = v + j - lead, tlen = 0;
-        if ((brackets >> j) & 1u) meta |= ((M.ob >> j) & 1u) ? (((M.curly >> j) & 1u) ? K_OPEN_OBJ : K_OPEN_ARR) : (((M.curly >> j) & 1u) ? K_CLOSE_OBJ : K_CLOSE_ARR);
-        else if ((closeq >> j) & 1u) {
-          const uint32_t qb = quotes & below;
-          uint32_t span, cls, op;
-          if (qb) { const uint32_t ob = 31 - tpw::clz(qb); op = v + ob; span = below & ~bits_below(ob + 1); cls = 0; }
-          else { op = so_pos; span = below; cls = so_cls; }
-          tpos = op + 1 - lead; tlen = (v + j) - op - 1;
-          meta |= K_STR;
-          if ((cls & 1u) | (m_special & span)) meta |= RM_SPECIAL;
-          if ((cls & 2u) | (m_nonkey & span)) meta |= RM_NONKEY;
-          if ((cls & 4u) | (m_hi & span)) meta |= RM_HI;
-          if ((cls & 8u) | (m_bs & span)) meta |= RM_BS;
-        } else {
-          meta |= K_NUM;
-          const uint32_t e = ~other & ~bits_below(j + 1);          // first byte after the run, within the lane
-          if (e) tlen = tpw::ffs(e) - 1 - j; else { tlen = 32 - j; meta |= RM_OPENEND; }
-        }
-        const uint32_t r = (head + rcount + (lane_off + k - done)) & (RING - 1);
-        sh.ring_pos[r] = tpos; sh.ring_len[r] = tlen; sh.ring_meta[r] = meta;
-        prevj = j;
-        ++k;
+    uint32_t other_nx = tpw::shfl_down(other, 1);       // the next lane's scalar bytes: a run may continue there
+    if (l == 31) other_nx = 0xFFFFFFFFu;                // unknown: treated as "continues" -> RM_OPENEND
+    for (uint32_t done = 0; done < total && !st.status; done += TOK_WIN) {
+      const uint32_t win = total - done > TOK_WIN ? TOK_WIN : total - done;
+      const uint32_t lo = done > lane_off ? done - lane_off : 0u, hi = done + win > lane_off ? done + win - lane_off : 0u;   // ranks [lo, hi) of this lane
+#define TP_TOKEN_PROLOGUE(MASK)                                                                               \
+      for (uint32_t tm = (MASK); tm;) {                                                                       \
+        const uint32_t j = tpw::ffs(tm) - 1;                                                                  \
+        tm &= tm - 1;                                                                                         \
+        const uint32_t below = bits_below(j), rank = tpw::popc(T & below);                                    \
+        if (rank < lo || rank >= hi) continue;                                                                \
+        const uint32_t pt = T & below;                                                                        \
+        uint32_t between = below, nc = sep_in & 0xFFFFu, nk = sep_in >> 16;                                   \
+        if (pt) { between = below & ~bits_below(32 - tpw::clz(pt)); nc = 0; nk = 0; }                         \
+        nc = sat3(nc + tpw::popc(comma_out & between));                                                       \
+        nk = sat3(nk + tpw::popc(colon_out & between));                                                       \
+        uint32_t meta = (nc << RM_NCOMMA_SH) | (nk << RM_NCOLON_SH), tpos = v + j - lead, tlen = 0;           \
+        const uint32_t r = (head + rcount + (lane_off + rank - done)) & (RING - 1);
+#define TP_TOKEN_EPILOGUE                                                                                     \
+        sh.ring_pos[r] = tpos; sh.ring_len[r] = tlen; sh.ring_meta[r] = meta;                                 \
       }
+      TP_TOKEN_PROLOGUE(brackets)
+        meta |= ((M.ob >> j) & 1u) ? (((M.curly >> j) & 1u) ? K_OPEN_OBJ : K_OPEN_ARR) : (((M.curly >> j) & 1u) ? K_CLOSE_OBJ : K_CLOSE_ARR);
+      TP_TOKEN_EPILOGUE
+      TP_TOKEN_PROLOGUE(closeq)
+        const uint32_t qb = quotes & below;
+        uint32_t span = below, cls = so_cls, op = so_pos;
+        if (qb) { const uint32_t ob = 31 - tpw::clz(qb); op = v + ob; span = below & ~bits_below(ob + 1); cls = 0; }
+        tpos = op + 1 - lead; tlen = (v + j) - op - 1;
+        meta |= K_STR;
+        if ((cls & 1u) | (m_special & span)) meta |= RM_SPECIAL;
+        if ((cls & 2u) | (m_nonkey & span)) meta |= RM_NONKEY;
+        if ((cls & 4u) | (m_hi & span)) meta |= RM_HI;
+        if ((cls & 8u) | (m_bs & span)) meta |= RM_BS;
+      TP_TOKEN_EPILOGUE
+      TP_TOKEN_PROLOGUE(starts)
+        meta |= K_NUM;
+        const uint32_t e = ~other & ~bits_below(j + 1);          // first byte after the run, within the lane
+        if (e) { tlen = tpw::ffs(e) - 1 - j; if (!(range_mask(j, j + tlen) & ~M.digit)) meta |= RM_ALLDIGIT; }
+        else if (~other_nx) tlen = 32 - j + tpw::ffs(~other_nx) - 1;   // ends in the next lane
+        else { tlen = 32 - j; meta |= RM_OPENEND; }
+      TP_TOKEN_EPILOGUE
+#undef TP_TOKEN_PROLOGUE
+#undef TP_TOKEN_EPILOGUE
       rcount += win;
       tpw::sync();
       while (rcount >= 33 && !st.status) {
         const uint32_t la = (sh.ring_meta[(head + 32) & (RING - 1)] >> RM_NCOLON_SH) & 3u;
-        tok_batch(s, n, toks, tok_cap, sh, st, head, 32, la);
+        tok_batch(s, n, toks, tok_cap, sh, st, head, 32, la, stage, wlo);
         head += 32; rcount -= 32;
       }
       tpw::sync();
@@ -518,11 +621,13 @@ TP_FN int tokenize(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, S
     if (st.status) break;
   }
   if (!st.status) {
+    const uint32_t steps = (vend + 1023) / 1024;
+    const uint32_t wlo = (steps - 1) * 1024 - 1024 - lead;
     if (c_instr || (c_sep & 0xFFFFu) || (c_sep >> 16)) st.status = TS_NOT_JSON;     // unterminated string / separators after the last token
     while (rcount && !st.status) {
       const uint32_t m = rcount > 32 ? 32u : rcount;
       const uint32_t la = rcount > 32 ? ((sh.ring_meta[(head + 32) & (RING - 1)] >> RM_NCOLON_SH) & 3u) : 0u;
-      tok_batch(s, n, toks, tok_cap, sh, st, head, m, la);
+      tok_batch(s, n, toks, tok_cap, sh, st, head, m, la, stage, wlo);
       head += m; rcount -= m;
     }
   }
@@ -711,22 +816,39 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
 // Table mode: token i opens a row of the array on top of the stack whose first row (rn members, primitives only) closed.
 // Lane r checks row r against the first row's token pattern; returns the number of leading rows that conform (each of
 // S = 2 + 2 rn tokens) after patching their openers and counting them as children.
-TP_FN uint32_t an_rows(const uint8_t* s, GTok* toks, uint32_t ntok, Shared& sh, AnState& st, uint32_t i) {
+TP_FN uint32_t an_rows(const uint8_t* s, GTok* toks, uint32_t ntok, Shared& sh, uint8_t* stage, AnState& st, uint32_t i) {
   const uint32_t l = tpw::lane();
   const uint32_t top = st.sp - 1;
   const uint32_t rn = sh.row0_n[top], r0 = sh.row0_idx[top] - 1, S = 2 + 2 * rn;
   const uint32_t avail = (ntok - i) / S;
-  const uint32_t R = avail > 32 ? 32u : avail;
-  bool ok = l < R;
+  uint32_t R = avail > 32 ? 32u : avail;
   const uint32_t t0 = i + l * S;
+  // source bytes of the candidate rows -> staging buffer (as many leading rows as fit)
+  const uint32_t a0 = toks[i].pos;
+  uint32_t rend = l < R ? toks[t0 + S - 1].pos + 1 : 0xFFFFFFFFu;
+  const uint32_t fits = tpw::ballot(l < R && rend >= a0 && rend - a0 <= STAGE - 32);
+  const uint32_t Rf = fits == 0xFFFFFFFFu ? 32u : tpw::ffs(~fits) - 1;
+  const uint8_t* sb = s;                               // base such that sb + pos addresses the row bytes
+  if (Rf) {
+    R = Rf;
+    const uint32_t a1 = tpw::shfl(rend, R - 1);
+    sb = stage - stage_load(stage, s, a0, a1);
+  }
+  bool ok = l < R;
   if (ok) {
     const uint32_t w0 = toks[t0].w, wc = toks[t0 + S - 1].w;
     ok = gt_kind(w0) == K_OPEN_OBJ && gt_nc(w0) == 1 && gt_nk(w0) == 0 && gt_kind(wc) == K_CLOSE_OBJ && gt_nc(wc) == 0 && gt_nk(wc) == 0;
-    for (uint32_t k = 0; k < rn && ok; ++k) {
-      const GTok a = toks[t0 + 1 + 2 * k];
-      const uint32_t vw = toks[t0 + 2 + 2 * k].w;
-      ok = gt_nc(a.w) == (k ? 1u : 0u) && gt_nk(a.w) == 0 && gt_kind(vw) >= K_STR && gt_kind(vw) != K_KEY && gt_nc(vw) == 0 && gt_nk(vw) == 1 &&
-           key_equals(s, toks[r0 + 1 + 2 * k], s + a.pos, gt_len(a.w)) && gt_kind(a.w) == K_KEY;
+    for (uint32_t kb = 0; kb < rn && ok; kb += 4) {            // four members per step: their token loads are issued together
+      GTok a[4]; uint32_t vw[4];
+#pragma unroll
+      for (uint32_t q = 0; q < 4; ++q) { const uint32_t k = kb + q < rn ? kb + q : rn - 1; a[q] = toks[t0 + 1 + 2 * k]; vw[q] = toks[t0 + 2 + 2 * k].w; }
+#pragma unroll
+      for (uint32_t q = 0; q < 4; ++q) {
+        const uint32_t k = kb + q < rn ? kb + q : rn - 1;
+        ok = ok && gt_nc(a[q].w) == (k ? 1u : 0u) && gt_nk(a[q].w) == 0 && gt_kind(vw[q]) >= K_STR && gt_kind(vw[q]) != K_KEY && gt_nc(vw[q]) == 0 &&
+             gt_nk(vw[q]) == 1 && gt_kind(a[q].w) == K_KEY && a[q].pos >= a0 && a[q].pos + gt_len(a[q].w) <= rend &&
+             key_equals(s, toks[r0 + 1 + 2 * k], sb + a[q].pos, gt_len(a[q].w));
+      }
     }
   }
   const uint32_t good = tpw::ballot(ok);
@@ -741,14 +863,14 @@ TP_FN uint32_t an_rows(const uint8_t* s, GTok* toks, uint32_t ntok, Shared& sh, 
   return ngood;
 }
 
-TP_FN int analyze(const uint8_t* s, GTok* toks, uint32_t ntok, uint32_t tok_cap, Shared& sh) {
+TP_FN int analyze(const uint8_t* s, GTok* toks, uint32_t ntok, uint32_t tok_cap, Shared& sh, uint8_t* stage) {
   AnState st; st.sp = 0; st.root_cnt = 0; st.last_was_key = 0; st.status = 0;
   uint32_t i = 0;
   bool force = false;
   while (i < ntok && !st.status) {
     if (!force && st.sp > 0 && table_candidate(sh, st.sp - 1) && gt_kind(toks[i].w) == K_OPEN_OBJ) {
       const uint32_t S = 2 + 2 * sh.row0_n[st.sp - 1];
-      const uint32_t g = an_rows(s, toks, ntok, sh, st, i);
+      const uint32_t g = an_rows(s, toks, ntok, sh, stage, st, i);
       i += g * S;
       if (g < 32) force = true;                       // the next row (if it is one) does not conform: generic walk
       continue;
@@ -992,18 +1114,37 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
 }
 
 // Table mode: `rows` rows of rn members each (2 + 2 rn tokens per row, primitives only) starting at token `first`;
-// every lane writes one row per round: line break, prefix, cells joined by commas.
-TP_FN void em_rows(const uint8_t* s, const GTok* toks, uint8_t* out, uint32_t out_cap, Shared& sh, EmState& st, bool report_errors) {
+// every lane writes one row per round: line break, prefix, cells joined by commas.  The round's source bytes come in and its
+// output goes out through the staging buffer (coalesced), as long as they fit.
+TP_FN void em_rows(const uint8_t* s, const GTok* toks, uint8_t* out, uint32_t out_cap, Shared& sh, uint8_t* stage, EmState& st, bool report_errors) {
   const uint32_t l = tpw::lane();
   const uint32_t rn = st.col_rn, S = 2 + 2 * rn, pre = sh.cfl[st.sp - 1];     // f_pre of the table frame = row prefix
-  for (uint32_t rb = 0; rb < st.col_rows; rb += 32) {
+  uint32_t rb = 0;
+  while (rb < st.col_rows) {
+    uint32_t R = st.col_rows - rb > 32 ? 32u : st.col_rows - rb;
     const uint32_t r = rb + l;
-    const bool act = r < st.col_rows;
     const uint32_t t0 = st.col_first + r * S;
+    // stage the source bytes of as many leading rows of the round as fit
+    const uint32_t a0 = toks[st.col_first + rb * S].pos;
+    const uint32_t rend = l < R ? toks[t0 + S - 1].pos + 1 : 0xFFFFFFFFu;
+    const uint32_t fits = tpw::ballot(l < R && rend >= a0 && rend - a0 <= ROW_SRC - 32);
+    const uint32_t Rf = fits == 0xFFFFFFFFu ? 32u : tpw::ffs(~fits) - 1;
+    const uint8_t* sb = s;
+    if (Rf) {
+      R = Rf;
+      sb = stage - stage_load(stage, s, a0, tpw::shfl(rend, R - 1));
+    } else R = 1;                                        // one over-long row at a time, straight from global memory
+    const bool act = l < R;
     uint32_t plen = 0, err = 0;
     if (act) {
       plen = 1 + pre + (rn - 1);
-      for (uint32_t k = 0; k < rn; ++k) plen += cell_len(s, toks[t0 + 2 + 2 * k], &err);
+      for (uint32_t kb = 0; kb < rn; kb += 4) {
+        GTok c[4];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) c[q] = toks[t0 + 2 + 2 * (kb + q < rn ? kb + q : rn - 1)];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) if (kb + q < rn) plen += cell_len(sb, c[q], &err);
+      }
     }
     const uint32_t incl = tpw::scan_incl(plen);
     const uint32_t off = st.ocur + incl - plen;
@@ -1015,24 +1156,30 @@ TP_FN void em_rows(const uint8_t* s, const GTok* toks, uint8_t* out, uint32_t ou
       if (report_errors || !(st.over || ov_first)) { st.status = (int)tpw::shfl(err, fe); return; }
     }
     if (ovm) { st.over = true; if (!report_errors) { st.status = TS_NOT_SMALLER; return; } }
+    const bool staged_out = Rf && total <= ROW_OUT && !st.over;
     if (act) {
-      Emit em; em.out = out; em.cap = out_cap; em.o = off;
+      Emit em;
+      if (staged_out) { em.out = stage + ROW_SRC - st.ocur; em.cap = st.ocur + ROW_OUT; }
+      else { em.out = out; em.cap = out_cap; }
+      em.o = off;
       em.put('\n');
       em.spaces(pre);
-      for (uint32_t k = 0; k < rn; ++k) { if (k) em.put(','); cell_put(em, s, toks[t0 + 2 + 2 * k]); }
+      for (uint32_t k = 0; k < rn; ++k) { if (k) em.put(','); cell_put(em, sb, toks[t0 + 2 + 2 * k]); }
     }
+    if (staged_out) { tpw::sync(); stage_flush(out, st.ocur, stage + ROW_SRC, total); }
     st.ocur += total;
+    rb += R;
   }
 }
 
-TP_FN int emit(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Shared& sh, bool report_errors) {
+TP_FN int emit(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Shared& sh, uint8_t* stage, bool report_errors) {
   EmState st; st.sp = 0; st.ocur = 0; st.status = 0; st.over = false; st.col_first = 0; st.col_rows = 0; st.col_rn = 0;
   uint32_t i = 0;
   while (i < ntok && !st.status) {
     const uint32_t m = ntok - i > 32 ? 32u : ntok - i;
     i += em_batch(s, toks, ntok, out, out_cap, sh, st, i, m, report_errors);
     if (!st.status && st.col_rows) {
-      em_rows(s, toks, out, out_cap, sh, st, report_errors);
+      em_rows(s, toks, out, out_cap, sh, stage, st, report_errors);
       i = st.col_first + st.col_rows * (2 + 2 * st.col_rn);       // the table's closing bracket comes next
     }
   }
@@ -1045,16 +1192,17 @@ TP_FN int emit(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8_t* out, 
 // Whole per-unit pipeline (all 32 lanes call it with the same arguments).  out_cap = n - 1 in the product (a
 // conversion is only kept when strictly smaller).  Returns a TS_* status, TS_FALLBACK (| reason << 8) when the sequential
 // encoder has to redo the unit.
+// `stage` = STAGE bytes of per-warp scratch, 16-byte aligned (shared memory on the GPU).
 TP_FN int toon_unit(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap, uint8_t* out, uint32_t out_cap, uint32_t* out_len, Shared& sh,
-                    bool report_errors) {
+                    uint8_t* stage, bool report_errors) {
   uint32_t ntok = 0;
-  int st = tokenize(s, n, toks, tok_cap, sh, &ntok);
+  int st = tokenize(s, n, toks, tok_cap, sh, stage, &ntok);
   if (st) return st;
   tpw::sync();
-  st = analyze(s, toks, ntok, tok_cap, sh);
+  st = analyze(s, toks, ntok, tok_cap, sh, stage);
   if (st) return st;
   tpw::sync();
-  return emit(s, toks, ntok, out, out_cap, out_len, sh, report_errors);
+  return emit(s, toks, ntok, out, out_cap, out_len, sh, stage, report_errors);
 }
 
 }  // namespace cftp

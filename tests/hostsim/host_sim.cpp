@@ -209,12 +209,14 @@ extern "C" int cfh_toon_tp(const uint8_t* text, uint32_t n, uint8_t* out, uint32
   memcpy(s, text, n);
   std::vector<cftp::GTok> toks(n / 2 + 64);
   std::vector<cftp::Shared> sh(1);
+  std::vector<uint8_t> stage_buf(cftp::STAGE + 64);
+  uint8_t* stage = stage_buf.data() + ((16 - ((uintptr_t)stage_buf.data() & 15u)) & 15u);
   int status[32];
   uint32_t olen[32];
   for (int i = 0; i < 32; ++i) { status[i] = -1; olen[i] = 0; }
   wemu::run_warp([&](uint32_t lane) {
     uint32_t ol = 0;
-    status[lane] = cftp::toon_unit(s, n, toks.data(), (uint32_t)toks.size(), out, out_cap, &ol, sh[0], report_errors != 0);
+    status[lane] = cftp::toon_unit(s, n, toks.data(), (uint32_t)toks.size(), out, out_cap, &ol, sh[0], stage, report_errors != 0);
     olen[lane] = ol;
   }, order & 1);
   for (int i = 1; i < 32; ++i) if (status[i] != status[0] || olen[i] != olen[0]) return -100 - i;   // the status must be warp-uniform
