@@ -26,7 +26,11 @@
  *          what `orjson.loads` (toon_encoder.py:281), `serde_json::from_slice` (lib.rs:353) and the
  *          string walk `_iter_strings` (harmful_content_detector.py:110-139) each recompute per payload
  *
+ *   cf_run_batch / cf_chain
+ *       -> the whole per-request plugin chain over one uploaded batch (mcpgateway/services/tool_service.py:5866-5872)
+ *
  * Environment (read once per process; defaults are the measured best on B200):
+ *   CF_SCAN_RESERVE_SMS=k   the persistent scan grid leaves k SMs free (a collective running beside it needs somewhere to go)
  *   CF_SCAN_WARPS / CF_SCAN_LB / CF_SCAN_ACC / CF_SCAN_STAGES   scan kernel variant (16 / 64 / 1 / 3)
  *   CF_PAIR_FILTER=0|1   force the byte / pair prefilter instead of choosing per rule set (tests, measurements)
  *
@@ -170,6 +174,44 @@ int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* 
 /* host buffers: upload + encode + download, synchronous */
 int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets,
                  uint32_t n_units, uint8_t* out_stream, uint32_t* out_len, int32_t* status);
+
+/* ---------------- the fused chain: ONE upload, every stage on the device-resident batch, one call ---------------- */
+/* SURVEY.md 8(b) cf_run_batch: what PluginManager.invoke_hook does plugin after plugin over each payload
+ * (mcpgateway/services/tool_service.py:5866-5872) — pattern scans (regex_filter dirty detection + deny + harmful),
+ * regex_filter rewriting of the units a rule matched, toon_encoder JSON->TOON — over ONE uploaded packed stream.
+ * unit_stages[i] (may be NULL = every stage in stage_mask) selects the stages that apply to unit i.
+ * Per unit a 24-byte verdict record; the rewritten / re-encoded texts come back packed in out_bytes with out_offsets[n+1]
+ * (a unit without output has out_offsets[i+1] == out_offsets[i]).
+ *   CF_STAGE_SCAN  verdict.match_bitmap = word 0 of the unit's pattern bitmap (all W words in bitmaps_full when not NULL)
+ *   CF_STAGE_SUB   units with a set CF_PAT_ORDERED bit are rewritten rule after rule (cf_sub_host semantics): CF_V_REWRITTEN.
+ *                  Such a unit is NOT TOON-encoded in the same call (the reference would encode the rewritten text): the
+ *                  caller re-submits it; flags carry CF_V_RESUBMIT when TOON was requested for it.
+ *   CF_STAGE_TOON  verdict.aux = CF_TOON_* status; CF_V_TOON when converted (out = the TOON text)
+ *   CF_STAGE_MASK  request_logging_masking on the same upload (verdict.aux = CF_MASK_* status, out = masked JSON);
+ *                  not combinable with CF_STAGE_TOON in one call (both produce the unit's output). */
+#define CF_STAGE_SCAN 1u
+#define CF_STAGE_SUB 2u
+#define CF_STAGE_MASK 4u
+#define CF_STAGE_TOON 8u
+#define CF_V_REWRITTEN 1u
+#define CF_V_TOON 2u
+#define CF_V_MASKED 4u
+#define CF_V_RESUBMIT 8u
+#define CF_TOON_SKIPPED 8       /* status of a unit whose unit_stages excluded CF_STAGE_TOON */
+typedef struct cf_verdict {
+  uint64_t match_bitmap;  /* bit i = pattern i matched (first 64 patterns) */
+  uint32_t flags;         /* CF_V_* */
+  uint32_t out_len;       /* bytes of this unit in out_bytes */
+  int32_t aux;            /* stage status: CF_TOON_* / CF_MASK_* */
+  uint32_t reserved;
+} cf_verdict;
+int cf_run_batch(cf_ctx* ctx, cf_prog* prog /* may be NULL without SCAN/SUB */, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
+                 const uint64_t* offsets, uint32_t n_units, uint32_t stage_mask, const uint8_t* unit_stages, uint32_t toon_flags, int mask_max_depth,
+                 cf_verdict* verdicts, uint64_t* bitmaps_full, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed);
+/* device-resident, asynchronous on cuda_stream: CF_STAGE_SCAN and/or CF_STAGE_TOON over the batch already uploaded (what
+ * bench.py times with the batch resident in HBM).  d_unit_stages may be NULL. */
+int cf_chain(cf_ctx* ctx, cf_prog* prog, cf_batch* b, uint32_t stage_mask, uint32_t toon_flags, uint64_t* d_bitmaps, const uint8_t* d_unit_stages,
+             uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream);
 
 /* number of kernels launched by this ctx so far (for bench.py's gpu_launches) */
 uint64_t cf_kernel_launches(const cf_ctx* ctx);

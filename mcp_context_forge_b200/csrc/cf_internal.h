@@ -32,7 +32,7 @@ struct cf_ctx {
   void* d_toon_scratch = nullptr;   // DOM node arrays for toon_kernel (grown on demand)
   uint64_t toon_scratch_bytes = 0;
   struct DevBuf { void* p = nullptr; size_t cap = 0; };
-  DevBuf tmp[8];                    // grow-only device scratch of the *_host entry points (no cudaMalloc per call)
+  DevBuf tmp[16];                   // grow-only device scratch of the *_host entry points (no cudaMalloc per call)
   DevBuf d_tok, d_ntok;             // structural index of the current batch (json_index_kernel)
   void* h_stage = nullptr;          // pinned host staging for gathered results
   size_t h_stage_bytes = 0;
@@ -45,6 +45,7 @@ struct cf_ctx {
   uint32_t scan_lane_bytes = 64;
   uint32_t scan_acc = 1;
   uint32_t scan_stages = 3;
+  uint32_t scan_reserve_sms = 0;   // CF_SCAN_RESERVE_SMS: SMs the persistent scan grid leaves free
   uint32_t tile() const { return scan_warps * 32 * scan_lane_bytes; }
   uint32_t box_rows() const { uint32_t rows = tile() / 128, nbox = (rows + 255) / 256; return rows / nbox; }
 };

@@ -747,6 +747,7 @@ int cf_init(int device_ordinal, cf_ctx** out) {
   if (const char* e = getenv("CF_SCAN_ACC")) ctx->scan_acc = (uint32_t)atoi(e);
   if (const char* e = getenv("CF_SCAN_LB")) ctx->scan_lane_bytes = (uint32_t)atoi(e);
   if (const char* e = getenv("CF_SCAN_STAGES")) ctx->scan_stages = (uint32_t)atoi(e);
+  if (const char* e = getenv("CF_SCAN_RESERVE_SMS")) ctx->scan_reserve_sms = (uint32_t)atoi(e);
   if (!scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages)) { ctx->err = "unsupported CF_SCAN_WARPS / CF_SCAN_LB / CF_SCAN_ACC / CF_SCAN_STAGES combination"; return CF_E_BADARG; }
   for (const auto& v : SCAN_VARIANTS)
     CF_CUDA(ctx, cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
@@ -949,6 +950,7 @@ int cf_scan(cf_ctx* ctx, cf_prog* p, cf_batch* b, uint64_t* d_bitmaps, void* cud
   const ScanVariant* sv = scan_variant(ctx->scan_warps, ctx->scan_lane_bytes, ctx->scan_acc, ctx->scan_stages);
   const scan_fn_t fn = p->use_pairs ? pair_variant(ctx->scan_warps, ctx->scan_lane_bytes) : sv->fn;
   uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM
+  if (ctx->scan_reserve_sms && ctx->scan_reserve_sms < grid) grid -= ctx->scan_reserve_sms;
   if (grid > ntiles) grid = ntiles;
   const bool prof = ctx->prof_on && (size_t)ctx->prof_used + 2 <= ctx->prof_ev.size();
   if (prof) cudaEventRecord(ctx->prof_ev[ctx->prof_used], st);
@@ -1013,12 +1015,12 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
   std::vector<uint64_t> rec(2 * (size_t)n_sel);
   do {
 #define SUB_CUDA(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = CF_E_CUDA; break; } }
-    SUB_CUDA(cudaMalloc(&d_scratch, total ? total : 16));
-    SUB_CUDA(cudaMalloc(&d_sel, n_sel * 4));
-    SUB_CUDA(cudaMalloc(&d_soff, n_sel * 8));
-    SUB_CUDA(cudaMalloc(&d_bound, n_sel * 8));
-    SUB_CUDA(cudaMalloc(&d_rec, n_sel * 16));
-    SUB_CUDA(cudaMalloc(&d_ooff, ((size_t)n_sel + 1) * 8));
+    // grow-only scratch of the context: no cudaMalloc / cudaFree per call
+    if ((rc = cf_dev_reserve(ctx, ctx->tmp[8], total ? total : 16)) || (rc = cf_dev_reserve(ctx, ctx->tmp[9], (size_t)n_sel * 4)) ||
+        (rc = cf_dev_reserve(ctx, ctx->tmp[10], (size_t)n_sel * 8)) || (rc = cf_dev_reserve(ctx, ctx->tmp[11], (size_t)n_sel * 8)) ||
+        (rc = cf_dev_reserve(ctx, ctx->tmp[12], (size_t)n_sel * 16)) || (rc = cf_dev_reserve(ctx, ctx->tmp[13], ((size_t)n_sel + 1) * 8))) break;
+    d_scratch = (uint8_t*)ctx->tmp[8].p; d_sel = (uint32_t*)ctx->tmp[9].p; d_soff = (uint64_t*)ctx->tmp[10].p; d_bound = (uint64_t*)ctx->tmp[11].p;
+    d_rec = (uint64_t*)ctx->tmp[12].p; d_ooff = (uint64_t*)ctx->tmp[13].p;
     SUB_CUDA(cudaMemcpy(d_sel, units, n_sel * 4, cudaMemcpyHostToDevice));
     SUB_CUDA(cudaMemcpy(d_soff, soff.data(), n_sel * 8, cudaMemcpyHostToDevice));
     SUB_CUDA(cudaMemcpy(d_bound, bound.data(), n_sel * 8, cudaMemcpyHostToDevice));
@@ -1043,7 +1045,8 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
     if (out_needed) *out_needed = need;
     if (need > out_cap || (!out_bytes && need)) { ctx->err = "output buffer too small"; rc = CF_E_CAPACITY; break; }
     if (need) {
-      SUB_CUDA(cudaMalloc(&d_out, need));
+      if ((rc = cf_dev_reserve(ctx, ctx->tmp[14], need))) break;
+      d_out = (uint8_t*)ctx->tmp[14].p;
       SUB_CUDA(cudaMemcpy(d_ooff, out_offsets, ((size_t)n_sel + 1) * 8, cudaMemcpyHostToDevice));
       sub_compact_kernel<<<n_sel, 256>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, d_sel, d_scratch, d_rec, d_ooff, d_out, n_sel);
       ctx->launches++;
@@ -1052,7 +1055,6 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
     }
 #undef SUB_CUDA
   } while (0);
-  cudaFree(d_scratch); cudaFree(d_sel); cudaFree(d_soff); cudaFree(d_bound); cudaFree(d_rec); cudaFree(d_ooff); cudaFree(d_out);
   return rc;
 }
 

@@ -102,11 +102,12 @@ static const uint32_t TP_WARP_SMEM = (uint32_t)sizeof(cftp::Shared) + cftp::STAG
 static const uint32_t TP_SMEM = TP_WARPS * TP_WARP_SMEM;                              // 110 592 B: two CTAs per SM
 __global__ void __launch_bounds__(TP_WARPS * 32, 2) toon_tp_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ offsets, uint32_t n_units,
                                                                     cftp::GTok* __restrict__ toks, uint8_t* __restrict__ out, uint32_t* __restrict__ out_len,
-                                                                    int32_t* __restrict__ status, uint32_t flags) {
+                                                                    int32_t* __restrict__ status, uint32_t flags, const uint8_t* __restrict__ unit_stages) {
   extern __shared__ __align__(16) uint8_t tp_smem[];
   const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const uint32_t u = blockIdx.x * TP_WARPS + wic;
   if (u >= n_units) return;
+  if (unit_stages && !(unit_stages[u] & CF_STAGE_TOON)) { if (lane == 0) { status[u] = CF_TOON_SKIPPED; out_len[u] = 0; } return; }
   cftp::Shared& sh = *reinterpret_cast<cftp::Shared*>(tp_smem + (size_t)wic * TP_WARP_SMEM);
   uint8_t* stage = tp_smem + (size_t)wic * TP_WARP_SMEM + sizeof(cftp::Shared);
   const uint64_t b = offsets[u];
@@ -187,9 +188,8 @@ int cf_json_index_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* 
   return CF_OK;
 }
 
-int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
-  if (!ctx || !b || !b->n || !d_out || !d_out_len || !d_status) return CF_E_BADARG;
-  cudaStream_t st = (cudaStream_t)cuda_stream;
+static int toon_launch(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, const uint8_t* d_unit_stages,
+                       cudaStream_t st) {
   uint64_t need = (b->nbytes / 2 + 4ull * b->n + 8) * sizeof(cfj::JNode);
   const uint64_t need_tp = (b->nbytes / 2 + (uint64_t)TP_TOK_SLACK * b->n + 8) * sizeof(cftp::GTok);
   if (need_tp > need) need = need_tp;
@@ -207,13 +207,14 @@ int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* 
     static bool smem_set = false;
     if (!smem_set) { CF_CUDA(ctx, cudaFuncSetAttribute(toon_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM)); smem_set = true; }
     toon_tp_kernel<<<(b->n + TP_WARPS - 1) / TP_WARPS, TP_WARPS * 32, TP_SMEM, st>>>(b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cftp::GTok*)ctx->d_toon_scratch,
-                                                                            d_out, d_out_len, d_status, flags);
+                                                                            d_out, d_out_len, d_status, flags, d_unit_stages);
     ctx->launches++;
     CF_CUDA(ctx, cudaGetLastError());
     // the units the fast path handed over: sequential encoder, one unit per warp (they are few)
     if (!(flags & CF_TOON_NO_HANDOVER)) cf_launch_toon_seq(json_blocks(b->n, 1), st, b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfj::JNode*)ctx->d_toon_scratch, d_out, d_out_len, d_status,
                                                      (flags & 1u) | TOON_ONLY_FALLBACK, 1);
   } else {
+    if (d_unit_stages) { ctx->err = "per-unit stage masks need the token-parallel encoder"; return CF_E_BADARG; }
     const uint32_t upw = units_per_warp(ctx, b->n);
     cf_launch_toon_seq(json_blocks(b->n, upw), st, b->d_buf + cf::FRONT_PAD, b->d_offsets, b->n, (cfj::JNode*)ctx->d_toon_scratch, d_out, d_out_len,
                                                        d_status, flags & ~TOON_ONLY_FALLBACK, upw);
@@ -221,6 +222,27 @@ int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* 
   if (prof) { cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], st); ctx->prof_used += 2; }
   ctx->launches++;
   CF_CUDA(ctx, cudaGetLastError());
+  return CF_OK;
+}
+
+int cf_toon(cf_ctx* ctx, cf_batch* b, uint32_t flags, uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
+  if (!ctx || !b || !b->n || !d_out || !d_out_len || !d_status) return CF_E_BADARG;
+  return toon_launch(ctx, b, flags, d_out, d_out_len, d_status, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int cf_chain(cf_ctx* ctx, cf_prog* prog, cf_batch* b, uint32_t stage_mask, uint32_t toon_flags, uint64_t* d_bitmaps, const uint8_t* d_unit_stages,
+             uint8_t* d_out, uint32_t* d_out_len, int32_t* d_status, void* cuda_stream) {
+  if (!ctx || !b || !b->n) return CF_E_BADARG;
+  if (stage_mask & ~(CF_STAGE_SCAN | CF_STAGE_TOON)) { ctx->err = "cf_chain runs CF_STAGE_SCAN / CF_STAGE_TOON; the other stages need cf_run_batch"; return CF_E_BADARG; }
+  int rc;
+  if (stage_mask & CF_STAGE_SCAN) {
+    if (!prog || !d_bitmaps) return CF_E_BADARG;
+    if ((rc = cf_scan(ctx, prog, b, d_bitmaps, cuda_stream))) return rc;
+  }
+  if (stage_mask & CF_STAGE_TOON) {
+    if (!d_out || !d_out_len || !d_status) return CF_E_BADARG;
+    if ((rc = toon_launch(ctx, b, toon_flags, d_out, d_out_len, d_status, d_unit_stages, (cudaStream_t)cuda_stream))) return rc;
+  }
   return CF_OK;
 }
 
@@ -260,11 +282,21 @@ int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream
   return CF_OK;
 }
 
+static int cf_mask_resident(cf_ctx* ctx, cf_batch* b, int max_depth, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, int32_t* status,
+                            uint64_t* out_needed);
 int cf_mask_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
                  int max_depth, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, int32_t* status, uint64_t* out_needed) {
   if (!ctx || !b || !out_offsets || !status) return CF_E_BADARG;
   int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
   if (rc) return rc;
+  return cf_mask_resident(ctx, b, max_depth, out_bytes, out_cap, out_offsets, status, out_needed);
+}
+// masking of the batch already uploaded
+static int cf_mask_resident(cf_ctx* ctx, cf_batch* b, int max_depth, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, int32_t* status,
+                            uint64_t* out_needed) {
+  int rc;
+  const uint64_t stream_bytes = b->nbytes;
+  const uint32_t n_units = b->n;
   const uint64_t nnodes = stream_bytes / 2 + 4ull * n_units + 8;
   const uint64_t need = nnodes * sizeof(cfj::JNode);
   if (need > ctx->toon_scratch_bytes) {
@@ -321,6 +353,135 @@ int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint6
   ctx->launches++;
   CF_CUDA(ctx, cudaGetLastError());
   CF_CUDA(ctx, cudaMemcpy(sensitive, d, n_units, cudaMemcpyDeviceToHost));
+  return CF_OK;
+}
+
+
+// ---- the fused chain with host buffers (include/cfgpu.h): one H2D of the stream, every stage on the resident batch, then
+// verdicts + only the produced texts cross PCIe back
+int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
+                 uint32_t stage_mask, const uint8_t* unit_stages, uint32_t toon_flags, int mask_max_depth, cf_verdict* verdicts, uint64_t* bitmaps_full,
+                 uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed) {
+  if (!ctx || !b || !stream || !offsets || !n_units || !verdicts || !out_offsets) return CF_E_BADARG;
+  if ((stage_mask & (CF_STAGE_SCAN | CF_STAGE_SUB)) && !prog) return CF_E_BADARG;
+  if ((stage_mask & CF_STAGE_TOON) && (stage_mask & CF_STAGE_MASK)) { ctx->err = "CF_STAGE_TOON and CF_STAGE_MASK both produce the unit's output: two calls"; return CF_E_BADARG; }
+  if (stage_mask & CF_STAGE_SUB) stage_mask |= CF_STAGE_SCAN;
+  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  if (rc) return rc;
+  const uint32_t W = prog ? prog->W : 1;
+  std::vector<uint64_t> bm;
+  std::vector<uint32_t> tlen;
+  std::vector<int32_t> tst;
+  uint8_t* d_us = nullptr;
+  if (unit_stages) {
+    if ((rc = cf_dev_reserve(ctx, ctx->tmp[7], n_units))) return rc;
+    d_us = (uint8_t*)ctx->tmp[7].p;
+    CF_CUDA(ctx, cudaMemcpyAsync(d_us, unit_stages, n_units, cudaMemcpyHostToDevice, 0));
+  }
+  // ---- launches, back to back
+  if (stage_mask & CF_STAGE_SCAN) {
+    if ((rc = cf_dev_reserve(ctx, ctx->tmp[6], (size_t)n_units * W * 8))) return rc;
+    if ((rc = cf_scan(ctx, prog, b, (uint64_t*)ctx->tmp[6].p, nullptr))) return rc;
+  }
+  if (stage_mask & CF_STAGE_TOON) {
+    if ((rc = cf_dev_reserve(ctx, ctx->tmp[0], stream_bytes + 16))) return rc;
+    if ((rc = cf_dev_reserve(ctx, ctx->tmp[1], (size_t)n_units * 4))) return rc;
+    if ((rc = cf_dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
+    if ((rc = toon_launch(ctx, b, toon_flags & ~(CF_TOON_PARSE_ONLY | CF_TOON_SEQUENTIAL), (uint8_t*)ctx->tmp[0].p, (uint32_t*)ctx->tmp[1].p, (int32_t*)ctx->tmp[2].p, d_us, 0))) return rc;
+  }
+  // ---- results of the launches
+  for (uint32_t i = 0; i < n_units; ++i) { verdicts[i].match_bitmap = 0; verdicts[i].flags = 0; verdicts[i].out_len = 0; verdicts[i].aux = 0; verdicts[i].reserved = 0; }
+  std::vector<uint32_t> dirty;
+  if (stage_mask & CF_STAGE_SCAN) {
+    bm.resize((size_t)n_units * W);
+    CF_CUDA(ctx, cudaMemcpy(bm.data(), ctx->tmp[6].p, bm.size() * 8, cudaMemcpyDeviceToHost));
+    if (bitmaps_full) memcpy(bitmaps_full, bm.data(), bm.size() * 8);
+    std::vector<uint64_t> rule_mask(W, 0);
+    for (int pi : prog->ordered_pat) rule_mask[(size_t)pi / 64] |= 1ull << (pi % 64);
+    for (uint32_t i = 0; i < n_units; ++i) {
+      verdicts[i].match_bitmap = bm[(size_t)i * W];
+      if ((stage_mask & CF_STAGE_SUB) && (!unit_stages || (unit_stages[i] & CF_STAGE_SUB))) {
+        bool d = false;
+        for (uint32_t w = 0; w < W; ++w) if (bm[(size_t)i * W + w] & rule_mask[w]) { d = true; break; }
+        if (d) dirty.push_back(i);
+      }
+    }
+  }
+  if (stage_mask & CF_STAGE_TOON) {
+    tlen.resize(n_units); tst.resize(n_units);
+    CF_CUDA(ctx, cudaMemcpy(tlen.data(), ctx->tmp[1].p, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+    CF_CUDA(ctx, cudaMemcpy(tst.data(), ctx->tmp[2].p, (size_t)n_units * 4, cudaMemcpyDeviceToHost));
+  }
+  // ---- regex_filter rewriting of the (few) units a rule matched
+  std::vector<uint8_t> sub_bytes;
+  std::vector<uint64_t> sub_off;
+  if (!dirty.empty()) {
+    sub_off.assign(dirty.size() + 1, 0);
+    uint64_t need = 0;
+    sub_bytes.resize(1 << 16);
+    rc = cf_sub_host(ctx, prog, b, dirty.data(), (uint32_t)dirty.size(), sub_bytes.data(), sub_bytes.size(), sub_off.data(), &need);
+    if (rc == CF_E_CAPACITY && need > sub_bytes.size()) {
+      sub_bytes.resize(need);
+      rc = cf_sub_host(ctx, prog, b, dirty.data(), (uint32_t)dirty.size(), sub_bytes.data(), sub_bytes.size(), sub_off.data(), &need);
+    }
+    if (rc) return rc;
+    for (size_t k = 0; k < dirty.size(); ++k) {
+      const uint32_t i = dirty[k];
+      verdicts[i].flags |= CF_V_REWRITTEN;
+      verdicts[i].out_len = (uint32_t)(sub_off[k + 1] - sub_off[k]);
+      if ((stage_mask & CF_STAGE_TOON) && (!unit_stages || (unit_stages[i] & CF_STAGE_TOON))) { verdicts[i].flags |= CF_V_RESUBMIT; tst[i] = CF_TOON_SKIPPED; tlen[i] = 0; }
+    }
+  }
+  if (stage_mask & CF_STAGE_TOON)
+    for (uint32_t i = 0; i < n_units; ++i) {
+      verdicts[i].aux = tst[i];
+      if (tst[i] == CF_TOON_CONVERTED && !(verdicts[i].flags & CF_V_REWRITTEN)) { verdicts[i].flags |= CF_V_TOON; verdicts[i].out_len = tlen[i]; }
+    }
+  // ---- masking on the same upload (sequential kernel; its own gather)
+  if (stage_mask & CF_STAGE_MASK) {
+    std::vector<int32_t> mst(n_units);
+    std::vector<uint64_t> moff((size_t)n_units + 1);
+    uint64_t need = 0;
+    rc = cf_mask_resident(ctx, b, mask_max_depth, out_bytes, out_cap, moff.data(), mst.data(), &need);
+    if (out_needed) *out_needed = need;
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n_units; ++i) {
+      out_offsets[i] = moff[i];
+      verdicts[i].aux = mst[i];
+      if (mst[i] == CF_MASK_OK) { verdicts[i].flags |= CF_V_MASKED; verdicts[i].out_len = (uint32_t)(moff[i + 1] - moff[i]); }
+    }
+    out_offsets[n_units] = moff[n_units];
+    return CF_OK;
+  }
+  // ---- pack the outputs: TOON texts gathered on the device (one D2H), rewritten texts from the substitution call
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_units; ++i) { out_offsets[i] = total; total += verdicts[i].out_len; }
+  out_offsets[n_units] = total;
+  if (out_needed) *out_needed = total;
+  if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; return CF_E_CAPACITY; }
+  if (stage_mask & CF_STAGE_TOON) {
+    uint64_t ttotal = 0;
+    std::vector<uint64_t> ooff((size_t)n_units + 1);
+    std::vector<uint32_t> glen(n_units);
+    for (uint32_t i = 0; i < n_units; ++i) { ooff[i] = ttotal; glen[i] = (verdicts[i].flags & CF_V_TOON) ? verdicts[i].out_len : 0u; ttotal += glen[i]; }
+    ooff[n_units] = ttotal;
+    if (ttotal) {
+      if ((rc = cf_dev_reserve(ctx, ctx->tmp[3], ((size_t)n_units + 1) * 8))) return rc;
+      if ((rc = cf_dev_reserve(ctx, ctx->tmp[4], ttotal))) return rc;
+      if ((rc = cf_stage_reserve(ctx, ttotal))) return rc;
+      CF_CUDA(ctx, cudaMemcpy(ctx->tmp[3].p, ooff.data(), ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
+      CF_CUDA(ctx, cudaMemcpy(ctx->tmp[1].p, glen.data(), (size_t)n_units * 4, cudaMemcpyHostToDevice));
+      compact_kernel<<<n_units, 128>>>((const uint8_t*)ctx->tmp[0].p, 1, 0, b->d_offsets, (const uint32_t*)ctx->tmp[1].p, (const uint64_t*)ctx->tmp[3].p, (uint8_t*)ctx->tmp[4].p, n_units);
+      ctx->launches++;
+      CF_CUDA(ctx, cudaGetLastError());
+      CF_CUDA(ctx, cudaMemcpy(ctx->h_stage, ctx->tmp[4].p, ttotal, cudaMemcpyDeviceToHost));
+      for (uint32_t i = 0; i < n_units; ++i) if (glen[i]) memcpy(out_bytes + out_offsets[i], (const uint8_t*)ctx->h_stage + ooff[i], glen[i]);
+    }
+  }
+  for (size_t k = 0; k < dirty.size(); ++k) {
+    const uint32_t i = dirty[k];
+    if (verdicts[i].out_len) memcpy(out_bytes + out_offsets[i], sub_bytes.data() + sub_off[k], verdicts[i].out_len);
+  }
   return CF_OK;
 }
 

@@ -76,6 +76,7 @@ struct Shared {
   uint32_t row0_idx[MAXD];             // arrays: 1 + token index of the first element when it is an object
   uint32_t row0_n[MAXD];               // arrays: member count of that first object once it closed
   uint32_t kh[KH_CAP];                 // key hashes of the open objects (stack)
+  uint32_t open_w[MAXD];               // analyze: the opener's token word (its separator bits survive the patch)
 };
 enum : uint32_t {
   C_OBJ = 1,
@@ -664,6 +665,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
   const uint32_t Km = tpw::ballot(act && kind == K_KEY), Vm = tpw::ballot(isV);
   uint32_t prevK = tpw::shfl_up(kind == K_KEY ? 1u : 0u, 1);
   if (l == 0) prevK = st.last_was_key;
+  const uint32_t hash = (act && kind == K_KEY) ? fnv1a(s + pos, len) : 0u;   // every key of the batch at once (the walk below is serial)
   uint32_t sp = st.sp, root_cnt = st.root_cnt;
   bool ubad = false, uunsup = false;
   uint32_t ufb = 0;                  // warp-uniform verdicts of the walk
@@ -696,8 +698,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
           // duplicate-key screen on the hashes (a repeated hash, real duplicate or not, goes to the sequential encoder)
           const uint32_t kb = sh.khbase[top];
           const bool mine = inrun && kind == K_KEY;
-          uint32_t hash = 0;
-          if (mine) { hash = fnv1a(s + pos, len); if (kb + ord >= KH_CAP) fb = FB_KH_CAP; else sh.kh[kb + ord] = hash; }
+          if (mine) { if (kb + ord >= KH_CAP) fb = FB_KH_CAP; else sh.kh[kb + ord] = hash; }
           tpw::sync();
           if (mine && kb + ord < KH_CAP) for (uint32_t j = kb; j < kb + ord; ++j) if (sh.kh[j] == hash) { fb = FB_DUP_HASH; break; }
           // table detection: the keys of every later row against the first row's, position by position
@@ -751,6 +752,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
       if (sp >= MAXD) { uunsup = true; break; }
       if (l == 0) {
         sh.open_idx[sp] = eidx; sh.cnt[sp] = 0; sh.khbase[sp] = newkb < KH_CAP ? newkb : KH_CAP;
+        sh.open_w[sp] = gt_make(ek, 0, ecomma, ecolon, 0);
         sh.cfl[sp] = ek == K_OPEN_OBJ ? (C_OBJ | C_ALIGNED | C_VALS_SIMPLE) : (C_ALL_SIMPLE | C_ALL_OBJ | C_KEYSET_OK | C_ROWS_SIMPLE);
         sh.row0_idx[sp] = 0; sh.row0_n[sp] = UNSET;
       }
@@ -793,7 +795,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
           }
         }
       }
-      if (l == 0 && oi < tok_cap) toks[oi].w = gt_patch(toks[oi].w, pk, pf, nn & GT_MAXLEN);
+      if (l == 0 && oi < tok_cap) toks[oi].w = gt_patch(sh.open_w[top], pk, pf, nn & GT_MAXLEN);
       --sp;
       tpw::sync();
     }

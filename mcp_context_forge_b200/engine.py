@@ -228,7 +228,40 @@ def sub_host(prog: Program, batch: Batch, unit_indices: Sequence[int]) -> List[b
     return [raw[int(offs[i]):int(offs[i + 1])] for i in range(n)]
 
 
-TOON_CONVERTED, TOON_NOT_SMALLER, TOON_NOT_JSON, TOON_VALUE_ERROR, TOON_ATTR_ERROR, TOON_UNSUPPORTED = 0, 1, 2, 3, 4, 6
+TOON_CONVERTED, TOON_NOT_SMALLER, TOON_NOT_JSON, TOON_VALUE_ERROR, TOON_ATTR_ERROR, TOON_UNSUPPORTED, TOON_SKIPPED = 0, 1, 2, 3, 4, 6, 8
+
+VERDICT_DTYPE = np.dtype([("match_bitmap", "<u8"), ("flags", "<u4"), ("out_len", "<u4"), ("aux", "<i4"), ("reserved", "<u4")])   # cf_verdict, 24 bytes
+
+
+def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray, stage_mask: int, unit_stages: Optional[np.ndarray] = None,
+              toon_flags: int = 0, mask_max_depth: int = 10, want_full_bitmaps: bool = False):
+    """cf_run_batch: ONE upload of the packed stream, every requested stage on the resident batch, verdicts + only the produced
+    texts back.  Returns (verdicts[VERDICT_DTYPE], out uint8[], out_offsets uint64[n+1], full bitmaps or None)."""
+    ctx = batch.ctx
+    n = len(offsets) - 1
+    nbytes = int(offsets[-1])
+    verdicts = np.zeros(n, dtype=VERDICT_DTYPE)
+    out_offs = np.zeros(n + 1, dtype=np.uint64)
+    W = prog.words if prog is not None else 1
+    full = np.zeros(n * W, dtype=np.uint64) if want_full_bitmaps else None
+    need = c_uint64(0)
+    cap = max(nbytes, 1 << 12)
+    sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+    us = None
+    if unit_stages is not None:
+        us = np.ascontiguousarray(unit_stages, dtype=np.uint8)
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        with ctx.lock:
+            rc = ctx.lib.cf_run_batch(ctx.h, prog.h if prog is not None else None, batch.h, sp, nbytes, offsets.ctypes.data, n, stage_mask,
+                                      us.ctypes.data if us is not None else None, toon_flags, mask_max_depth, verdicts.ctypes.data,
+                                      full.ctypes.data if full is not None else None, out.ctypes.data, cap, out_offs.ctypes.data, byref(need))
+        if rc == N.CF_E_CAPACITY and need.value > cap:
+            cap = int(need.value)
+            continue
+        ctx.check(rc, "cf_run_batch")
+        break
+    return verdicts, out, out_offs, full
 
 
 def toon_host(batch: Batch, stream, offsets: np.ndarray, report_errors: bool = True):

@@ -32,6 +32,32 @@ class DenyListPlugin(Plugin):
             self._prog.compile_host()
         self._batcher: GpuBatcher | None = None
 
+    # ---- chain protocol (mcp_context_forge_b200.manager.BatchedPluginManager)
+    CHAIN_HOOKS = ("prompt_pre_fetch",)
+
+    def chain_register(self, prog: engine.Program) -> bool:
+        self._chain_mask = 0
+        for w in self._deny_list:
+            self._chain_mask |= 1 << prog.add_literal(w)
+        return True
+
+    def chain_stage(self) -> int:
+        return 1      # CF_STAGE_SCAN
+
+    def chain_units(self, hook: str, payload):
+        return [v for v in payload.args.values() if isinstance(v, str)] if payload.args else []
+
+    def chain_finish(self, hook: str, payload, units, results) -> PromptPrehookResult:
+        if payload.args and self._deny_list:
+            it = iter(results)
+            for key, value in payload.args.items():
+                hit = (next(it).bitmap & self._chain_mask) != 0 if isinstance(value, str) else any(word in value for word in self._deny_list)
+                if hit:
+                    violation = PluginViolation(reason="Prompt not allowed", description="A deny word was found in the prompt", code="deny", details={})
+                    logger.warning(f"Deny word detected in prompt argument '{key}'")
+                    return PromptPrehookResult(modified_payload=payload, violation=violation, continue_processing=False)
+        return PromptPrehookResult(modified_payload=payload)
+
     async def prompt_pre_fetch(self, payload: PromptPrehookPayload, context: PluginContext) -> PromptPrehookResult:
         if payload.args and self._prog is not None:
             keys = list(payload.args)

@@ -70,6 +70,38 @@ class HarmfulContentDetectorPlugin(Plugin):
         self._prog.compile_host()
         self._batcher: GpuBatcher | None = None
 
+    # ---- chain protocol (mcp_context_forge_b200.manager.BatchedPluginManager)
+    CHAIN_HOOKS = ("prompt_pre_fetch", "tool_post_invoke")
+
+    def chain_register(self, prog: engine.Program) -> bool:
+        self._chain_bits = [prog.add_search(p, re.IGNORECASE) for _, p in self._bits]
+        self._chain_mask = 0
+        for b in self._chain_bits:
+            self._chain_mask |= 1 << b
+        return True
+
+    def chain_stage(self) -> int:
+        return 1      # CF_STAGE_SCAN
+
+    def chain_units(self, hook: str, payload: Any):
+        if hook == "prompt_pre_fetch":
+            return [s for _, s in _iter_strings(payload.args or {})]
+        text = payload.result
+        if isinstance(text, (dict, list)):
+            return [s for _, s in _iter_strings(text)]
+        return [text] if isinstance(text, str) else []
+
+    def chain_finish(self, hook: str, payload: Any, units: List[str], results: List[Any]):
+        findings: List[Tuple[str, str]] = []
+        mask = self._chain_mask
+        for r in results:
+            bm = r.bitmap & mask
+            if bm:
+                for i, sb in enumerate(self._chain_bits):
+                    if (bm >> sb) & 1:
+                        findings.append(self._bits[i])
+        return self._result(PromptPrehookResult if hook == "prompt_pre_fetch" else ToolPostInvokeResult, findings)
+
     def _gpu(self) -> GpuBatcher:
         if self._batcher is None:
             self._batcher = GpuBatcher.get()

@@ -37,7 +37,13 @@ def literal_replacement(template: str, pattern: "re.Pattern[str]") -> str:
     (escape processing by sre's own template parser).  Group references need capture positions,
     which the DFA engine does not produce -> UnsupportedPattern."""
     parts = _sre_parser.parse_template(template, pattern)
-    if any(not isinstance(p, str) for p in parts):
+    if isinstance(parts, tuple):
+        # Python 3.11 (the reference supports >= 3.11): (groups, literals) with None where a group goes
+        groups, literals = parts
+        if groups:
+            raise UnsupportedPattern(f"replacement template {template!r} references groups")
+        return "".join(x for x in literals if x is not None)
+    if any(not isinstance(p, str) for p in parts):                    # Python 3.12+: flat [str | group index, ...]
         raise UnsupportedPattern(f"replacement template {template!r} references groups")
     return "".join(parts)
 
@@ -59,6 +65,54 @@ class SearchReplacePlugin(Plugin):
         if self._rule_mask:
             self._prog.compile_host()
         self._batcher: Optional[GpuBatcher] = None
+
+    # ---- chain protocol (mcp_context_forge_b200.manager.BatchedPluginManager): the whole chain of a wave of requests in ONE launch
+    CHAIN_HOOKS = ("prompt_pre_fetch", "tool_pre_invoke", "tool_post_invoke")
+
+    def chain_register(self, prog: engine.Program) -> bool:
+        """Add this plugin's rules to the chain's shared program (rule order = config order).  One regex_filter per chain:
+        cf_sub applies every ordered rule of the program."""
+        if getattr(prog, "_has_ordered_owner", None) not in (None, self):
+            return False
+        prog._has_ordered_owner = self
+        self._chain_mask = 0
+        for word in self._srconfig.words:
+            try:
+                compiled = re.compile(word.search)
+            except re.error:
+                continue
+            self._chain_mask |= 1 << prog.add_sub(word.search, 0, literal_replacement(word.replace, compiled))
+        return True
+
+    def chain_stage(self) -> int:
+        return 3      # CF_STAGE_SCAN | CF_STAGE_SUB
+
+    def chain_units(self, hook: str, payload: Any) -> Optional[List[str]]:
+        if hook == "tool_post_invoke":
+            r = payload.result
+            if r and isinstance(r, dict):
+                return [v for v in r.values() if isinstance(v, str)]
+            if r and isinstance(r, str):
+                return [r]
+            return []
+        if hook in ("prompt_pre_fetch", "tool_pre_invoke"):
+            return [v for v in payload.args.values() if isinstance(v, str)] if payload.args else []
+        return None
+
+    def chain_finish(self, hook: str, payload: Any, units: List[str], results: List[Any]) -> Any:
+        new = [u if r.rewritten is None else r.rewritten for u, r in zip(units, results)]
+        if hook == "tool_post_invoke":
+            r = payload.result
+            if r and isinstance(r, dict):
+                it = iter(new)
+                payload = payload.model_copy(update={"result": {k: (next(it) if isinstance(v, str) else v) for k, v in r.items()}})
+            elif r and isinstance(r, str):
+                payload = payload.model_copy(update={"result": new[0]})
+            return ToolPostInvokeResult(modified_payload=payload)
+        if payload.args:
+            it = iter(new)
+            payload = payload.model_copy(update={"args": {k: (next(it) if isinstance(v, str) else v) for k, v in payload.args.items()}})
+        return (PromptPrehookResult if hook == "prompt_pre_fetch" else ToolPreInvokeResult)(modified_payload=payload)
 
     async def _apply(self, values: List[str]) -> List[str]:
         if not self._rule_mask or not values:

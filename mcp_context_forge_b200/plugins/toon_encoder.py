@@ -35,6 +35,7 @@ class ToonEncoderPlugin(Plugin):
         self._items_attempted = 0
         self._items_converted = 0
         self._total_bytes_saved = 0
+        self._items_unsupported = 0
         self._batcher: Optional[GpuBatcher] = None
 
     def _should_process_tool(self, tool_name: str) -> bool:
@@ -72,6 +73,41 @@ class ToonEncoderPlugin(Plugin):
                 new_item["annotations"]["format"] = "toon"
         return new_item
 
+    # ---- chain protocol (mcp_context_forge_b200.manager.BatchedPluginManager)
+    CHAIN_HOOKS = ("tool_post_invoke",)
+
+    def chain_register(self, prog) -> bool:
+        return True
+
+    def chain_stage(self) -> int:
+        return 8      # CF_STAGE_TOON
+
+    def chain_toon_flags(self) -> int:
+        return 0 if self._skip_on_error else 1      # CF_TOON_REPORT_ERRORS
+
+    def _content(self, payload: ToolPostInvokePayload):
+        if not self._should_process_tool(payload.name) or not isinstance(payload.result, dict):
+            return None
+        content = payload.result.get("content", [])
+        return content if content and isinstance(content, list) else None
+
+    def chain_units(self, hook: str, payload: ToolPostInvokePayload):
+        content = self._content(payload)
+        if content is None:
+            return []
+        return [item["text"] for item in content if self._eligible(item) is not None]
+
+    def chain_finish(self, hook: str, payload: ToolPostInvokePayload, units, results) -> ToolPostInvokeResult:
+        start_time = time.monotonic()
+        content = self._content(payload)
+        if content is None:
+            return ToolPostInvokeResult(continue_processing=True)
+        self._tools_processed += 1
+        raws = [self._eligible(item) for item in content]
+        it = iter(results)
+        outcomes = {i: (r.toon_status, r.toon_text) for i, raw in enumerate(raws) if raw is not None for r in (next(it),)}
+        return self._finish(payload, content, raws, outcomes, start_time)
+
     async def tool_post_invoke(self, payload: ToolPostInvokePayload, _context: PluginContext) -> ToolPostInvokeResult:
         start_time = time.monotonic()
         tool_name = payload.name
@@ -93,6 +129,12 @@ class ToonEncoderPlugin(Plugin):
                 self._batcher = GpuBatcher.get()
             for i, oc in zip(idx, await self._batcher.toon([raws[i] for i in idx], report_errors=not self._skip_on_error)):
                 outcomes[i] = oc
+        return self._finish(payload, content, raws, outcomes, start_time)
+
+    def _finish(self, payload: ToolPostInvokePayload, content, raws, outcomes, start_time) -> ToolPostInvokeResult:
+        """Everything after the per-item conversion (reference :285-326, :170-219): identical for the per-plugin and the chain path."""
+        tool_name = payload.name
+        result = payload.result
 
         new_content = []
         modified = False
@@ -121,8 +163,11 @@ class ToonEncoderPlugin(Plugin):
                 new_content.append(item)
             elif status == engine.TOON_NOT_SMALLER:
                 new_content.append(item)
-            else:  # TOON_UNSUPPORTED: outside the device limits — never guess, never fall back silently
-                raise RuntimeError(f"ToonEncoder(GPU): payload of tool '{tool_name}' exceeds the device encoder's limits (nesting > 64 or number > 3200 bits)")
+            else:  # TOON_UNSUPPORTED: outside the device limits (nesting > 64, number > 3200 bits) — never guessed: the item keeps its JSON,
+                   # loudly (warning + counter), instead of turning a deeply nested tool result into a plugin error
+                self._items_unsupported += 1
+                logger.warning(f"ToonEncoder(GPU): an item of tool '{tool_name}' exceeds the device encoder's limits; left as JSON")
+                new_content.append(item)
 
         if modified:
             self._tools_converted += 1

@@ -125,6 +125,10 @@ def _emit_node(out: List[int], node, flags: int, mode: str, tail: bool) -> None:
         _group, add, delete, sub = av
         _emit_seq(out, sub, _combine_flags(flags, add, delete), mode, tail)
     elif op in (_k.MAX_REPEAT, _k.MIN_REPEAT):
+        # sre ends an unbounded loop on a zero-width iteration; the priority closure of the ordered automaton would go on into
+        # the body's lower-priority branch instead (r'(?:c)+(?:(?:s)*?)+' and friends).  Existence (search) is unaffected.
+        if mode == "sub" and av[1] == _k.MAXREPEAT and av[2].getwidth()[0] == 0:
+            raise UnsupportedPattern("unbounded repeat of a sub-pattern that can match the empty string (substitution mode)")
         mn, mx, sub = av
         out.extend((A_REPEAT, mn, REPEAT_INF if mx == _k.MAXREPEAT else mx, 1 if op is _k.MAX_REPEAT else 0))
         _emit_seq(out, sub, flags, mode, False)

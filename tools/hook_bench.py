@@ -51,6 +51,46 @@ plugin_settings:
 """
 
 
+def latency(manager_cls, cfg, pol, hook, payloads, window_us, rate_per_s, seconds=2.0):
+    """Open-loop arrivals at `rate_per_s` for `seconds`: added latency per request (submit -> result) p50 / p99 in microseconds."""
+    from mcp_context_forge_b200.manager import BatchedPluginManager
+    kw = {"window_us": window_us} if manager_cls is BatchedPluginManager else {}
+    m = manager_cls(cfg, timeout=120, hook_policies=pol, **kw)
+    loop = asyncio.new_event_loop()
+    loop.run_until_complete(m.initialize())
+    gc = fw.GlobalContext(request_id="lat")
+    lats = []
+
+    async def one(p):
+        t0 = time.perf_counter()
+        await m.invoke_hook(hook, p, gc)
+        lats.append(time.perf_counter() - t0)
+
+    async def drive():
+        await asyncio.gather(*[one(p) for p in payloads[:64]])       # warm-up
+        lats.clear()
+        tasks = []
+        t0 = time.perf_counter()
+        i = 0
+        while True:
+            now = time.perf_counter() - t0
+            if now >= seconds:
+                break
+            due = int(now * rate_per_s)
+            while i < due:
+                tasks.append(asyncio.ensure_future(one(payloads[i % len(payloads)])))
+                i += 1
+            await asyncio.sleep(0)
+        await asyncio.gather(*tasks)
+        return i / (time.perf_counter() - t0)
+
+    achieved = loop.run_until_complete(drive())
+    loop.run_until_complete(m.shutdown())
+    lats.sort()
+    return {"window_us": window_us, "offered_per_s": rate_per_s, "completed_per_s": round(achieved, 1), "p50_us": round(lats[len(lats) // 2] * 1e6, 1),
+            "p99_us": round(lats[int(len(lats) * 0.99)] * 1e6, 1), "requests": len(lats)}
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     with tempfile.TemporaryDirectory() as td:
@@ -119,6 +159,29 @@ def main():
                 ok = (exp is None and txt == post[k - 1].result["content"][0]["text"]) or txt == exp
             out[name]["spot_check_vs_oracle"] = bool(ok)
         loop.run_until_complete(m.shutdown())
+        # ---- the chain-level batched executor (mcp_context_forge_b200.manager): one fused launch per wave
+        from mcp_context_forge_b200.manager import BatchedPluginManager
+        bm = BatchedPluginManager(cfg, timeout=120, hook_policies=pol)
+        loop.run_until_complete(bm.initialize())
+
+        async def bwave(hook, payloads):
+            return await asyncio.gather(*[bm.invoke_hook(hook, p, gc) for p in payloads])
+
+        for name, hook, payloads in (("prompt_pre_fetch 2 KiB (harmful+deny+regex_filter)", "prompt_pre_fetch", pre),
+                                     ("tool_post_invoke 16 KiB JSON (harmful+regex_filter+toon)", "tool_post_invoke", post)):
+            loop.run_until_complete(bwave(hook, payloads))
+            c0, a0, d0, r0 = bm.launch_calls, bm.assemble_s, bm.device_s, bm.replay_s
+            t0 = time.perf_counter()
+            for _ in range(3):
+                res2 = loop.run_until_complete(bwave(hook, payloads))
+            dt = (time.perf_counter() - t0) / 3
+            out[name]["batched_manager"] = {"payloads_per_s": round(n / dt, 1), "ms_per_wave": round(dt * 1e3, 2), "fused_launches_per_wave": (bm.launch_calls - c0) / 3,
+                                            "ms_assemble_python": round((bm.assemble_s - a0) / 3 * 1e3, 2), "ms_pack_upload_kernels_download": round((bm.device_s - d0) / 3 * 1e3, 2),
+                                            "ms_replay_python": round((bm.replay_s - r0) / 3 * 1e3, 2), "slow_path_calls": bm.slow_path_calls}
+        loop.run_until_complete(bm.shutdown())
+        if os.environ.get("HOOK_LATENCY", "1") == "1":
+            out["latency_tool_post_invoke_16KiB"] = [latency(BatchedPluginManager, cfg, pol, "tool_post_invoke", post, w, 4000) for w in (0, 50, 200, 1000)]
+            out["latency_tool_post_invoke_16KiB_per_plugin_coalescer"] = latency(fw.PluginManager, cfg, pol, "tool_post_invoke", post, 0, 4000)
         print(json.dumps(out))
 
 
