@@ -187,6 +187,8 @@ int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream
  *                  Such a unit is NOT TOON-encoded in the same call (the reference would encode the rewritten text): the
  *                  caller re-submits it; flags carry CF_V_RESUBMIT when TOON was requested for it.
  *   CF_STAGE_TOON  verdict.aux = CF_TOON_* status; CF_V_TOON when converted (out = the TOON text)
+ * stream == NULL runs the stages on the batch that is ALREADY resident (uploaded by cf_batch_upload or a previous call): bench.py's
+ * device-resident `value`; offsets must then be the host copy of that batch's offsets.
  *   CF_STAGE_MASK  request_logging_masking on the same upload (verdict.aux = CF_MASK_* status, out = masked JSON);
  *                  not combinable with CF_STAGE_TOON in one call (both produce the unit's output). */
 #define CF_STAGE_SCAN 1u
@@ -220,6 +222,8 @@ uint64_t cf_kernel_launches(const cf_ctx* ctx);
  * recorded on the launching stream; used by bench.py for roofline.achieved */
 int cf_profile_begin(cf_ctx* ctx, uint32_t max_launches); /* 0 disables */
 int cf_profile_collect(cf_ctx* ctx, double* total_ms, uint32_t* n_launches);
+/* same, one duration per recorded launch, in launch order (cf_scan and the TOON stage record one pair each); resets the list */
+int cf_profile_collect_each(cf_ctx* ctx, double* ms, uint32_t cap, uint32_t* n_launches);
 
 /* last scan's device-side counters: [0]=prefilter candidates, [1]=DFA verify steps */
 int cf_scan_counters(cf_ctx* ctx, uint64_t out[2]);

@@ -63,6 +63,7 @@ _SIGS = {
     "cf_scan_counters": (c_int, [c_void_p, c_void_p]),
     "cf_profile_begin": (c_int, [c_void_p, c_uint32]),
     "cf_profile_collect": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint32)]),
+    "cf_profile_collect_each": (c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
 }
 
 _lib = None

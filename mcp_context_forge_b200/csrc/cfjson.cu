@@ -362,11 +362,13 @@ int cf_classify_keys_host(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint6
 int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes, const uint64_t* offsets, uint32_t n_units,
                  uint32_t stage_mask, const uint8_t* unit_stages, uint32_t toon_flags, int mask_max_depth, cf_verdict* verdicts, uint64_t* bitmaps_full,
                  uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed) {
-  if (!ctx || !b || !stream || !offsets || !n_units || !verdicts || !out_offsets) return CF_E_BADARG;
+  if (!ctx || !b || !offsets || !n_units || !verdicts || !out_offsets) return CF_E_BADARG;
   if ((stage_mask & (CF_STAGE_SCAN | CF_STAGE_SUB)) && !prog) return CF_E_BADARG;
   if ((stage_mask & CF_STAGE_TOON) && (stage_mask & CF_STAGE_MASK)) { ctx->err = "CF_STAGE_TOON and CF_STAGE_MASK both produce the unit's output: two calls"; return CF_E_BADARG; }
   if (stage_mask & CF_STAGE_SUB) stage_mask |= CF_STAGE_SCAN;
-  int rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  int rc = CF_OK;
+  if (stream) rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+  else if (b->n != n_units || b->nbytes != stream_bytes) { ctx->err = "resident run: the batch on the device is a different one"; return CF_E_BADARG; }
   if (rc) return rc;
   const uint32_t W = prog ? prog->W : 1;
   std::vector<uint64_t> bm;
@@ -482,6 +484,22 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
     const uint32_t i = dirty[k];
     if (verdicts[i].out_len) memcpy(out_bytes + out_offsets[i], sub_bytes.data() + sub_off[k], verdicts[i].out_len);
   }
+  return CF_OK;
+}
+
+
+int cf_profile_collect_each(cf_ctx* ctx, double* ms, uint32_t cap, uint32_t* n_launches) {
+  if (!ctx || !ms || !n_launches) return CF_E_BADARG;
+  uint32_t n = 0;
+  for (uint32_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    CF_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[i + 1]));
+    float t = 0;
+    CF_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+    if (n < cap) ms[n] = t;
+    ++n;
+  }
+  *n_launches = n;
+  ctx->prof_used = 0;
   return CF_OK;
 }
 

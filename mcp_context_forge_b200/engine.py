@@ -246,7 +246,10 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
     full = np.zeros(n * W, dtype=np.uint64) if want_full_bitmaps else None
     need = c_uint64(0)
     cap = max(nbytes, 1 << 12)
-    sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
+    if stream is None:                                   # resident run: the batch already holds these units
+        sp = None
+    else:
+        sp = stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p)
     us = None
     if unit_stages is not None:
         us = np.ascontiguousarray(unit_stages, dtype=np.uint8)

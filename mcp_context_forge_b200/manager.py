@@ -74,6 +74,7 @@ class BatchedPluginManager(PluginManager):
         self._chains: Dict[str, Optional[_Chain]] = {}
         self._pending: Dict[str, list] = {}
         self._scheduled: Dict[str, bool] = {}
+        self._busy: Dict[str, bool] = {}
         self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="cfgpu-chain")
         self._ctx: Optional[engine.Context] = None
         self._batch: Optional[engine.Batch] = None
@@ -127,17 +128,24 @@ class BatchedPluginManager(PluginManager):
                                     return_exceptions=True)
 
     async def _flush(self, hook: str) -> None:
+        """One wave at a time per hook: requests that arrive while a wave is on the GPU park and form the next wave the moment it
+        returns (the batch size adapts to the load by itself; `window_us` only adds a floor)."""
         self._scheduled[hook] = False
-        waiting = self._pending.get(hook) or []
-        self._pending[hook] = []
-        while waiting:
-            wave, waiting = waiting[: self.max_wave], waiting[self.max_wave:]
-            try:
-                await self._run_wave(hook, wave)
-            except BaseException as exc:  # noqa: BLE001 - a failed launch fails every parked request loudly (no CPU fallback)
-                for *_, fut in wave:
-                    if not fut.done():
-                        fut.set_exception(exc)
+        if self._busy.get(hook):
+            return
+        self._busy[hook] = True
+        try:
+            while self._pending.get(hook):
+                waiting = self._pending[hook]
+                wave, self._pending[hook] = waiting[: self.max_wave], waiting[self.max_wave:]
+                try:
+                    await self._run_wave(hook, wave)
+                except BaseException as exc:  # noqa: BLE001 - a failed launch fails every parked request loudly (no CPU fallback)
+                    for *_, fut in wave:
+                        if not fut.done():
+                            fut.set_exception(exc)
+        finally:
+            self._busy[hook] = False
 
     # ---- one wave
     def _speculate(self, chain: _Chain, wave: list):
@@ -253,7 +261,7 @@ class BatchedPluginManager(PluginManager):
             if ref.conditions and not payload_matches(current, hook, ref.conditions, global_context):
                 continue
             key = global_context.request_id + ref.uuid
-            ctx = (local_contexts or {}).get(key) or PluginContext(global_context=global_context)
+            ctx = (local_contexts or {}).get(key) or PluginContext.model_construct(state={}, global_context=global_context, metadata={})
             contexts[key] = ctx
             try:
                 spec = plan.get(ref.uuid)
@@ -298,4 +306,5 @@ class BatchedPluginManager(PluginManager):
                     return (PluginResult(continue_processing=False, modified_payload=current if changed else None, violation=result.violation, metadata=metadata,
                                          retry_delay_ms=retry_delay_ms), contexts)
                 logger.warning("Plugin %s (%s) reported a violation in %s; continuing", ref.name, mode.value, hook)
-        return (PluginResult(continue_processing=True, modified_payload=current if changed else None, violation=None, metadata=metadata, retry_delay_ms=retry_delay_ms), contexts)
+        return (PluginResult.model_construct(continue_processing=True, modified_payload=current if changed else None, violation=None, metadata=metadata,
+                                             retry_delay_ms=retry_delay_ms), contexts)

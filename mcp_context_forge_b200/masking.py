@@ -139,3 +139,69 @@ def mask_sensitive_headers(headers: Any) -> Dict[Any, Any]:
         else:
             out[k] = v
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# RequestLoggingMiddleware remainder
+# ---------------------------------------------------------------------------------------------------------------------------
+# /root/reference/mcpgateway/middleware/request_logging_middleware.py:83-99
+SENSITIVE_KEYS = ("password", "passphrase", "secret", "token", "api_key", "apikey", "access_token", "refresh_token", "client_secret", "authorization",
+                  "auth_token", "jwt_token", "private_key")
+NON_JSON_MASKED = "<contains sensitive data - masked>"
+_fallback_prog: Optional[engine.Program] = None
+
+
+def _probe_pattern(key: str) -> str:
+    """`key in text.lower()` as a pattern over the ORIGINAL text: every letter matches itself, its capital and whatever other
+    code point `str.lower()` maps to exactly that letter (only U+212A KELVIN SIGN -> 'k'; U+0130 lowers to TWO code points and
+    therefore never produces a bare 'i')."""
+    out = []
+    for c in key:
+        if c.isalpha():
+            out.append("[" + c + c.upper() + ("\u212a" if c == "k" else "") + "]")
+        else:
+            out.append("\\" + c if not c.isalnum() and c != "_" else c)
+    return "".join(out)
+
+
+def non_json_fallback_batch(payloads: Sequence[bytes]) -> List[str]:
+    """The middleware's non-JSON branch (request_logging_middleware.py:661-667) for many request bodies at once:
+    `s = body.decode("utf-8", errors="ignore")`; if any of the 13 SENSITIVE_KEYS occurs in `s.lower()` the body is logged as
+    "<contains sensitive data - masked>", else as `s`.  The 13 probes are ONE fused scan over the packed bodies."""
+    global _fallback_prog
+    if not payloads:
+        return []
+    texts = [bytes(p).decode("utf-8", errors="ignore") for p in payloads]
+    if _fallback_prog is None:
+        prog = engine.Program()
+        for k in SENSITIVE_KEYS:
+            prog.add_search(_probe_pattern(k), 0)
+        _fallback_prog = prog
+    hits = GpuBatcher.get().scan_groups(_fallback_prog, [texts])[0]
+    return [NON_JSON_MASKED if h else t for h, t in zip(hits, texts)]
+
+
+def mask_sensitive_headers_batch(headers_list: Sequence[Any]) -> List[Dict[Any, Any]]:
+    """`mask_sensitive_headers` (lib.rs:318-344) for the header dicts of many requests: every distinct header name of the
+    wave is classified in ONE launch."""
+    for h in headers_list:
+        if not isinstance(h, dict):
+            raise TypeError("headers must be a dict")
+    keys: Dict[str, bool] = {}
+    for h in headers_list:
+        for k in h:
+            keys.setdefault(str(k), False)
+    _classify(keys)
+    out = []
+    for h in headers_list:
+        m = {}
+        for k, v in h.items():
+            ks = str(k)
+            if keys[ks]:
+                m[k] = MASKED_VALUE
+            elif "".join(chr(ord(c) + 32) if "A" <= c <= "Z" else c for c in ks) == "cookie" and isinstance(v, str):
+                m[k] = _mask_cookie_header(v)
+            else:
+                m[k] = v
+        out.append(m)
+    return out

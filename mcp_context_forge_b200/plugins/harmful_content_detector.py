@@ -127,7 +127,8 @@ class HarmfulContentDetectorPlugin(Plugin):
             return cls(continue_processing=False,
                        violation=PluginViolation(reason="Harmful content", description=f"Detected categories: {', '.join(cats)}", code="HARMFUL_CONTENT",
                                                  details={"categories": cats, "findings": findings[:5]}))
-        return cls(metadata={"harmful_categories": cats} if cats else {})
+        return cls(metadata={"harmful_categories": cats}) if cats else cls.model_construct(continue_processing=True, modified_payload=None, violation=None, metadata={},
+                                                                                          retry_delay_ms=0)
 
     async def prompt_pre_fetch(self, payload: PromptPrehookPayload, context: PluginContext) -> PromptPrehookResult:
         """reference :157-181."""

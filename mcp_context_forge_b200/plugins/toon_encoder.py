@@ -50,10 +50,10 @@ class ToonEncoderPlugin(Plugin):
         text = item.get("text", "")
         if item.get("type") != "text" or not isinstance(text, str):
             return None
-        try:
-            raw = text.encode("utf-8")
-        except UnicodeEncodeError:          # the reference's len(text.encode("utf-8")) raises here too
-            raise
+        if text.isascii():                  # len(text.encode("utf-8")) without the copy (the common case)
+            n = len(text)
+            return text if self._min_size_bytes <= n <= self._max_size_bytes else None
+        raw = text.encode("utf-8")          # raises UnicodeEncodeError on lone surrogates, like the reference's len(text.encode("utf-8"))
         if len(raw) < self._min_size_bytes or len(raw) > self._max_size_bytes:
             return None
         return raw

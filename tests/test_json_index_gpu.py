@@ -6,7 +6,7 @@ import pytest
 
 import hostsim_util as hs
 from mcp_context_forge_b200 import engine, synth
-from test_json_index_cpu import EDGE, corpus
+from test_json_index_cpu import EDGE, corpus, py_tokens
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,9 @@ def test_index_matches_host_build(classify):
         exp, exp_unt = hs.json_index(data)
         assert unt == exp_unt, data[:100]
         assert [(int(p) & 0x7FFFFFFF, bool(int(p) >> 31)) for p, _ in toks] == [(p, c) for p, c, _ in exp], data[:100]
+        # ... and DIRECTLY against the independent Python restatement of the token definition (not only the shared header)
+        ptoks, punt = py_tokens(data)
+        assert [(int(p) & 0x7FFFFFFF, bool(int(p) >> 31)) for p, _ in toks] == list(ptoks) and unt == punt, data[:100]
         if classify:
             assert [int(a) for _, a in toks] == [a for _, _, a in exp], data[:100]
 

@@ -110,8 +110,10 @@ def test_batched_chain_equals_sequential_chain(harm_mode, regex_prio):
                 bad = [(i, norm(x), norm(y)) for i, (x, y) in enumerate(zip(a, b)) if norm(x) != norm(y)]
                 assert not bad, (hook, vae, bad[:2])
         # something of everything happened
-        kinds = {norm(x)[0] for x in a}
-        assert bat.slow_path_calls > 0                      # regex_filter rewrote values: the plugins behind it ran their own hook
+        if regex_prio == 50:
+            assert bat.slow_path_calls > 0                  # regex_filter ran first and rewrote values: the plugins behind it ran their own hook
+        else:
+            assert bat.slow_path_calls == 0                 # nothing behind regex_filter reads what it rewrote: every verdict came from the fused launch
         assert bat.slow_path_calls < 6 * 160 * 3
         loop.run_until_complete(seq.shutdown())
         loop.run_until_complete(bat.shutdown())

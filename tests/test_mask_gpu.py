@@ -68,3 +68,31 @@ def test_benchmark_scenario_payload(mod):
     raw = json.dumps(payload).encode()
     assert mod.mask_sensitive_json_bytes(raw, 12) == mask_ref.mask_json_bytes(raw, 12)
     assert mod.mask_sensitive_data(payload, 12) == mask_ref.mask_value(payload, 12)
+
+
+def test_non_json_fallback_and_header_batch():
+    """the middleware's non-JSON branch (13 lowercase substring probes, request_logging_middleware.py:661-667) and
+    the header path for a wave of requests, against the reference's own expressions evaluated in Python."""
+    import random
+
+    from mcp_context_forge_b200 import masking
+
+    rng = random.Random(4)
+    words = ["hello", "TOKEN", "Api_Key", "user=bob", "pass word", "PassPhrase", "refresh_token=1", "tokKen", "toKen", "apİ_key", "secreté", "AUTHORIZATION:",
+             "client-secret", "private_key", "plain text", "x" * 200, "jwt_TOKEN", "Auth_Token"]
+    bodies = []
+    for _ in range(300):
+        b = " ".join(rng.choice(words) for _ in range(rng.randint(0, 6))).encode("utf-8")
+        if rng.random() < 0.2:
+            i = rng.randrange(len(b) + 1)
+            b = b[:i] + rng.choice([b"\xff", b"\xc3", b"\xe2\x84"]) + b[i:]           # invalid UTF-8: errors="ignore" drops it
+        bodies.append(b)
+    bodies += [b"", b"tok\xffen", b"TOK\xc4\xb0EN"]
+    got = masking.non_json_fallback_batch(bodies)
+    for b, g in zip(bodies, got):
+        s = b.decode("utf-8", errors="ignore")
+        exp = "<contains sensitive data - masked>" if any(k in s.lower() for k in masking.SENSITIVE_KEYS) else s
+        assert g == exp, (b, g, exp)
+    assert sum(1 for g in got if g == masking.NON_JSON_MASKED) > 50
+    hs = [{"Content-Type": "json", "Authorization": "Bearer x", "Cookie": "a=1; session_id=9", "X-Api-Key": "k", "X-Token-Count": "3"}, {"cookie": "jwt=1", "Accept": "*/*"}, {}]
+    assert masking.mask_sensitive_headers_batch(hs) == [masking.mask_sensitive_headers(h) for h in hs]

@@ -58,3 +58,27 @@ def test_json_bytes_format():
     for bad in (b'{"a":1,}', b"[01]", b"NaN", b'"\\ud800"', b"\xff", b"[1e400]", b"", b"[" * 200 + b"]" * 200):
         with pytest.raises(ValueError):
             f(bad)
+
+
+def test_serde_json_format_vectors():
+    """Pins the bytes-API formatting (numbers through ryu's shortest round trip + pretty layout, string escapes, sorted keys, duplicate
+    keys) of BOTH the oracle restatement and the code the CUDA kernel runs (host build of csrc/json_mask.h) to published vectors:
+    tests/golden/serde_format.json (provenance inside)."""
+    import hostsim_util as hs
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "serde_format.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    for src, exp in g["numbers"]:
+        doc = f"[{src}]".encode()
+        assert m.mask_json_bytes(doc, 10) == f"[{exp}]".encode(), (src, m.mask_json_bytes(doc, 10))
+        st, out = hs.mask_host(doc, 10)
+        assert st == 0 and out == f"[{exp}]".encode(), (src, st, out)
+    for src in g["errors"]:
+        doc = f"[{src}]".encode()
+        with pytest.raises(ValueError):
+            m.mask_json_bytes(doc, 10)
+        assert hs.mask_host(doc, 10)[0] == 2, src
+    for src, exp in g["strings"] + g["documents"]:
+        assert m.mask_json_bytes(src.encode("utf-8"), 10) == exp.encode("utf-8"), src
+        st, out = hs.mask_host(src.encode("utf-8"), 10)
+        assert st == 0 and out == exp.encode("utf-8"), (src, st, out)
