@@ -461,23 +461,20 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
   out_offsets[n_units] = total;
   if (out_needed) *out_needed = total;
   if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; return CF_E_CAPACITY; }
-  if (stage_mask & CF_STAGE_TOON) {
-    uint64_t ttotal = 0;
-    std::vector<uint64_t> ooff((size_t)n_units + 1);
+  if ((stage_mask & CF_STAGE_TOON) && total) {
+    // gather the TOON texts on the device AT THEIR FINAL OFFSETS (rewritten units leave holes), then ONE D2H straight into out_bytes
     std::vector<uint32_t> glen(n_units);
-    for (uint32_t i = 0; i < n_units; ++i) { ooff[i] = ttotal; glen[i] = (verdicts[i].flags & CF_V_TOON) ? verdicts[i].out_len : 0u; ttotal += glen[i]; }
-    ooff[n_units] = ttotal;
-    if (ttotal) {
+    bool any = false;
+    for (uint32_t i = 0; i < n_units; ++i) { glen[i] = (verdicts[i].flags & CF_V_TOON) ? verdicts[i].out_len : 0u; any = any || glen[i]; }
+    if (any) {
       if ((rc = cf_dev_reserve(ctx, ctx->tmp[3], ((size_t)n_units + 1) * 8))) return rc;
-      if ((rc = cf_dev_reserve(ctx, ctx->tmp[4], ttotal))) return rc;
-      if ((rc = cf_stage_reserve(ctx, ttotal))) return rc;
-      CF_CUDA(ctx, cudaMemcpy(ctx->tmp[3].p, ooff.data(), ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice));
-      CF_CUDA(ctx, cudaMemcpy(ctx->tmp[1].p, glen.data(), (size_t)n_units * 4, cudaMemcpyHostToDevice));
+      if ((rc = cf_dev_reserve(ctx, ctx->tmp[4], total))) return rc;
+      CF_CUDA(ctx, cudaMemcpyAsync(ctx->tmp[3].p, out_offsets, ((size_t)n_units + 1) * 8, cudaMemcpyHostToDevice, 0));
+      CF_CUDA(ctx, cudaMemcpyAsync(ctx->tmp[1].p, glen.data(), (size_t)n_units * 4, cudaMemcpyHostToDevice, 0));
       compact_kernel<<<n_units, 128>>>((const uint8_t*)ctx->tmp[0].p, 1, 0, b->d_offsets, (const uint32_t*)ctx->tmp[1].p, (const uint64_t*)ctx->tmp[3].p, (uint8_t*)ctx->tmp[4].p, n_units);
       ctx->launches++;
       CF_CUDA(ctx, cudaGetLastError());
-      CF_CUDA(ctx, cudaMemcpy(ctx->h_stage, ctx->tmp[4].p, ttotal, cudaMemcpyDeviceToHost));
-      for (uint32_t i = 0; i < n_units; ++i) if (glen[i]) memcpy(out_bytes + out_offsets[i], (const uint8_t*)ctx->h_stage + ooff[i], glen[i]);
+      CF_CUDA(ctx, cudaMemcpy(out_bytes, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
     }
   }
   for (size_t k = 0; k < dirty.size(); ++k) {

@@ -356,6 +356,68 @@ TP_SLOW bool string_slow(const uint8_t* s, uint32_t n, uint32_t pos, uint32_t le
   return cfj::parse_string(s, n, &p, sf, &h) && p == pos + len + 1;
 }
 
+// Strict UTF-8 over s[a .. a+len), the whole warp on one (long) string, lane i <-> byte i of a 32-byte chunk: a byte must be a
+// continuation byte exactly when one of the three bytes before it is a lead that reaches it, leads are C2..F4, and the second
+// byte of E0 / ED / F0 / F4 sequences is range-checked (no overlongs, no surrogates, nothing above U+10FFFF) — what
+// cfj::parse_string checks one code point at a time.  The byte behind the string is its closing quote: a truncated tail fails.
+TP_FN bool warp_utf8_valid(const uint8_t* s, uint32_t a, uint32_t len) {
+  const uint32_t l = tpw::lane();
+  bool bad = false;
+  for (uint32_t base = 0; base <= len; base += 32) {
+    const uint32_t i = base + l;
+    if (i <= len) {
+      const uint32_t p = a + i;
+      const uint32_t b0 = s[p], b1 = i >= 1 ? s[p - 1] : 0u, b2 = i >= 2 ? s[p - 2] : 0u, b3 = i >= 3 ? s[p - 3] : 0u;
+      const bool cont = (b0 & 0xC0u) == 0x80u;
+      const bool must = b1 >= 0xC0u || b2 >= 0xE0u || b3 >= 0xF0u;
+      if (cont != must) bad = true;
+      if (b0 >= 0x80u && !cont && (b0 < 0xC2u || b0 > 0xF4u)) bad = true;
+      if (cont && ((b1 == 0xE0u && b0 < 0xA0u) || (b1 == 0xEDu && b0 > 0x9Fu) || (b1 == 0xF0u && b0 < 0x90u) || (b1 == 0xF4u && b0 > 0x8Fu))) bad = true;
+    }
+  }
+  return !tpw::any(bad);
+}
+TP_FN uint32_t utf8_first_cp(const uint8_t* b) {
+  const uint32_t c = b[0];
+  if (c < 0x80) return c;
+  const uint32_t need = c >= 0xF0 ? 3u : c >= 0xE0 ? 2u : 1u;
+  uint32_t cp = c & (0x3Fu >> need);
+  for (uint32_t k = 1; k <= need; ++k) cp = (cp << 6) | (b[k] & 0x3Fu);
+  return cp;
+}
+static const uint32_t LONG_HI = 96;      // non-ASCII / escaped strings at least this long are validated by the whole warp
+
+// Escapes of a long string s[a .. a+len), whole warp: every unescaped backslash must start one of JSON's two-character escapes
+// (a \uXXXX escape makes the caller take the sequential validator: its code point decides the predicates).
+// Returns a bit set: 1 invalid escape, 2 some \u escape, 4 an escape TOON writes differently (\/ \b \f), 8 \b or \f (a control
+// character toon._quote_string rejects).
+enum : uint32_t { XE_BAD = 1, XE_U = 2, XE_COMPLEX = 4, XE_CTRL = 8 };
+TP_FN uint32_t warp_escapes(const uint8_t* s, uint32_t a, uint32_t len) {
+  const uint32_t l = tpw::lane();
+  uint32_t res = 0, e_in = 0, pend = 0;                 // e_in: the chunk's first byte is escaped; pend: it is an escape's code character
+  for (uint32_t base = 0; base < len; base += 32) {
+    const uint32_t i = base + l;
+    const uint32_t c = i < len ? (uint32_t)s[a + i] : 0u;
+    const uint32_t bs = tpw::ballot(c == '\\');
+    uint32_t e_out;
+    const uint32_t escaped = find_escaped(bs, e_in, &e_out);
+    const uint32_t start = bs & ~escaped;                // backslashes that open an escape
+    const uint32_t code = (start << 1) | pend;            // their code characters
+    if ((code >> l) & 1u) {
+      if (i >= len) res |= XE_BAD;                        // the string ends on a lone backslash (cannot happen: the quote would be escaped)
+      else if (c == 'u') res |= XE_U;
+      else if (c == '/') res |= XE_COMPLEX;
+      else if (c == 'b' || c == 'f') res |= XE_COMPLEX | XE_CTRL;
+      else if (!(c == '"' || c == '\\' || c == 'n' || c == 'r' || c == 't')) res |= XE_BAD;
+    }
+    pend = start >> 31;
+    e_in = e_out;
+  }
+  if (pend) res |= XE_BAD;
+  for (uint32_t d = 16; d; d >>= 1) res |= tpw::shfl(res, (l + d) & 31u);   // OR over the lanes (butterfly by rotation)
+  return res;
+}
+
 // ----------------------------------------------------------------------------------------------------------------------
 // tokenize, classification batch: raw tokens ring[head .. head+m) -> validated GTok toks[ntok ..); la_ncolon = colons in
 // front of the token that follows the batch (a string followed by a colon is a key)
@@ -376,7 +438,7 @@ TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap,
   const uint32_t ncomma = (meta >> RM_NCOMMA_SH) & 3u, ncolon = (meta >> RM_NCOLON_SH) & 3u;
   uint32_t nxt_ncolon = tpw::shfl_down(ncolon, 1);
   if (l + 1 >= m) nxt_ncolon = la_ncolon;
-  bool bad = false, unsup = false;
+  bool bad = false, unsup = false, long_hi = false;
   uint32_t fb = 0, fl = 0;
   const bool isK = act && kind == K_STR && ncolon == 0 && nxt_ncolon >= 1;
   if (act && kind == K_NUM) {                       // scalar run starting at pos
@@ -400,6 +462,7 @@ TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap,
     // only the first / last bytes (and up to five for the reserved words) are looked at on the fast path
     const uint8_t* b = in_window(s, win, wlo, pos, len);
     if (len > GT_MAXLEN) fb = FB_TOO_LONG;
+    else if ((meta & (RM_HI | RM_BS)) && len >= LONG_HI && !(b[0] >= '0' && b[0] <= '9')) long_hi = true;   // whole-warp validation below
     else if ((meta & (RM_BS | RM_HI)) || (len && b[0] >= '0' && b[0] <= '9')) {
       // escapes, non-ASCII or number-like candidates: the sequential validator decides (same function as json_toon.h)
       uint32_t sf = 0;
@@ -419,6 +482,49 @@ TP_FN void tok_batch(const uint8_t* s, uint32_t n, GTok* toks, uint32_t tok_cap,
       } else if (len == 0 || res || (meta & RM_SPECIAL) || b[0] == ' ' || b[len - 1] == ' ') fl |= SF_Q;
     }
     if (isK) kind = K_KEY;
+  }
+  // long non-ASCII strings without escapes: strict UTF-8 by the whole warp, one string after the other; what is left of the
+  // predicates needs the first and the last code point only (no escapes: the text is the bytes; no digit in front: not number-like)
+  for (uint32_t lm = tpw::ballot(long_hi); lm; lm &= lm - 1) {
+    const uint32_t j = tpw::ffs(lm) - 1;
+    const uint32_t jpos = tpw::shfl(pos, j), jlen = tpw::shfl(len, j), jmeta = tpw::shfl(meta, j);
+    const bool ok = !(jmeta & RM_HI) || warp_utf8_valid(s, jpos, jlen);
+    const uint32_t xe = (jmeta & RM_BS) ? warp_escapes(s, jpos, jlen) : 0u;
+    if (l == j) {
+      if (!ok || (xe & XE_BAD)) bad = true;
+      else if (xe & XE_U) {                              // \uXXXX: the decoded code points decide — sequential validator
+        uint32_t sf = 0;
+        if (!string_slow(s, n, pos, len, &sf)) bad = true;
+        else if (isK) fb = FB_KEY_ESCAPE;
+        else {
+          if (sf & cfj::JF_Q) fl |= SF_Q;
+          if (sf & cfj::JF_CTRLERR) fl |= SF_CTRLERR;
+          if (has_complex_escape(s + pos, len)) fl |= SF_ESCX;
+        }
+      } else if (isK) { if (meta & RM_BS) fb = FB_KEY_ESCAPE; }   // (a key with non-ASCII bytes is never a valid unquoted key: fl stays 0)
+      else if (meta & RM_BS) {
+        // two-character escapes only: each decodes to a character that forces quotes (" \ \n \r \t, \b \f) except \/
+        const uint8_t* g = s + pos;
+        uint32_t q = len - 1;
+        while (q && (g[q] & 0xC0u) == 0x80u) --q;
+        bool quoting = (meta & RM_SPECIAL) || (xe & XE_CTRL) != 0;
+        if (!quoting) {                                  // any escape other than \/ ?  (scan by this lane only when still undecided)
+          for (uint32_t i = 0; i + 1 < len; ++i) if (g[i] == '\\') { if (g[i + 1] != '/') { quoting = true; break; } ++i; }
+        }
+        const uint32_t fc = g[0] == '\\' ? (g[1] == '/' ? (uint32_t)'/' : 0u) : utf8_first_cp(g);      // 0: an escape that quotes anyway
+        const bool last_esc = q >= 1 && len >= 2 && ((g[len - 2] == '\\') && true);                     // conservatively handled below
+        uint32_t lc = utf8_first_cp(g + q);
+        (void)last_esc;
+        if (quoting || (fc && cfj::is_pyspace(fc)) || cfj::is_pyspace(lc)) fl |= SF_Q;
+        if (xe & XE_CTRL) fl |= SF_CTRLERR | SF_Q;
+        if (xe & XE_COMPLEX) fl |= SF_ESCX;
+      } else {
+        const uint8_t* g = s + pos;
+        uint32_t q = len - 1;
+        while (q && (g[q] & 0xC0u) == 0x80u) --q;
+        if ((meta & RM_SPECIAL) || cfj::is_pyspace(utf8_first_cp(g)) || cfj::is_pyspace(utf8_first_cp(g + q))) fl |= SF_Q;
+      }
+    }
   }
   if (len > GT_MAXLEN) { if (kind == K_NUM || kind == K_LIT) unsup = true; else if (!fb) fb = FB_TOO_LONG; len = 0; }
   if (st.ntok + m > tok_cap) fb = FB_TOK_CAP;
@@ -670,6 +776,10 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
   bool ubad = false, uunsup = false;
   uint32_t ufb = 0;                  // warp-uniform verdicts of the walk
   uint32_t cur = 0, consumed = m;
+  // The entry on top of the stack lives in (warp-uniform) registers during the walk; shared memory holds the entries below it and
+  // is brought up to date when a container is pushed and at the end of the batch.
+  uint32_t T_oi = 0, T_cnt = 0, T_cfl = 0, T_khb = 0, T_r0i = 0, T_r0n = UNSET, T_ow = 0;
+  if (sp) { const uint32_t k = sp - 1; T_oi = sh.open_idx[k]; T_cnt = sh.cnt[k]; T_cfl = sh.cfl[k]; T_khb = sh.khbase[k]; T_r0i = sh.row0_idx[k]; T_r0n = sh.row0_n[k]; T_ow = sh.open_w[k]; }
   while (true) {
     const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
     const uint32_t run = range_mask(cur, e);
@@ -679,8 +789,8 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
         if (inrun && (kind == K_KEY || ncomma || ncolon || root_cnt + tpw::popc(run & ltm) != 0)) bad = true;
         root_cnt += tpw::popc(run);
       } else {
-        const uint32_t top = sp - 1, tfl = sh.cfl[top], c0 = sh.cnt[top];
-        const bool isobj = (tfl & C_OBJ) != 0;
+        const uint32_t c0 = T_cnt;
+        const bool isobj = (T_cfl & C_OBJ) != 0;
         const uint32_t Vr = Vm & run, Kr = Km & run;
         const uint32_t ord = c0 + tpw::popc(Vr & ltm);
         if (inrun) {
@@ -689,14 +799,11 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
             else if (ncolon != 1 || ncomma != 0 || !prevK) bad = true;
           } else if (kind == K_KEY || ncolon != 0 || ncomma != (ord > 0 ? 1u : 0u)) bad = true;
         }
-        tpw::sync();
-        if (l == 0) {
-          sh.cnt[top] = c0 + tpw::popc(Vr);
-          if (!isobj && Vr) sh.cfl[top] = nondict_element(tfl, sh.row0_idx[top], sh.row0_n[top]);
-        }
+        T_cnt = c0 + tpw::popc(Vr);
+        if (!isobj && Vr) T_cfl = nondict_element(T_cfl, T_r0i, T_r0n);
         if (isobj && Kr) {
           // duplicate-key screen on the hashes (a repeated hash, real duplicate or not, goes to the sequential encoder)
-          const uint32_t kb = sh.khbase[top];
+          const uint32_t kb = T_khb;
           const bool mine = inrun && kind == K_KEY;
           if (mine) { if (kb + ord >= KH_CAP) fb = FB_KH_CAP; else sh.kh[kb + ord] = hash; }
           tpw::sync();
@@ -704,8 +811,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
           // table detection: the keys of every later row against the first row's, position by position
           if (sp >= 2) {
             const uint32_t par = sp - 2, pfl = sh.cfl[par];
-            if (!(pfl & C_OBJ) && (pfl & C_KEYSET_OK) && (pfl & C_ROW0_SIMPLE) && !(pfl & C_ND_SEEN) && sh.row0_n[par] != UNSET &&
-                sh.open_idx[top] + 1 != sh.row0_idx[par]) {
+            if (!(pfl & C_OBJ) && (pfl & C_KEYSET_OK) && (pfl & C_ROW0_SIMPLE) && !(pfl & C_ND_SEEN) && sh.row0_n[par] != UNSET && T_oi + 1 != sh.row0_idx[par]) {
               const uint32_t r0 = sh.row0_idx[par] - 1, rn = sh.row0_n[par];
               bool mism = false, diff = false;
               if (mine) {
@@ -716,92 +822,81 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
                 }
               }
               const bool anym = tpw::any(mism), anyd = tpw::any(diff);
-              if (anym && l == 0) sh.cfl[top] = (sh.cfl[top] & ~C_ALIGNED) | (anyd ? C_DIFFSET : 0u);
+              if (anym) T_cfl = (T_cfl & ~C_ALIGNED) | (anyd ? C_DIFFSET : 0u);
             }
           }
+          tpw::sync();
         }
-        tpw::sync();
       }
     }
     if (e >= m) break;
     // ---- the bracket at lane e
-    const uint32_t ek = tpw::shfl(kind, e), ecomma = tpw::shfl(ncomma, e), ecolon = tpw::shfl(ncolon, e), eprevK = tpw::shfl(prevK, e);
+    const uint32_t ek = tpw::shfl(kind, e), ew = tpw::shfl(t.w, e), eprevK = tpw::shfl(prevK, e);
+    const uint32_t ecomma = gt_nc(ew), ecolon = gt_nk(ew);
     const uint32_t eidx = i + e;
     if (ek <= K_OPEN_ARR) {
       uint32_t newkb = 0;
       if (sp == 0) { if (ecomma || ecolon || root_cnt) ubad = true; ++root_cnt; }
       else {
-        const uint32_t top = sp - 1;
-        uint32_t tfl = sh.cfl[top];
-        const uint32_t ord = sh.cnt[top];
-        const bool isobj = (tfl & C_OBJ) != 0;
-        if (ek == K_OPEN_OBJ && (e > 0 || !force) && table_candidate(sh, top)) { consumed = e; break; }   // a table row: table mode takes it from here
+        const uint32_t ord = T_cnt;
+        const bool isobj = (T_cfl & C_OBJ) != 0;
+        if (ek == K_OPEN_OBJ && (e > 0 || !force) && !isobj && T_cnt > 0 && (T_cfl & C_KEYSET_OK) && (T_cfl & C_ROW0_SIMPLE) && !(T_cfl & C_ND_SEEN) &&
+            T_r0n != UNSET && T_r0n != 0) { consumed = e; break; }   // a table row: table mode takes it from here
         if (isobj) { if (ecolon != 1 || ecomma != 0 || !eprevK) ubad = true; }
         else if (ecolon != 0 || ecomma != (ord > 0 ? 1u : 0u)) ubad = true;
-        tfl &= ~C_ALL_SIMPLE;
-        if (isobj) tfl &= ~C_VALS_SIMPLE;
-        else if (ek == K_OPEN_ARR) tfl = nondict_element(tfl, sh.row0_idx[top], sh.row0_n[top]);
-        newkb = sh.khbase[top] + (isobj ? ord + 1 : 0u);
-        tpw::sync();
-        if (l == 0) {
-          sh.cnt[top] = ord + 1;
-          sh.cfl[top] = tfl;
-          if (!isobj && ord == 0 && ek == K_OPEN_OBJ) sh.row0_idx[top] = eidx + 1;
-        }
+        T_cfl &= ~C_ALL_SIMPLE;
+        if (isobj) T_cfl &= ~C_VALS_SIMPLE;
+        else if (ek == K_OPEN_ARR) T_cfl = nondict_element(T_cfl, T_r0i, T_r0n);
+        newkb = T_khb + (isobj ? ord + 1 : 0u);
+        T_cnt = ord + 1;
+        if (!isobj && ord == 0 && ek == K_OPEN_OBJ) T_r0i = eidx + 1;
       }
       if (sp >= MAXD) { uunsup = true; break; }
-      if (l == 0) {
-        sh.open_idx[sp] = eidx; sh.cnt[sp] = 0; sh.khbase[sp] = newkb < KH_CAP ? newkb : KH_CAP;
-        sh.open_w[sp] = gt_make(ek, 0, ecomma, ecolon, 0);
-        sh.cfl[sp] = ek == K_OPEN_OBJ ? (C_OBJ | C_ALIGNED | C_VALS_SIMPLE) : (C_ALL_SIMPLE | C_ALL_OBJ | C_KEYSET_OK | C_ROWS_SIMPLE);
-        sh.row0_idx[sp] = 0; sh.row0_n[sp] = UNSET;
-      }
+      if (sp && l == 0) { const uint32_t k = sp - 1; sh.open_idx[k] = T_oi; sh.cnt[k] = T_cnt; sh.cfl[k] = T_cfl; sh.khbase[k] = T_khb; sh.row0_idx[k] = T_r0i; sh.row0_n[k] = T_r0n; sh.open_w[k] = T_ow; }
+      T_oi = eidx; T_cnt = 0; T_khb = newkb < KH_CAP ? newkb : KH_CAP;
+      T_cfl = ek == K_OPEN_OBJ ? (C_OBJ | C_ALIGNED | C_VALS_SIMPLE) : (C_ALL_SIMPLE | C_ALL_OBJ | C_KEYSET_OK | C_ROWS_SIMPLE);
+      T_r0i = 0; T_r0n = UNSET; T_ow = gt_make(ek, 0, ecomma, ecolon, 0);
       ++sp;
       tpw::sync();
     } else {
       if (sp == 0) { ubad = true; break; }
-      const uint32_t top = sp - 1, tfl = sh.cfl[top], nn = sh.cnt[top], oi = sh.open_idx[top];
+      const uint32_t tfl = T_cfl, nn = T_cnt, oi = T_oi;
       const bool isobj = (tfl & C_OBJ) != 0;
       if ((ek == K_CLOSE_OBJ) != isobj || ecomma || ecolon) ubad = true;
       if (nn > GT_MAXLEN) ufb = FB_TOO_LONG;
       uint32_t pk, pf;
       if (isobj) { pk = K_OPEN_OBJ; pf = 0; }
       else {
-        const bool col = (tfl & C_ALL_OBJ) && (tfl & C_KEYSET_OK) && (tfl & C_ROWS_SIMPLE) && sh.row0_n[top] != 0;
+        const bool col = (tfl & C_ALL_OBJ) && (tfl & C_KEYSET_OK) && (tfl & C_ROWS_SIMPLE) && T_r0n != 0;
         const uint32_t mode = nn == 0 ? AM_EMPTY : col ? AM_COLUMNAR : (tfl & C_ALL_SIMPLE) ? AM_INLINE : AM_ITEMS;
         if (col && (tfl & C_PERMUTED)) ufb = FB_ROW_ORDER;          // the rows need a gather: sequential encoder
         uint32_t xf = 0;
-        if (sh.row0_idx[top] && !(tfl & C_ALL_OBJ)) xf = (tfl & C_CRASH) ? AF_CRASH : (!(tfl & C_ROW0_SIMPLE) && sh.row0_n[top] != 0) ? AF_MIXED : 0u;
+        if (T_r0i && !(tfl & C_ALL_OBJ)) xf = (tfl & C_CRASH) ? AF_CRASH : (!(tfl & C_ROW0_SIMPLE) && T_r0n != 0) ? AF_MIXED : 0u;
         pk = K_OPEN_ARR; pf = mode | xf;
       }
-      if (sp >= 2 && isobj) {
-        const uint32_t par = sp - 2;
-        uint32_t pfl = sh.cfl[par];
-        if (!(pfl & C_OBJ)) {
-          if (!(tfl & C_VALS_SIMPLE)) pfl &= ~C_ROWS_SIMPLE;
-          if (oi + 1 == sh.row0_idx[par]) {                          // the first row
-            if (tfl & C_VALS_SIMPLE) pfl |= C_ROW0_SIMPLE;
-            tpw::sync();
-            if (l == 0) { sh.row0_n[par] = nn; sh.cfl[par] = pfl; }
-          } else {
-            const uint32_t rn = sh.row0_n[par];
-            if (rn != UNSET && (pfl & C_KEYSET_OK) && !(pfl & C_ND_SEEN)) {
-              // same key set?  (no duplicate keys here — those went to the sequential encoder — so equal counts + every key found = equal sets)
-              if (nn != rn || (tfl & C_DIFFSET)) pfl &= ~C_KEYSET_OK;
-              else if (!(tfl & C_ALIGNED)) pfl |= C_PERMUTED;
-            }
-            tpw::sync();
-            if (l == 0) sh.cfl[par] = pfl;
+      if (l == 0 && oi < tok_cap) toks[oi].w = gt_patch(T_ow, pk, pf, nn & GT_MAXLEN);
+      --sp;
+      if (sp) {                                                      // the parent comes back into the registers
+        const uint32_t k = sp - 1;
+        T_oi = sh.open_idx[k]; T_cnt = sh.cnt[k]; T_cfl = sh.cfl[k]; T_khb = sh.khbase[k]; T_r0i = sh.row0_idx[k]; T_r0n = sh.row0_n[k]; T_ow = sh.open_w[k];
+        if (isobj && !(T_cfl & C_OBJ)) {                             // an object element of an array closed: table bookkeeping
+          if (!(tfl & C_VALS_SIMPLE)) T_cfl &= ~C_ROWS_SIMPLE;
+          if (oi + 1 == T_r0i) {                                     // the first row
+            if (tfl & C_VALS_SIMPLE) T_cfl |= C_ROW0_SIMPLE;
+            T_r0n = nn;
+          } else if (T_r0n != UNSET && (T_cfl & C_KEYSET_OK) && !(T_cfl & C_ND_SEEN)) {
+            // same key set?  (no duplicate keys here — those went to the sequential encoder — so equal counts + every key found = equal sets)
+            if (nn != T_r0n || (tfl & C_DIFFSET)) T_cfl &= ~C_KEYSET_OK;
+            else if (!(tfl & C_ALIGNED)) T_cfl |= C_PERMUTED;
           }
         }
       }
-      if (l == 0 && oi < tok_cap) toks[oi].w = gt_patch(sh.open_w[top], pk, pf, nn & GT_MAXLEN);
-      --sp;
-      tpw::sync();
     }
     cur = e + 1;
     evm &= evm - 1;
   }
+  if (sp && l == 0) { const uint32_t k = sp - 1; sh.open_idx[k] = T_oi; sh.cnt[k] = T_cnt; sh.cfl[k] = T_cfl; sh.khbase[k] = T_khb; sh.row0_idx[k] = T_r0i; sh.row0_n[k] = T_r0n; sh.open_w[k] = T_ow; }
+  tpw::sync();
   st.sp = sp; st.root_cnt = root_cnt;
   if (consumed) st.last_was_key = tpw::shfl(kind == K_KEY ? 1u : 0u, consumed - 1);
   // verdicts of lanes past the stop point do not count (their tokens are walked again)
@@ -947,6 +1042,9 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
   const uint32_t Vm = tpw::ballot(isV);
   uint32_t cur = 0, consumed = m;
   st.col_rows = 0;
+  // the frame on top of the stack lives in (warp-uniform) registers during the walk
+  uint32_t F_mode = M_ROOT, F_pre = 0, F_ind = 0, F_cnt = 0;
+  if (sp) { const uint32_t k = sp - 1; F_mode = f_mode[k]; F_pre = f_pre[k]; F_ind = f_ind[k]; F_cnt = f_cnt[k]; }
   while (true) {
     const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
     const uint32_t run = range_mask(cur, e);
@@ -954,7 +1052,7 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
       const bool inrun = (run >> l) & 1u;
       if (sp == 0) { if (inrun) pc.body = B_SPAN; }
       else {
-        const uint32_t top = sp - 1, mode = f_mode[top], pre = f_pre[top], ind = f_ind[top], c0 = f_cnt[top];
+        const uint32_t mode = F_mode, pre = F_pre, ind = F_ind, c0 = F_cnt;
         const uint32_t Vr = Vm & run;
         const uint32_t ord = c0 + tpw::popc(Vr & ltm);
         if (inrun) {
@@ -972,17 +1070,16 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
             else if (mode == M_ARR_ITEMS) { pc.nl = 1; pc.spaces = pre + 2 * (ind + 1); pc.l1 = lit2('-', ' '); pc.l1n = 2; }
           }
         }
-        tpw::sync();
-        if (l == 0) f_cnt[top] = c0 + tpw::popc(Vr);
-        tpw::sync();
+        F_cnt = c0 + tpw::popc(Vr);
       }
     }
     if (e >= m) break;
     const uint32_t ek = tpw::shfl(kind, e);
     if (ek <= K_OPEN_ARR) {
-      const uint32_t en = tpw::shfl(len, e), efl = tpw::shfl(fl, e), enk = tpw::shfl(nk, e);
+      const uint32_t ew = tpw::shfl(t.w, e), enk = tpw::shfl(nk, e);
+      const uint32_t en = gt_len(ew), efl = gt_flags(ew);
       uint32_t pmode = M_ROOT, pre = 0, ind = 0, ord = 0;
-      if (sp > 0) { const uint32_t top = sp - 1; pmode = f_mode[top]; pre = f_pre[top]; ind = f_ind[top]; ord = f_cnt[top]; tpw::sync(); if (l == 0) f_cnt[top] = ord + 1; }
+      if (sp > 0) { pmode = F_mode; pre = F_pre; ind = F_ind; ord = F_cnt; F_cnt = ord + 1; }
       uint32_t nmode = M_DEAD, npre = 0, nind = 0;
       Piece q; q.l0 = 0; q.nl = 0; q.spaces = 0; q.l1 = 0; q.l1n = 0; q.body = B_NONE; q.tail = T_COLON;
       uint32_t eerr = 0;
@@ -1026,8 +1123,8 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
       }
       if (l == e) { pc = q; err = eerr; }
       if (sp >= MAXD) { st.status = TS_UNSUPPORTED; break; }
-      tpw::sync();
-      if (l == 0) { f_mode[sp] = nmode; f_pre[sp] = npre; f_ind[sp] = nind; f_cnt[sp] = 0; }
+      if (sp && l == 0) { const uint32_t k = sp - 1; f_mode[k] = F_mode; f_pre[k] = F_pre; f_ind[k] = F_ind; f_cnt[k] = F_cnt; }
+      F_mode = nmode; F_pre = npre; F_ind = nind; F_cnt = 0;
       ++sp;
       tpw::sync();
       if (table && !eerr) {                                        // rows are written one lane per row (em_rows)
@@ -1037,10 +1134,13 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
       }
     } else {
       --sp;
+      if (sp) { const uint32_t k = sp - 1; F_mode = f_mode[k]; F_pre = f_pre[k]; F_ind = f_ind[k]; F_cnt = f_cnt[k]; }
     }
     cur = e + 1;
     evm &= evm - 1;
   }
+  if (sp && l == 0) { const uint32_t k = sp - 1; f_mode[k] = F_mode; f_pre[k] = F_pre; f_ind[k] = F_ind; f_cnt[k] = F_cnt; }
+  tpw::sync();
   st.sp = sp;
   if (st.status) return consumed;
   if (l >= consumed) { act = false; pc.l0 = 0; pc.nl = 0; pc.l1n = 0; pc.body = B_NONE; err = 0; }

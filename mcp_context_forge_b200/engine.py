@@ -245,7 +245,11 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
     W = prog.words if prog is not None else 1
     full = np.zeros(n * W, dtype=np.uint64) if want_full_bitmaps else None
     need = c_uint64(0)
-    cap = max(nbytes, 1 << 12)
+    # the output buffer lives with the Batch and only grows (a fresh np.empty per call costs a page fault per 4 KiB of output)
+    out = getattr(batch, "_out", None)
+    cap = max(nbytes, 1 << 12) if out is None else len(out)
+    if out is None or len(out) < min(nbytes, 1 << 12):
+        out = batch._out = np.empty(cap, dtype=np.uint8)
     if stream is None:                                   # resident run: the batch already holds these units
         sp = None
     else:
@@ -254,7 +258,8 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
     if unit_stages is not None:
         us = np.ascontiguousarray(unit_stages, dtype=np.uint8)
     while True:
-        out = np.empty(cap, dtype=np.uint8)
+        if len(out) < cap:
+            out = batch._out = np.empty(cap, dtype=np.uint8)
         with ctx.lock:
             rc = ctx.lib.cf_run_batch(ctx.h, prog.h if prog is not None else None, batch.h, sp, nbytes, offsets.ctypes.data, n, stage_mask,
                                       us.ctypes.data if us is not None else None, toon_flags, mask_max_depth, verdicts.ctypes.data,

@@ -205,7 +205,7 @@ class BatchedPluginManager(PluginManager):
         hot = np.nonzero(flags)[0].tolist()                      # units with an output
         texts: Dict[int, bytes] = {}
         if hot:
-            raw = out.tobytes()
+            raw = out[: int(out_offs[-1])].tobytes()          # `out` is the batch's reusable buffer: copy what this wave produced
             for i in hot:
                 texts[i] = raw[int(out_offs[i]):int(out_offs[i + 1])]
         fl = flags.tolist()

@@ -119,13 +119,13 @@ def toon_host(text: str, unlimited: bool = False, indexed: bool = False):
     unlimited=True lifts the product's "strictly smaller" capacity so the encoder output itself can
     be compared with the reference's toon.encode.  indexed=True parses through the structural index +
     token-driven builder (json_index.h — the path the CUDA kernels take) instead of the sequential parser."""
-    b = text.encode("utf-8", "surrogatepass")
+    b = text if isinstance(text, bytes) else text.encode("utf-8", "surrogatepass")
     cap = len(b) * 6 + 4096 if unlimited else max(len(b) - 1, 0)
     out = ctypes.create_string_buffer(max(cap, 1))
     n = ctypes.c_uint32()
     fn = lib().cfh_toon_indexed if indexed else lib().cfh_toon
     st = fn(b, len(b), out, cap, ctypes.byref(n))
-    return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)
+    return st, (out.raw[: n.value].decode("utf-8", "surrogatepass") if st == 0 else None)
 
 
 def toon_tp(text, unlimited: bool = False, report_errors: bool = True, order: int = 0):
@@ -138,7 +138,7 @@ def toon_tp(text, unlimited: bool = False, report_errors: bool = True, order: in
     why = ctypes.c_uint32()
     st = lib().cfh_toon_tp(b, len(b), out, cap, ctypes.byref(n), 1 if report_errors else 0, order, ctypes.byref(why))
     toon_tp.last_reason = why.value
-    return st, (out.raw[: n.value].decode("utf-8") if st == 0 else None)
+    return st, (out.raw[: n.value].decode("utf-8", "surrogatepass") if st == 0 else None)
 
 
 def index_equiv(data: bytes):

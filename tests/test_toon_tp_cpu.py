@@ -124,3 +124,63 @@ def test_long_strings_and_chunk_boundaries():
                           "long": " ".join("w%d" % rng.randint(0, 999) for _ in range(60 + pad)), "esc": "a\\nb" * (pad % 5), "n": -pad}, separators=(",", ":"))
         for order in (0, 1):
             assert hs.toon_tp(doc, unlimited=True, order=order | ((pad % 16) << 4)) == hs.toon_host(doc, unlimited=True), pad
+
+
+def test_long_non_ascii_strings_whole_warp_utf8():
+    """Strings of >= 96 bytes with non-ASCII content take the whole-warp UTF-8 validator: valid text in several scripts, every
+    class of malformed sequence at varying offsets, and the Unicode-whitespace / special-character quoting rules at both ends."""
+    rng = random.Random(11)
+    pieces = ["é", "ß", "日本語", "\U0001F600", "Ünï", "a", " ", "word ", "x-y", "\u00a0", "\u3000", "\u2028", "K", "ſ"]
+    docs = []
+    for _ in range(300):
+        body = "".join(rng.choice(pieces) for _ in range(rng.randint(40, 160)))
+        lead = rng.choice(["", "\u00a0", "\u3000", " ", "é", "x"])
+        tail = rng.choice(["", "\u00a0", "\u2028", " ", "é", "x"])
+        docs.append(json.dumps({"k": lead + body + tail, "n": 1, lead + "key" + body[:60] + "é" * 40: 2}, ensure_ascii=False).encode("utf-8"))
+    bad_seqs = [b"\xc0\x80", b"\xc1\xbf", b"\xe0\x80\x80", b"\xe0\x9f\xbf", b"\xed\xa0\x80", b"\xed\xbf\xbf", b"\xf0\x80\x80\x80", b"\xf0\x8f\xbf\xbf", b"\xf4\x90\x80\x80",
+                b"\xf5\x80\x80\x80", b"\x80", b"\xbf", b"\xc3", b"\xe2\x82", b"\xf0\x9f\x98", b"\xff", b"\xc3\xc3\xa9", b"\xe2\x28\xa1", b"\xf0\x28\x8c\xbc"]
+    good_seqs = [b"\xc2\x80", b"\xdf\xbf", b"\xe0\xa0\x80", b"\xed\x9f\xbf", b"\xee\x80\x80", b"\xef\xbf\xbf", b"\xf0\x90\x80\x80", b"\xf4\x8f\xbf\xbf"]
+    for seq in bad_seqs + good_seqs:
+        for off in (0, 1, 31, 32, 33, 95, 150):
+            for at_end in (False, True):
+                filler = ("é" * 100).encode("utf-8")
+                body = filler[:off * 2 // 2 * 1] if False else (b"a" * off + filler)
+                body = (body + seq) if at_end else (body[:off] + seq + body[off:])
+                docs.append(b'{"k":"' + body + b'","z":[1,2]}')
+    n_checked = 0
+    for d in docs:
+        a = hs.toon_host(d, unlimited=True)
+        for order in (0, 1 | (7 << 4)):
+            b = hs.toon_tp(d, unlimited=True, order=order)
+            assert b[0] == 7 or a == b, (d[:120], a, b)
+            n_checked += b[0] != 7
+    assert n_checked > 800
+
+
+def test_long_escaped_strings_whole_warp_escape_check():
+    """Strings of >= 96 bytes with backslash escapes take the whole-warp escape validator (two-character escapes) or, with \\uXXXX,
+    the sequential one: every escape kind, invalid escapes, backslash runs across the 32-byte chunks, quoting at both ends."""
+    rng = random.Random(12)
+    esc = ['\\n', '\\t', '\\r', '\\"', '\\\\', '\\/', '\\b', '\\f', '\\u00e9', '\\u0041', '\\ud83d\\ude00', '\\u0009', '\\u002c']
+    plain = ["word", " ", "é", "x", "lorem ipsum", "a/b", "日本"]
+    docs = []
+    for _ in range(400):
+        kinds = rng.sample(esc, rng.randint(1, 3)) if rng.random() < 0.8 else ['\\/']
+        body = "".join(rng.choice(plain + kinds) for _ in range(rng.randint(30, 120)))
+        lead = rng.choice(["", "\\/", "\\n", " ", "x"])
+        tail = rng.choice(["", "\\/", "\\t", " ", "x", "\\\\"])
+        docs.append(('{"k":"' + lead + body + tail + '","n":[1,2]}').encode("utf-8"))
+    for bad in ['\\x', '\\u12g4', '\\ud800', '\\udc00', '\\u12', '\\ ', '\\a']:
+        for off in (0, 30, 31, 32, 33, 64, 100):
+            docs.append(('{"k":"' + "a" * off + bad + "b" * 120 + '"}').encode("utf-8"))
+    for run in range(1, 9):                                     # backslash runs straddling chunk boundaries
+        for off in (28, 29, 30, 31, 32, 60, 61, 62, 63):
+            docs.append(('{"k":"' + "a" * off + "\\" * run + ('"' if run % 2 else 'n') + "b" * 100 + '"}').encode("utf-8"))
+    n_checked = 0
+    for d in docs:
+        a = hs.toon_host(d, unlimited=True)
+        for order in (0, 1 | (9 << 4)):
+            b = hs.toon_tp(d, unlimited=True, order=order)
+            assert b[0] == 7 or a == b, (d[:160], a, b)
+            n_checked += b[0] != 7
+    assert n_checked > 900

@@ -19,6 +19,14 @@ for shape, size, n in CASES:
     if shape == "M":   # BASELINE configs[3]: mixed 2 / 16 / 256 KiB tabular payloads (by count 80 % / 19 % / 1 %)
         pool = {k: [synth.payload("A", k, seed=s).encode() for s in range(8)] for k in (2048, 16384, 262144)}
         texts = [pool[262144 if i % 100 == 0 else 16384 if i % 5 == 0 else 2048][i % 8] for i in range(n)]
+    elif shape == "P":   # prose inside a JSON document (one long string value), as in bench.py's chain mix
+        import json
+        base = [json.dumps({"title": f"document {s}", "lang": "en", "body": synth.payload("C", size - 64, seed=s)}, ensure_ascii=False, separators=(",", ":")).encode() for s in range(64)]
+        texts = [base[i % 64] for i in range(n)]
+    elif shape == "N":   # prose with newline escapes
+        import json
+        base = [json.dumps({"log": synth.payload("C", size - 64, seed=s).replace(". ", ".\n").replace(" a", "\na", 40)}, ensure_ascii=True).encode() for s in range(64)]
+        texts = [base[i % 64] for i in range(n)]
     else:
         base = [synth.payload(shape, size, seed=s).encode() for s in range(64)]
         texts = [base[i % 64] for i in range(n)]
