@@ -608,8 +608,9 @@ def scan_bench(args, rank, local_rank, world):
     d_bm = torch.zeros(n * W, dtype=torch.int64, device="cuda")
     d_bms = [d_bm, torch.zeros(n * W, dtype=torch.int64, device="cuda")] if world > 1 else [d_bm]
     # the gather carries 16 bits per unit (14 patterns), not the 64-bit word
-    d_small = [torch.zeros(n, dtype=torch.int16, device="cuda") for _ in range(2)] if world > 1 else None
-    d_alls = [torch.zeros(world * n, dtype=torch.int16, device="cuda") for _ in range(2)] if world > 1 else None
+    # (NCCL has no 16-bit integer type: the buffers are bytes, written through an int16 view)
+    d_small = [torch.zeros(2 * n, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+    d_alls = [torch.zeros(world * 2 * n, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
     pending = []
     step_no = [0]
     batch = engine.Batch(ctx, nbytes, n)
@@ -626,7 +627,7 @@ def scan_bench(args, rank, local_rank, world):
             pending.pop(0).wait()
         ctx.check(lib.cf_scan(ctx.h, prog.h, batch.h, d_bms[k].data_ptr(), cs), "cf_scan")
         if world > 1:
-            d_small[k].copy_(d_bms[k])                      # W == 1: the low 16 bits hold all 14 pattern bits
+            d_small[k].view(torch.int16).copy_(d_bms[k])    # W == 1: the low 16 bits hold all 14 pattern bits
             pending.append(dist.all_gather_into_tensor(d_alls[k], d_small[k], async_op=True))
 
     def drain():

@@ -698,6 +698,7 @@ template <typename T>
 static int upload(cf_ctx* ctx, const std::vector<T>& v, const T** out, std::vector<void*>& allocs) {
   void* d = nullptr;
   size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+  bytes = (bytes + 15) & ~(size_t)15;   // the scan kernel stages tables into shared memory in whole 32-bit words (compute-sanitizer memcheck, round 2)
   CF_CUDA(ctx, cudaMalloc(&d, bytes));
   allocs.push_back(d);
   if (!v.empty()) CF_CUDA(ctx, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));

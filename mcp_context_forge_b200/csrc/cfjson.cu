@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "cf_internal.h"
 #include "json_index.h"
 #include "json_mask.h"
@@ -366,9 +368,13 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
   if ((stage_mask & (CF_STAGE_SCAN | CF_STAGE_SUB)) && !prog) return CF_E_BADARG;
   if ((stage_mask & CF_STAGE_TOON) && (stage_mask & CF_STAGE_MASK)) { ctx->err = "CF_STAGE_TOON and CF_STAGE_MASK both produce the unit's output: two calls"; return CF_E_BADARG; }
   if (stage_mask & CF_STAGE_SUB) stage_mask |= CF_STAGE_SCAN;
+  struct Nvtx { Nvtx(const char* n) { nvtxRangePushA(n); } ~Nvtx() { nvtxRangePop(); } } nvtx_call("cf_run_batch");   // ranges: assemble (caller) | h2d | kernels | d2h
   int rc = CF_OK;
-  if (stream) rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
-  else if (b->n != n_units || b->nbytes != stream_bytes) { ctx->err = "resident run: the batch on the device is a different one"; return CF_E_BADARG; }
+  if (stream) {
+    nvtxRangePushA("cf_run_batch:h2d");
+    rc = cf_batch_upload(ctx, b, stream, stream_bytes, offsets, n_units, nullptr);
+    nvtxRangePop();
+  } else if (b->n != n_units || b->nbytes != stream_bytes) { ctx->err = "resident run: the batch on the device is a different one"; return CF_E_BADARG; }
   if (rc) return rc;
   const uint32_t W = prog ? prog->W : 1;
   std::vector<uint64_t> bm;
@@ -381,6 +387,7 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
     CF_CUDA(ctx, cudaMemcpyAsync(d_us, unit_stages, n_units, cudaMemcpyHostToDevice, 0));
   }
   // ---- launches, back to back
+  nvtxRangePushA("cf_run_batch:kernels");
   if (stage_mask & CF_STAGE_SCAN) {
     if ((rc = cf_dev_reserve(ctx, ctx->tmp[6], (size_t)n_units * W * 8))) return rc;
     if ((rc = cf_scan(ctx, prog, b, (uint64_t*)ctx->tmp[6].p, nullptr))) return rc;
@@ -391,7 +398,9 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
     if ((rc = cf_dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
     if ((rc = toon_launch(ctx, b, toon_flags & ~(CF_TOON_PARSE_ONLY | CF_TOON_SEQUENTIAL), (uint8_t*)ctx->tmp[0].p, (uint32_t*)ctx->tmp[1].p, (int32_t*)ctx->tmp[2].p, d_us, 0))) return rc;
   }
+  nvtxRangePop();
   // ---- results of the launches
+  Nvtx nvtx_d2h("cf_run_batch:d2h+verdicts");
   for (uint32_t i = 0; i < n_units; ++i) { verdicts[i].match_bitmap = 0; verdicts[i].flags = 0; verdicts[i].out_len = 0; verdicts[i].aux = 0; verdicts[i].reserved = 0; }
   std::vector<uint32_t> dirty;
   if (stage_mask & CF_STAGE_SCAN) {

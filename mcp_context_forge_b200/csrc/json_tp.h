@@ -780,6 +780,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
   // is brought up to date when a container is pushed and at the end of the batch.
   uint32_t T_oi = 0, T_cnt = 0, T_cfl = 0, T_khb = 0, T_r0i = 0, T_r0n = UNSET, T_ow = 0;
   if (sp) { const uint32_t k = sp - 1; T_oi = sh.open_idx[k]; T_cnt = sh.cnt[k]; T_cfl = sh.cfl[k]; T_khb = sh.khbase[k]; T_r0i = sh.row0_idx[k]; T_r0n = sh.row0_n[k]; T_ow = sh.open_w[k]; }
+  tpw::sync();                       // every lane has its copy before lane 0 may overwrite the slot (push / write-back)
   while (true) {
     const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
     const uint32_t run = range_mask(cur, e);
@@ -879,6 +880,7 @@ TP_FN uint32_t an_batch(const uint8_t* s, GTok* toks, uint32_t tok_cap, Shared& 
       if (sp) {                                                      // the parent comes back into the registers
         const uint32_t k = sp - 1;
         T_oi = sh.open_idx[k]; T_cnt = sh.cnt[k]; T_cfl = sh.cfl[k]; T_khb = sh.khbase[k]; T_r0i = sh.row0_idx[k]; T_r0n = sh.row0_n[k]; T_ow = sh.open_w[k];
+        tpw::sync();
         if (isobj && !(T_cfl & C_OBJ)) {                             // an object element of an array closed: table bookkeeping
           if (!(tfl & C_VALS_SIMPLE)) T_cfl &= ~C_ROWS_SIMPLE;
           if (oi + 1 == T_r0i) {                                     // the first row
@@ -1045,6 +1047,7 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
   // the frame on top of the stack lives in (warp-uniform) registers during the walk
   uint32_t F_mode = M_ROOT, F_pre = 0, F_ind = 0, F_cnt = 0;
   if (sp) { const uint32_t k = sp - 1; F_mode = f_mode[k]; F_pre = f_pre[k]; F_ind = f_ind[k]; F_cnt = f_cnt[k]; }
+  tpw::sync();
   while (true) {
     const uint32_t e = evm ? tpw::ffs(evm) - 1 : m;
     const uint32_t run = range_mask(cur, e);
@@ -1134,7 +1137,7 @@ TP_FN uint32_t em_batch(const uint8_t* s, const GTok* toks, uint32_t ntok, uint8
       }
     } else {
       --sp;
-      if (sp) { const uint32_t k = sp - 1; F_mode = f_mode[k]; F_pre = f_pre[k]; F_ind = f_ind[k]; F_cnt = f_cnt[k]; }
+      if (sp) { const uint32_t k = sp - 1; F_mode = f_mode[k]; F_pre = f_pre[k]; F_ind = f_ind[k]; F_cnt = f_cnt[k]; tpw::sync(); }
     }
     cur = e + 1;
     evm &= evm - 1;
