@@ -112,6 +112,12 @@ __global__ void __launch_bounds__(TP_WARPS * 32, 2) toon_tp_kernel(const uint8_t
   if (unit_stages && !(unit_stages[u] & CF_STAGE_TOON)) { if (lane == 0) { status[u] = CF_TOON_SKIPPED; out_len[u] = 0; } return; }
   cftp::Shared& sh = *reinterpret_cast<cftp::Shared*>(tp_smem + (size_t)wic * TP_WARP_SMEM);
   uint8_t* stage = tp_smem + (size_t)wic * TP_WARP_SMEM + sizeof(cftp::Shared);
+  if (lane == 0) {                                   // the warp's mbarrier for its bulk TMA loads into the staging buffer
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sh.sbar_bar)));
+    sh.sbar_phase = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   const uint64_t b = offsets[u];
   const uint64_t len64 = offsets[u + 1] - b - 1;
   if (len64 > 0x7FFFFFFFull) { if (lane == 0) { status[u] = cfj::TS_UNSUPPORTED; out_len[u] = 0; } return; }

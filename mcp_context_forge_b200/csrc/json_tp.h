@@ -77,6 +77,8 @@ struct Shared {
   uint32_t row0_n[MAXD];               // arrays: member count of that first object once it closed
   uint32_t kh[KH_CAP];                 // key hashes of the open objects (stack)
   uint32_t open_w[MAXD];               // analyze: the opener's token word (its separator bits survive the patch)
+  unsigned long long sbar_bar;         // mbarrier of the staging buffer's bulk TMA loads (initialised by the kernel)
+  uint32_t sbar_phase, sbar_pad;
 };
 enum : uint32_t {
   C_OBJ = 1,
@@ -103,12 +105,33 @@ static const uint32_t WIN = 2048;            // tokenizer: the last two 1 KiB st
 static const uint32_t ROW_SRC = 5120, ROW_OUT = STAGE - ROW_SRC;   // table rows: source bytes of a round | its output
 
 // stage[0..) <- s[a0 .. a1) where a0 is rounded down to the 16-byte grid; returns the unit position of stage[0] (can be negative)
-TP_FN int64_t stage_load(uint8_t* stage, const uint8_t* s, uint32_t a0, uint32_t a1) {
+// On the GPU the copy is ONE bulk TMA transfer (cp.async.bulk global -> shared, SASS UBLKCP) completing on the warp's mbarrier.
+struct StageBar { uint64_t bar; uint32_t phase; };     // lives in the warp's shared memory (Shared::sbar)
+TP_FN int64_t stage_load(uint8_t* stage, const uint8_t* s, uint32_t a0, uint32_t a1, StageBar& sb) {
   const uint32_t lead = (uint32_t)((uintptr_t)(s + a0) & 15u);
   const uint8_t* g = s + a0 - lead;
   const uint32_t bytes = a1 - a0 + lead;
+#ifdef __CUDA_ARCH__
+  const uint32_t b16 = (bytes + 15u) & ~15u;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sb.bar), dst = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint32_t parity = sb.phase;
+  tpw::sync();                                                          // every lane is done with the buffer's previous contents
+  if (tpw::lane() == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy accesses to the buffer are ordered before the async-proxy write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b16) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g), "r"(b16), "r"(bar) : "memory");
+    sb.phase = parity ^ 1u;
+  }
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+  tpw::sync();
+#else
+  (void)sb;
   for (uint32_t o = tpw::lane() * 16; o < bytes; o += 512) *reinterpret_cast<uint4*>(stage + o) = *reinterpret_cast<const uint4*>(g + o);
   tpw::sync();
+#endif
   return (int64_t)a0 - (int64_t)lead;
 }
 // out[dst .. dst+len) <- stage[0 .. len), coalesced (16-byte stores on the aligned middle)
@@ -931,7 +954,7 @@ TP_FN uint32_t an_rows(const uint8_t* s, GTok* toks, uint32_t ntok, Shared& sh, 
   if (Rf) {
     R = Rf;
     const uint32_t a1 = tpw::shfl(rend, R - 1);
-    sb = stage - stage_load(stage, s, a0, a1);
+    sb = stage - stage_load(stage, s, a0, a1, *reinterpret_cast<StageBar*>(&sh.sbar_bar));
   }
   bool ok = l < R;
   if (ok) {
@@ -1237,7 +1260,7 @@ TP_FN void em_rows(const uint8_t* s, const GTok* toks, uint8_t* out, uint32_t ou
     const uint8_t* sb = s;
     if (Rf) {
       R = Rf;
-      sb = stage - stage_load(stage, s, a0, tpw::shfl(rend, R - 1));
+      sb = stage - stage_load(stage, s, a0, tpw::shfl(rend, R - 1), *reinterpret_cast<StageBar*>(&sh.sbar_bar));
     } else R = 1;                                        // one over-long row at a time, straight from global memory
     const bool act = l < R;
     uint32_t plen = 0, err = 0;
