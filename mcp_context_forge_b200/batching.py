@@ -99,6 +99,30 @@ class GpuBatcher:
             i += len(g)
         return out
 
+    def scan_sub_groups(self, prog: engine.Program, groups: Sequence[Sequence[Unit]], rule_mask: int) -> List[List[tuple]]:
+        """Like sub_groups, but every unit also gets its verdict bitmap: [(bits, rewritten bytes | None)] (sql_sanitizer)."""
+        flat: List[bytes] = [engine.encode_unit(u) for g in groups for u in g]
+        if not flat:
+            return [[] for _ in groups]
+        if prog.h is None:
+            prog.compile(self.ctx)
+        stream, offs = engine.pack_units(flat)
+        batch = self._ensure_batch(len(stream), len(flat))
+        bm = engine.bitmaps_to_ints(engine.scan_host(prog, batch, stream, offs), len(flat), prog.words)
+        self.launches += 1
+        self.units_seen += len(flat)
+        dirty = [i for i, v in enumerate(bm) if v & rule_mask]
+        res: List[tuple] = [(v, None) for v in bm]
+        if dirty:
+            for i, new in zip(dirty, engine.sub_host(prog, batch, dirty)):
+                res[i] = (bm[i], new)
+            self.launches += 1
+        out, i = [], 0
+        for g in groups:
+            out.append(res[i:i + len(g)])
+            i += len(g)
+        return out
+
     def toon_groups(self, groups: Sequence[Sequence[Unit]], report_errors: bool = True) -> List[List[tuple]]:
         """JSON texts -> [(status, toon_bytes_or_None)] per text, one launch for all groups."""
         flat: List[bytes] = [engine.encode_unit(u) for g in groups for u in g]
@@ -125,6 +149,9 @@ class GpuBatcher:
 
     async def sub(self, prog: engine.Program, units: Sequence[Unit], rule_mask: int) -> List[Optional[bytes]]:
         return await self._submit(prog, "sub", rule_mask, units)
+
+    async def scan_sub(self, prog: engine.Program, units: Sequence[Unit], rule_mask: int) -> List[tuple]:
+        return await self._submit(prog, "scan_sub", rule_mask, units)
 
     async def _submit(self, prog: engine.Program, op: str, arg: int, units: Sequence[Unit]):
         if not units:
@@ -153,6 +180,8 @@ class GpuBatcher:
                     results = self.scan_groups(prog, groups)
                 elif op == "sub":
                     results = self.sub_groups(prog, groups, arg)
+                elif op == "scan_sub":
+                    results = self.scan_sub_groups(prog, groups, arg)
                 else:
                     results = self.toon_groups(groups, bool(arg))
             except Exception as exc:  # surface the failure to every caller (no silent fallback)

@@ -8,4 +8,6 @@
       -> mcp_context_forge_b200.plugins.harmful_content_detector.HarmfulContentDetectorPlugin
   plugins.toon_encoder.toon_encoder.ToonEncoderPlugin
       -> mcp_context_forge_b200.plugins.toon_encoder.ToonEncoderPlugin
+  plugins.sql_sanitizer.sql_sanitizer.SQLSanitizerPlugin
+      -> mcp_context_forge_b200.plugins.sql_sanitizer.SQLSanitizerPlugin
 """

@@ -352,8 +352,70 @@ def gen_masking():
     dump("masking_twin.json", {"classifier": classifier, "mask_sensitive_data": data_cases, "cookies": cookie_cases, "headers": header_cases})
 
 
+# ------------------------------------------------------------------------------------------------
+def gen_sql_sanitizer():
+    """plugins/sql_sanitizer/sql_sanitizer.py through its two hooks."""
+    from cpex.framework import GlobalContext, PluginConfig, PluginContext, PromptPrehookPayload, ToolPreInvokePayload
+    from plugins.sql_sanitizer.sql_sanitizer import SQLSanitizerPlugin
+
+    ctx = PluginContext(global_context=GlobalContext(request_id="golden"))
+    rng = random.Random(4242)
+    frags = ["SELECT * FROM t", "select a, b from t where a = 1", "DROP TABLE users", "drop", "dropped", "Truncate x", "ALTER\ttable", "grant all", "REVOKE",
+             "DELETE FROM t", "delete\n from t WHERE id=1", "DELETE  FROM", "deletefrom", "UPDATE t SET a=1", "update  é SET", "UPDATE ", "update t set a=1 where b=2",
+             "nowhere", "WHERE", "-- comment", "--", "-", "a -- b\nc", "/* block */", "/* multi\nline */", "/*", "*/", "/*/", "/**/", "x /* DROP */ y",
+             "-- DROP\n", "/* where */", "'a' + b", "%s", "%.2f", "{name}", "{", "}", "f\"{x}\"", ";", " ", "\n", "\r\n", "é", "ſelect", "İ", "K", "\u212a", "日本語", ""]
+
+    def text():
+        return rng.choice(["", " ", "\n", "; "]).join(rng.choice(frags) for _ in range(rng.randint(0, 5)))
+
+    def value(d):
+        r = rng.random()
+        if d <= 0 or r < 0.5:
+            return text()
+        if r < 0.6:
+            return rng.choice([7, None, True, 2.5])
+        if r < 0.8:
+            return {rng.choice(["sql", "query", "q", "note"]): value(d - 1) for _ in range(rng.randint(0, 3))}
+        return [rng.choice([text(), {rng.choice(["sql", "q"]): value(d - 1)}, [text()], 5]) for _ in range(rng.randint(0, 3))]
+
+    configs = [
+        None,
+        {"fields": None, "blocked_statements": _SQL_DEFAULT, "block_delete_without_where": True, "block_update_without_where": True, "strip_comments": True,
+         "require_parameterization": False, "block_on_violation": True},                                    # tests/unit/plugins/test_sql_sanitizer.py:22-37
+        {"block_on_violation": False},
+        {"block_on_violation": False, "require_parameterization": True, "fields": ["sql", "query"]},
+        {"strip_comments": False, "require_parameterization": True},
+        {"strip_comments": False, "block_on_violation": False, "block_delete_without_where": False},
+        {"blocked_statements": [r"\bEXEC(?:UTE)?\b", r"xp_\w+", r";\s*--"], "block_update_without_where": False, "block_on_violation": False},
+        {"blocked_statements": [], "block_on_violation": False, "fields": []},
+    ]
+    out = []
+    for cfg in configs:
+        plug = SQLSanitizerPlugin(PluginConfig(name="sql", kind="x", hooks=["prompt_pre_fetch", "tool_pre_invoke"], config=cfg))
+        cases = []
+        fixed = [{"path": "sql.txt", "edits": [{"new": "DROP table tab1;", "old": "DROP table tab1;"}], "dry_run": False}, {"message": "DROP table asdf"},
+                 {}, {"sql": "select 1 -- x", "nested": {"sql": "/* c */ select 2", "deep": {"query": "DELETE FROM t -- where"}}},
+                 {"sql": ["DROP x", "ok -- c", {"sql": "update t set a=1 /* where */"}], "query": "a + b"}]
+        for i in range(90):
+            args = fixed[i] if i < len(fixed) else {rng.choice(["sql", "query", "q", "other"]): value(3) for _ in range(rng.randint(0, 4))}
+            hook = "tool_pre_invoke" if i % 2 == 0 else "prompt_pre_fetch"
+            if hook == "tool_pre_invoke":
+                r = run(plug.tool_pre_invoke(ToolPreInvokePayload(name="t", args=args), ctx))
+            else:
+                r = run(plug.prompt_pre_fetch(PromptPrehookPayload(prompt_id="p", args=args), ctx))
+            cases.append({"hook": hook, "args": args, "continue_processing": r.continue_processing, "metadata": r.metadata,
+                          "out_args": r.modified_payload.args if r.modified_payload is not None else None,
+                          "violation": r.violation.model_dump(exclude={"plugin_name", "http_status_code", "mcp_error_code", "http_headers"}) if r.violation else None})
+        out.append({"config": cfg, "cases": cases})
+    dump("sql_sanitizer.json", out)
+
+
+_SQL_DEFAULT = [r"\bDROP\b", r"\bTRUNCATE\b", r"\bALTER\b", r"\bGRANT\b", r"\bREVOKE\b"]
+
+
 if __name__ == "__main__":
     install_shims()
-    gen_pattern_plugins()
-    gen_toon()
-    gen_masking()
+    only = sys.argv[1:]
+    for name, fn in (("pattern_plugins", gen_pattern_plugins), ("toon", gen_toon), ("masking", gen_masking), ("sql_sanitizer", gen_sql_sanitizer)):
+        if not only or name in only:
+            fn()
