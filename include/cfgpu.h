@@ -79,6 +79,12 @@ int cf_builder_add_pattern(cf_builder* b, const uint32_t* ast, uint32_t nwords, 
                            uint32_t* out_index);
 /* literal replacement bytes (UTF-8) for a CF_PAT_ORDERED pattern */
 int cf_builder_set_replacement(cf_builder* b, uint32_t pattern_index, const uint8_t* repl, uint32_t len);
+/* replacement TEMPLATE with group references (`re.sub` templates `\\1`, `\\g<name>`, `\\g<0>`; the reference passes the
+ * configured `replace` string straight to `pattern.sub`, plugins/regex_filter/search_replace.py:130): `parts` holds n_parts
+ * triples {kind, a, b} — kind 0: literal bytes literals[a .. a+b), kind 1: the text of group a (0 = the whole match; a group
+ * that did not take part contributes nothing).  The pattern's AST must carry its A_GROUP nodes (csrc/re_backend.h). */
+int cf_builder_set_template(cf_builder* b, uint32_t pattern_index, const uint8_t* literals, uint32_t literals_len,
+                            const uint32_t* parts, uint32_t n_parts);
 /* run the host part of compilation now (idempotent); reports table sizes */
 typedef struct cf_compile_stats {
   uint32_t n_patterns, words_per_bitmap, n_classes, n_states, n_accsets, n_ordered;
@@ -105,6 +111,11 @@ int cf_batch_upload(cf_ctx* ctx, cf_batch* b, const uint8_t* stream, uint64_t st
                     const uint64_t* offsets, uint32_t n_units, void* cuda_stream);
 uint32_t cf_batch_units(const cf_batch* b);
 uint64_t cf_batch_bytes(const cf_batch* b);
+/* Page-locked host memory for the buffers a caller hands to the *_host / cf_run_batch entry points (packed stream in, produced
+ * texts out).  Any host pointer works; a pageable one is copied through the driver's bounce buffer at a fraction of the PCIe rate
+ * (measured: 306 MB of TOON text per step, 21 ms pageable vs 6 ms pinned). */
+int cf_host_alloc(cf_ctx* ctx, uint64_t bytes, void** out);
+void cf_host_free(cf_ctx* ctx, void* p);
 
 /* ---------------- stage 1: multi-pattern scan ---------------- */
 /* device-resident: d_bitmaps = device pointer to n_units*W uint64 (may be torch-owned memory) */

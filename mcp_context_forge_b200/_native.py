@@ -34,6 +34,7 @@ _SIGS = {
     "cf_builder_set_word_set": (c_int, [c_void_p, c_void_p, c_uint32]),
     "cf_builder_add_pattern": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, POINTER(c_uint32)]),
     "cf_builder_set_replacement": (c_int, [c_void_p, c_uint32, c_char_p, c_uint32]),
+    "cf_builder_set_template": (c_int, [c_void_p, c_uint32, c_char_p, c_uint32, c_void_p, c_uint32]),
     "cf_builder_compile_host": (c_int, [c_void_p, POINTER(CompileStats)]),
     "cf_init": (c_int, [c_int, POINTER(c_void_p)]),
     "cf_shutdown": (None, [c_void_p]),
@@ -44,6 +45,8 @@ _SIGS = {
     "cf_prog_patterns": (c_uint32, [c_void_p]),
     "cf_batch_create": (c_int, [c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "cf_batch_free": (None, [c_void_p]),
+    "cf_host_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p)]),
+    "cf_host_free": (None, [c_void_p, c_void_p]),
     "cf_batch_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "cf_batch_units": (c_uint32, [c_void_p]),
     "cf_batch_bytes": (c_uint64, [c_void_p]),

@@ -59,7 +59,10 @@ def needs_build() -> bool:
     if not os.path.exists(SO):
         return True
     for s in SOURCES:
-        if _stale(SO, _deps(os.path.join(CSRC, s))):
+        obj = os.path.join(OBJ, os.path.splitext(s)[0] + ".o")
+        # the object against its sources (a source edited while an earlier build was running is newer than its object but older
+        # than the library that build linked), and the library against the object
+        if _stale(obj, _deps(os.path.join(CSRC, s))) or _stale(SO, [obj]):
             return True
     return False
 

@@ -608,6 +608,33 @@ def payload_matches(payload: Any, hook_type: Any, conditions: list[PluginConditi
 
 
 # --------------------------------------------------------------------------------------------- manager
+_osa = object.__setattr__
+
+
+def fast_construct(cls: type, values: dict) -> Any:
+    """`cls.model_construct(**values)` for a model without private attributes when EVERY field is given (no defaults to fill,
+    no validation — the values come from our own code): four attribute stores instead of pydantic's generic path (≈ 4x faster;
+    the executor builds five such objects per request)."""
+    m = cls.__new__(cls)
+    _osa(m, "__dict__", values)
+    _osa(m, "__pydantic_fields_set__", set(values))
+    _osa(m, "__pydantic_extra__", None)
+    _osa(m, "__pydantic_private__", None)
+    return m
+
+
+def fast_copy(model: Any, updates: dict) -> Any:
+    """`model.model_copy(update=updates)` (shallow) for a model without extras / private attributes."""
+    if model.__pydantic_extra__ is not None or model.__pydantic_private__ is not None:
+        return model.model_copy(update=updates)
+    m = model.__class__.__new__(model.__class__)
+    _osa(m, "__dict__", {**model.__dict__, **updates})
+    _osa(m, "__pydantic_fields_set__", model.__pydantic_fields_set__ | updates.keys())
+    _osa(m, "__pydantic_extra__", None)
+    _osa(m, "__pydantic_private__", None)
+    return m
+
+
 _LEGACY_MODES = {
     PluginMode.ENFORCE: (PluginMode.SEQUENTIAL, OnError.FAIL),
     PluginMode.ENFORCE_IGNORE_ERROR: (PluginMode.SEQUENTIAL, OnError.IGNORE),
@@ -696,7 +723,7 @@ class PluginManager:
         for f in policy.writable_fields:
             if f in type(current).model_fields and getattr(modified, f) is not getattr(current, f):
                 updates[f] = getattr(modified, f)
-        return current.model_copy(update=updates) if updates else current
+        return fast_copy(current, updates) if updates else current
 
     async def _run_one(self, ref: PluginRef, hook: str, payload: Any, ctx: PluginContext) -> PluginResult:
         fn = getattr(ref.plugin, hook)

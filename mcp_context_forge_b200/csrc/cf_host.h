@@ -13,6 +13,7 @@ struct cf_builder {
   std::vector<uint8_t> ordered;
   std::vector<std::vector<uint8_t>> repl;
   std::vector<uint8_t> has_repl;
+  std::vector<std::vector<uint32_t>> tmpl;   // per pattern: {kind, a, b} triples when the replacement references groups, else empty
   cfre::CharSet word;
   cfre::CompileOut out;
   bool compiled = false;

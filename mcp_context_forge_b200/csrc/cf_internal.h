@@ -71,6 +71,11 @@ struct cf_prog {
   std::vector<uint8_t*> d_repl;
   std::vector<uint32_t> repl_len;
   std::vector<uint32_t> ordered_minlen;   // minimum match length (code points) of each ordered rule
+  struct RuleTmpl {                       // replacement template with group references (n_parts == 0: literal replacement)
+    uint32_t *d_code = nullptr, *d_sets = nullptr, *d_parts = nullptr;
+    uint32_t ninst = 0, wpc = 1, nslots = 2, n_parts = 0, nrefs = 0, lit_len = 0;
+  };
+  std::vector<RuleTmpl> tmpl;             // per ordered rule
   std::vector<uint64_t> h_offsets;        // host copy of the last batch's offsets (cf_sub_host sizing)
   const void* h_offsets_owner = nullptr;
   uint64_t h_offsets_gen = 0;

@@ -585,6 +585,11 @@ struct SubRule {
   const uint32_t* E;
   const uint8_t* repl;
   uint32_t repl_len;
+  uint32_t nullable;          // the rule can match "": every position is a candidate, re.sub's must_advance rule applies
+  // replacement template with group references (n_parts == 0: `repl` is the literal replacement)
+  const uint32_t* parts;      // {kind, a, b} triples; literals live in `repl`
+  cf::NfaView nfa;
+  uint32_t n_parts;
 };
 
 struct SubParams {
@@ -595,6 +600,8 @@ struct SubParams {
   const uint64_t* bound;
   uint8_t* scratch;
   uint64_t* rec;              // per selected unit: [0] = final text offset in scratch (or ~0: unchanged), [1] = length
+  uint32_t* pike;             // per selected unit: pike_words of Pike-VM scratch (rules with group references only)
+  uint64_t pike_words;
   uint32_t n_sel;
   uint32_t n_rules;
   SubRule rules[SUB_MAX_RULES];
@@ -604,12 +611,38 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
   for (uint64_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
+// One replacement at out_pos for the match of rule R that starts at sp: the literal, or the template with the group texts of
+// THIS match (captures by lane 0's Pike VM pass, spans broadcast through shared memory).  Returns the bytes written.
+__device__ __forceinline__ uint64_t emit_replacement(const SubRule& R, const uint8_t* src, uint64_t len, uint64_t sp, bool must_advance, uint8_t* dst,
+                                                     uint32_t lane, uint32_t* caps_s, uint32_t* pike) {
+  if (R.n_parts == 0) { warp_copy(dst, R.repl, R.repl_len, lane); return R.repl_len; }
+  __syncwarp();
+  if (lane == 0) {
+    for (uint32_t k = 0; k < R.nfa.nslots; ++k) caps_s[k] = cf::CAP_UNSET;
+    cf::pike_captures(R.dfa, R.nfa, src, 0, len, sp, must_advance, pike, caps_s);
+  }
+  __syncwarp();
+  uint64_t o = 0;
+  for (uint32_t k = 0; k < R.n_parts; ++k) {
+    const uint32_t kind = R.parts[3 * k], a = R.parts[3 * k + 1], b = R.parts[3 * k + 2];
+    if (kind == 0) { warp_copy(dst + o, R.repl + a, b, lane); o += b; }
+    else {
+      const uint32_t g0 = caps_s[2 * a], g1 = caps_s[2 * a + 1];
+      if (g0 != cf::CAP_UNSET && g1 != cf::CAP_UNSET && g1 >= g0) { warp_copy(dst + o, src + g0, g1 - g0, lane); o += g1 - g0; }
+    }
+  }
+  return o;
+}
+
 __global__ void __launch_bounds__(SUB_WARPS * 32) sub_kernel(const __grid_constant__ SubParams P) {
   __shared__ uint32_t mlen_s[SUB_WARPS][SUB_WIN];
+  __shared__ uint32_t caps_all[SUB_WARPS][64];
   const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const uint32_t w = blockIdx.x * SUB_WARPS + wic;
   if (w >= P.n_sel) return;
   uint32_t* mlen = mlen_s[wic];
+  uint32_t* caps_s = caps_all[wic];
+  uint32_t* pike = P.pike ? P.pike + (uint64_t)w * P.pike_words : nullptr;
   const uint32_t u = P.sel[w];
   const uint8_t* src = P.stream + P.offsets[u];
   uint64_t len = P.offsets[u + 1] - P.offsets[u] - 1;
@@ -622,6 +655,50 @@ __global__ void __launch_bounds__(SUB_WARPS * 32) sub_kernel(const __grid_consta
     uint8_t* dst = bufs[which];
     uint64_t out_pos = 0, copied = 0, cur = 0;
     uint32_t nmatch = 0;
+    if (R.nullable) {
+      // Every character boundary of [0, len] is a candidate (no prefilter).  Per position: e1 = the leftmost-first match, and, when
+      // that is the empty match, e2 = the best NON-empty match there — what sre finds when it retries the position with
+      // must_advance after an empty match (pattern_subx).  mlen = e1 - sp, mlen2 = e2 - sp (0: there is none).
+      uint32_t* mlen2 = mlen + SUB_WIN / 2;                 // 256 positions per iteration in this mode
+      for (uint64_t wbase = 0; wbase <= len; wbase += SUB_WIN / 2) {
+        const uint64_t b0 = wbase + (uint64_t)lane * 8;
+        uint32_t has = 0;
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint64_t sp = b0 + k;
+          if (sp > len || (sp < len && (src[sp] & 0xC0) == 0x80)) continue;
+          const uint64_t e1 = cf::match_first(R.dfa, src, 0, len, sp);
+          if (e1 == ~0ull) continue;
+          uint32_t m1 = (uint32_t)(e1 - sp), m2 = 0;
+          if (e1 == sp) {
+            const uint64_t e2 = cf::match_first(R.dfa, src, 0, len, sp, true);
+            if (e2 != ~0ull) m2 = (uint32_t)(e2 - sp);
+          }
+          mlen[lane * 8 + k] = m1; mlen2[lane * 8 + k] = m2;
+          has |= 1u << k;
+        }
+        __syncwarp();
+        for (uint32_t L = 0; L < 32; ++L) {
+          uint32_t mk = __shfl_sync(0xFFFFFFFFu, has, L);
+          while (mk) {
+            const uint32_t k = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const uint64_t sp = wbase + (uint64_t)L * 8 + k;
+            if (sp < cur) continue;                     // inside the previous match
+            const uint32_t m1 = mlen[L * 8 + k], m2 = mlen2[L * 8 + k];
+            warp_copy(dst + out_pos, src + copied, sp - copied, lane);
+            out_pos += sp - copied;
+            out_pos += emit_replacement(R, src, len, sp, false, dst + out_pos, lane, caps_s, pike);
+            ++nmatch;
+            if (m1 == 0 && m2) {                        // empty match, then the non-empty one at the same position
+              out_pos += emit_replacement(R, src, len, sp, true, dst + out_pos, lane, caps_s, pike);
+              ++nmatch;
+            }
+            copied = cur = sp + (m1 ? m1 : m2);
+          }
+        }
+        __syncwarp();
+      }
+    } else
     for (uint64_t wbase = 0; wbase < len; wbase += SUB_WIN) {
       // prefilter the 16 start positions owned by this lane (5-byte window: start-1 .. start+3)
       const uint64_t b0 = wbase + (uint64_t)lane * 16;
@@ -654,8 +731,7 @@ __global__ void __launch_bounds__(SUB_WARPS * 32) sub_kernel(const __grid_consta
           const uint32_t ml = mlen[L * 16 + k];
           warp_copy(dst + out_pos, src + copied, sp - copied, lane);
           out_pos += sp - copied;
-          warp_copy(dst + out_pos, R.repl, R.repl_len, lane);
-          out_pos += R.repl_len;
+          out_pos += emit_replacement(R, src, len, sp, false, dst + out_pos, lane, caps_s, pike);
           copied = cur = sp + ml;
           ++nmatch;
         }
@@ -722,7 +798,7 @@ static int upload_dfa(cf_ctx* ctx, const cfre::DfaOut& d, DevDfa& o) {
   o.t.nranges = (uint32_t)d.range_start.size();
   o.t.ncols = d.ncols;
   o.t.W = d.W;
-  for (int i = 0; i < 4; ++i) o.t.start_state[i] = d.start_state[i];
+  for (int i = 0; i < 4; ++i) { o.t.start_state[i] = d.start_state[i]; o.t.start_adv[i] = d.start_adv[i]; }
   return CF_OK;
 }
 
@@ -817,6 +893,19 @@ int cf_compile(cf_ctx* ctx, cf_builder* b, cf_prog** out) {
     p->d_repl.push_back(dr);
     p->repl_len.push_back((uint32_t)rl);
     p->ordered_minlen.push_back(b->out.info[i].min_len_chars);
+    cf_prog::RuleTmpl T;
+    if (!b->tmpl[i].empty()) {
+      const cfre::NfaOut& nf = b->out.ordered_nfa[oi];
+      T.ninst = nf.ninst; T.wpc = nf.wpc; T.nslots = 2 * (nf.ngroups + 1); T.n_parts = (uint32_t)(b->tmpl[i].size() / 3);
+      for (uint32_t k = 0; k < T.n_parts; ++k) { if (b->tmpl[i][3 * k] == 1) ++T.nrefs; else T.lit_len += b->tmpl[i][3 * k + 2]; }
+      CF_CUDA(ctx, cudaMalloc(&T.d_code, nf.code.size() * 4));
+      CF_CUDA(ctx, cudaMemcpy(T.d_code, nf.code.data(), nf.code.size() * 4, cudaMemcpyHostToDevice));
+      CF_CUDA(ctx, cudaMalloc(&T.d_sets, nf.setbits.size() * 4));
+      CF_CUDA(ctx, cudaMemcpy(T.d_sets, nf.setbits.data(), nf.setbits.size() * 4, cudaMemcpyHostToDevice));
+      CF_CUDA(ctx, cudaMalloc(&T.d_parts, b->tmpl[i].size() * 4));
+      CF_CUDA(ctx, cudaMemcpy(T.d_parts, b->tmpl[i].data(), b->tmpl[i].size() * 4, cudaMemcpyHostToDevice));
+    }
+    p->tmpl.push_back(T);
     ++oi;
   }
   return CF_OK;
@@ -829,6 +918,7 @@ void cf_free_prog(cf_prog* p) {
   for (auto& d : p->ordered) for (void* a : d.allocs) cudaFree(a);
   for (auto* e : p->d_ordered_E) cudaFree(e);
   for (auto* r : p->d_repl) cudaFree(r);
+  for (auto& t : p->tmpl) { cudaFree(t.d_code); cudaFree(t.d_sets); cudaFree(t.d_parts); }
   cudaFree(p->d_E);
   cudaFree(p->d_always);
   delete p;
@@ -870,6 +960,18 @@ int cf_batch_create(cf_ctx* ctx, uint64_t max_stream_bytes, uint32_t max_units, 
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)cr); return CF_E_CUDA; }
   return CF_OK;
+}
+
+int cf_host_alloc(cf_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out || !bytes) return CF_E_BADARG;
+  *out = nullptr;
+  CF_CUDA(ctx, cudaSetDevice(ctx->device));
+  CF_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return CF_OK;
+}
+void cf_host_free(cf_ctx* ctx, void* p) {
+  (void)ctx;
+  if (p) cudaFreeHost(p);
 }
 
 void cf_batch_free(cf_batch* b) {
@@ -989,19 +1091,24 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
     p->h_offsets_owner = b;
     p->h_offsets_gen = b->generation;
   }
-  // worst-case growth of one unit through all rules
-  double growth = 1.0;
-  for (uint32_t r = 0; r < nr; ++r) {
-    uint32_t ml = p->ordered_minlen[r] ? p->ordered_minlen[r] : 1;
-    double g = (double)((p->repl_len[r] + ml - 1) / ml);
-    growth *= g > 1.0 ? g : 1.0;
-  }
+  // worst-case growth of one unit through all rules: a rule with matches of >= ml bytes turns L bytes into at most L * ceil(repl / ml);
+  // a rule that can match "" has at most L + 1 empty and L non-empty matches
   std::vector<uint64_t> soff(n_sel), bound(n_sel);
   uint64_t total = 0;
   for (uint32_t i = 0; i < n_sel; ++i) {
     if (units[i] >= b->n) { ctx->err = "unit index out of range"; return CF_E_BADARG; }
     uint64_t len = p->h_offsets[units[i] + 1] - p->h_offsets[units[i]] - 1;
-    double bd = (double)len * growth + 16.0;
+    double bd = (double)len;
+    for (uint32_t r = 0; r < nr; ++r) {
+      const uint32_t ml = p->ordered_minlen[r];
+      const cf_prog::RuleTmpl& T = p->tmpl[r];
+      if (T.n_parts) {             // every match: its literals + each referenced group (at most the match itself)
+        const double nmatch = ml ? bd / ml + 1.0 : 2.0 * bd + 1.0;
+        bd = bd * (1.0 + T.nrefs) + nmatch * (double)T.lit_len;
+      } else if (ml == 0) bd += (2.0 * bd + 1.0) * (double)p->repl_len[r];
+      else { const double g = (double)((p->repl_len[r] + ml - 1) / ml); if (g > 1.0) bd *= g; }
+    }
+    bd += 16.0;
     if (bd > 4e9) { ctx->err = "substitution rules expand a unit beyond 4 GB"; return CF_E_CAPACITY; }
     bound[i] = ((uint64_t)bd + 15) & ~15ull;
     soff[i] = total;
@@ -1035,6 +1142,20 @@ int cf_sub_host(cf_ctx* ctx, cf_prog* p, cf_batch* b, const uint32_t* units, uin
       SP.rules[r].E = p->d_ordered_E[r];
       SP.rules[r].repl = p->d_repl[r];
       SP.rules[r].repl_len = p->repl_len[r];
+      SP.rules[r].nullable = p->ordered_minlen[r] == 0;
+      const cf_prog::RuleTmpl& T = p->tmpl[r];
+      SP.rules[r].parts = T.d_parts;
+      SP.rules[r].n_parts = T.n_parts;
+      SP.rules[r].nfa.code = T.d_code; SP.rules[r].nfa.setbits = T.d_sets;
+      SP.rules[r].nfa.ninst = T.ninst; SP.rules[r].nfa.start = 0; SP.rules[r].nfa.wpc = T.wpc; SP.rules[r].nfa.nslots = T.nslots;
+    }
+    SP.pike = nullptr; SP.pike_words = 0;
+    for (uint32_t r = 0; r < nr; ++r)
+      if (p->tmpl[r].n_parts) { const uint64_t wds = cf::pike_scratch_words(p->tmpl[r].ninst, p->tmpl[r].nslots); if (wds > SP.pike_words) SP.pike_words = wds; }
+    if (SP.pike_words) {
+      if ((uint64_t)n_sel * SP.pike_words * 4 > (4ull << 30)) { ctx->err = "capture scratch exceeds 4 GiB (too many units for a rule with group references)"; rc = CF_E_CAPACITY; break; }
+      if ((rc = cf_dev_reserve(ctx, ctx->tmp[15], (size_t)n_sel * SP.pike_words * 4))) break;
+      SP.pike = (uint32_t*)ctx->tmp[15].p;
     }
     sub_kernel<<<(n_sel + SUB_WARPS - 1) / SUB_WARPS, SUB_WARPS * 32>>>(SP);
     ctx->launches++;

@@ -66,11 +66,17 @@ bool parse_node(const std::vector<uint32_t>& w, size_t& pos, Node& out, int dept
       if (pos >= w.size()) return false;
       out.kind = w[pos++];
       return out.kind >= AS_WORD_B && out.kind <= AS_END_DOLLAR;
+    case A_GROUP:
+      if (pos >= w.size()) return false;
+      out.kind = w[pos++];
+      if (out.kind == 0 || out.kind > 99) return false;
+      out.kids.resize(1);
+      return parse_node(w, pos, out.kids[0], depth + 1);
     default: return false;
   }
 }
 
-enum : uint8_t { I_CHAR, I_SPLIT, I_ASSERT, I_MATCH };
+enum : uint8_t { I_CHAR, I_SPLIT, I_ASSERT, I_MATCH, I_SAVE };   // I_SAVE: kind = capture slot (an epsilon edge for the DFAs)
 struct Inst { uint8_t op; int x = -1, y = -1; int set = -1; uint32_t kind = 0; int pat = -1; };
 
 struct Prog {
@@ -118,6 +124,12 @@ struct Prog {
         return cur;
       }
       case A_ASSERT: { Inst i; i.op = I_ASSERT; i.kind = n.kind; i.x = next; return add(i); }
+      case A_GROUP: {
+        Inst c; c.op = I_SAVE; c.kind = 2 * n.kind + 1; c.x = next;
+        int body = comp(n.kids[0], add(c));
+        Inst o; o.op = I_SAVE; o.kind = 2 * n.kind; o.x = body;
+        return add(o);
+      }
       case A_REPEAT: {
         const Node& c = n.kids[0];
         int cur;
@@ -260,6 +272,7 @@ struct DfaBuilder {
   std::vector<int> out_chars;
   std::vector<int> out_match;
   bool cut = false;
+  bool no_empty = false;            // must-advance start state: a zero-length match is not a match and cuts nothing
 
   DfaBuilder(const Prog& p, const Classes& c, bool ord, uint32_t np, size_t maxs)
       : prog(p), C(c), ordered(ord), npat(np), W(ord ? 1 : (np + 63) / 64), max_states(maxs) {
@@ -285,6 +298,7 @@ struct DfaBuilder {
         bool v = false;
         if (in.op == I_ASSERT) v = true;
         else if (in.op == I_SPLIT) v = (in.x >= 0 && needs_ctx[in.x]) || (in.y >= 0 && needs_ctx[in.y]);
+        else if (in.op == I_SAVE) v = in.x >= 0 && needs_ctx[in.x];
         if (v) { needs_ctx[i] = 1; changed = true; }
       }
     }
@@ -317,16 +331,22 @@ struct DfaBuilder {
       const Inst& in = prog.insts[p];
       switch (in.op) {
         case I_CHAR: out_chars.push_back(p); break;
-        case I_MATCH: out_match.push_back(in.pat); if (ordered) cut = true; break;
+        case I_MATCH: if (no_empty) break; out_match.push_back(in.pat); if (ordered) cut = true; break;
         case I_ASSERT: if (holds(in.kind, P, col)) stack.push_back(in.x); break;
         case I_SPLIT: stack.push_back(in.y); stack.push_back(in.x); break;
+        case I_SAVE: stack.push_back(in.x); break;
       }
     }
   }
 
+  // P carries P_ADV for the must-advance start states (sre: `state->must_advance && ptr == state->start` fails the SUCCESS
+  // opcode and backtracks, Modules/_sre/sre_lib.h SRE_OP_SUCCESS): only the closure at the start position is affected.
+  static const uint32_t P_ADV = 4;
   void closure(const std::vector<int>& kernel, uint32_t P, uint32_t col) {
     ++stamp; out_chars.clear(); out_match.clear(); cut = false;
-    for (int pc : kernel) { if (cut) break; addthread(pc, P, col); }
+    no_empty = (P & P_ADV) != 0;
+    for (int pc : kernel) { if (cut) break; addthread(pc, P & 3u, col); }
+    no_empty = false;
   }
 
   uint32_t get_state(uint32_t P, std::vector<int>& kernel) {
@@ -334,7 +354,7 @@ struct DfaBuilder {
     if (!ordered) { std::sort(kernel.begin(), kernel.end()); kernel.erase(std::unique(kernel.begin(), kernel.end()), kernel.end()); }
     bool need = false;
     for (int pc : kernel) if (needs_ctx[pc]) { need = true; break; }
-    if (!need) P = cf::P_OTHER;
+    if (!need) P = (P & P_ADV) | cf::P_OTHER;
     auto key = std::make_pair(P, kernel);
     auto it = ids.find(key);
     if (it != ids.end()) return it->second;
@@ -359,12 +379,16 @@ struct DfaBuilder {
   }
 
   // Build all states reachable from the given start kernels.  Returns start ids per context.
-  void build(const std::vector<int>& start_kernel, uint32_t start_state[4]) {
+  void build(const std::vector<int>& start_kernel, uint32_t start_state[4], uint32_t* start_adv = nullptr) {
     uint32_t ncols = C.ncls + 1;
     if (ordered) { accsets.assign(2, 0); accsets[1] = 1; }
     for (uint32_t P = 0; P < 4; ++P) {
       std::vector<int> k = start_kernel;
       start_state[P] = get_state(P, k);
+    }
+    if (start_adv) for (uint32_t P = 0; P < 4; ++P) {
+      std::vector<int> k = start_kernel;
+      start_adv[P] = get_state(P | P_ADV, k);
     }
     size_t done = 1;
     trans.assign(ncols, 0);   // DEAD row
@@ -395,7 +419,8 @@ struct DfaBuilder {
     }
   }
 
-  void emit(DfaOut& o, const uint32_t start_state[4]) const {
+  void emit(DfaOut& o, const uint32_t start_state[4], const uint32_t* start_adv = nullptr) const {
+    for (int i = 0; i < 4; ++i) o.start_adv[i] = start_adv ? start_adv[i] : 0;
     o.ascii_cls = C.ascii_cls; o.range_start = C.range_start; o.range_cls = C.range_cls;
     o.cls_ctx = C.cls_ctx; o.trans = trans; o.accsets = accsets;
     o.ncols = C.ncls + 1; o.nstates = (uint32_t)states.size(); o.W = W;
@@ -737,6 +762,7 @@ static bool nullable_no_assert(const Prog& prog, int start) {
     const Inst& in = prog.insts[p];
     if (in.op == I_MATCH) return true;
     if (in.op == I_SPLIT) { st.push_back(in.x); st.push_back(in.y); }
+    if (in.op == I_SAVE) st.push_back(in.x);
   }
   return false;
 }
@@ -757,10 +783,56 @@ static uint32_t min_len(const Prog& prog, int start) {
       case I_MATCH: return dist[p];
       case I_CHAR: relax(in.x, 1); break;
       case I_ASSERT: relax(in.x, 0); break;
+      case I_SAVE: relax(in.x, 0); break;
       case I_SPLIT: relax(in.x, 0); relax(in.y, 0); break;
     }
   }
   return 0xFFFFFFFFu;
+}
+
+// The instructions reachable from `start`, renumbered in discovery order, with per-rule set numbering.
+static void export_nfa(const Prog& prog, const Classes& C, int start, NfaOut& o) {
+  std::vector<int> id(prog.insts.size(), -1), order, st = {start};
+  while (!st.empty()) {
+    int p = st.back(); st.pop_back();
+    if (p < 0 || id[p] >= 0) continue;
+    id[p] = (int)order.size();
+    order.push_back(p);
+    const Inst& in = prog.insts[p];
+    if (in.op == I_SPLIT) { st.push_back(in.y); st.push_back(in.x); }
+    else if (in.op != I_MATCH) st.push_back(in.x);
+  }
+  std::map<int, uint32_t> setmap;
+  o.wpc = (C.ncls + 31) / 32;
+  o.ninst = (uint32_t)order.size();
+  o.start = 0;
+  o.ngroups = 0;
+  o.code.assign((size_t)o.ninst * 3, 0);
+  for (size_t k = 0; k < order.size(); ++k) {
+    const Inst& in = prog.insts[order[k]];
+    uint32_t arg = 0, x = in.x >= 0 ? (uint32_t)id[in.x] : 0, y = 0;
+    switch (in.op) {
+      case I_CHAR: {
+        auto it = setmap.find(in.set);
+        if (it == setmap.end()) {
+          uint32_t sid = (uint32_t)setmap.size();
+          it = setmap.insert({in.set, sid}).first;
+          o.setbits.resize((size_t)(sid + 1) * o.wpc, 0);
+          for (uint32_t c = 0; c < C.ncls; ++c) if (C.set_has[in.set][c]) o.setbits[(size_t)sid * o.wpc + (c >> 5)] |= 1u << (c & 31);
+        }
+        arg = it->second;
+        break;
+      }
+      case I_SPLIT: y = in.y >= 0 ? (uint32_t)id[in.y] : 0; break;
+      case I_ASSERT: arg = in.kind; break;
+      case I_SAVE: arg = in.kind; if (in.kind / 2 > o.ngroups) o.ngroups = in.kind / 2; break;
+      case I_MATCH: break;
+    }
+    o.code[3 * k] = (uint32_t)in.op | (arg << 8);
+    o.code[3 * k + 1] = x;
+    o.code[3 * k + 2] = y;
+  }
+  if (o.setbits.empty()) o.setbits.assign(o.wpc, 0);
 }
 
 }  // namespace
@@ -792,8 +864,10 @@ int compile(const std::vector<PatternIn>& pats, const std::vector<uint8_t>& want
   uint32_t W = (npat + 63) / 64;
   out->always_bits.assign(W, 0);
   for (uint32_t i = 0; i < npat; ++i) {
-    out->info[i].nullable_always = nullable_no_assert(prog, prog.start[i]);
     out->info[i].min_len_chars = min_len(prog, prog.start[i]);
+    // A substitution rule that can match "" (with or without assertions) is applied to every unit: its verdict bit only selects
+    // the units the substitution kernel visits, and "matches somewhere, possibly at the very end" is not worth a scan of its own.
+    out->info[i].nullable_always = nullable_no_assert(prog, prog.start[i]) || (want_ordered[i] && out->info[i].min_len_chars == 0);
     if (out->info[i].nullable_always) out->always_bits[i >> 6] |= 1ull << (i & 63);
   }
 
@@ -822,17 +896,20 @@ int compile(const std::vector<PatternIn>& pats, const std::vector<uint8_t>& want
     if (!want_ordered[i]) continue;
     DfaBuilder B(prog, C, true, npat, 60000);
     std::vector<int> k = {prog.start[i]};
-    uint32_t ss[4];
-    B.build(k, ss);
+    uint32_t ss[4], sa[4];
+    B.build(k, ss, sa);
     if (B.overflow) { if (err) *err = "ordered DFA too large for pattern " + std::to_string(i); return CF_E_TOO_LARGE; }
     DfaOut d;
-    B.emit(d, ss);
+    B.emit(d, ss, sa);
     out->ordered.push_back(std::move(d));
     std::vector<PatFilter> one(1);
     one[0] = pf[i];
     FilterOut fo;
     assign_buckets(one, fo, false);
     out->ordered_filter.push_back(fo);
+    NfaOut nfa;
+    export_nfa(prog, C, prog.start[i], nfa);
+    out->ordered_nfa.push_back(std::move(nfa));
   }
   return 0;
 }

@@ -18,7 +18,8 @@ namespace cfre {
 //   A_ALT    n child*                  ordered alternation (leftmost-first)
 //   A_REPEAT min max greedy child      max = 0xFFFFFFFF means unbounded
 //   A_ASSERT kind
-enum : uint32_t { A_EMPTY = 0, A_SET = 1, A_CAT = 2, A_ALT = 3, A_REPEAT = 4, A_ASSERT = 5 };
+//   A_GROUP  index child               capturing group (emitted for substitution rules only; index >= 1)
+enum : uint32_t { A_EMPTY = 0, A_SET = 1, A_CAT = 2, A_ALT = 3, A_REPEAT = 4, A_ASSERT = 5, A_GROUP = 6 };
 enum : uint32_t {
   AS_WORD_B = 1, AS_NOT_WORD_B = 2, AS_BEGIN_STRING = 3, AS_BEGIN_LINE = 4,
   AS_END_STRING = 5, AS_END_LINE = 6, AS_END_DOLLAR = 7
@@ -42,6 +43,7 @@ struct DfaOut {
   std::vector<uint64_t> accsets;      // naccs * W
   uint32_t ncols = 0, nstates = 0, W = 1;
   uint32_t start_state[4] = {0, 0, 0, 0};
+  uint32_t start_adv[4] = {0, 0, 0, 0};   // ordered DFAs: start states that do not accept a zero-length match (re.sub's must_advance)
 };
 
 struct FilterOut {
@@ -53,8 +55,17 @@ struct FilterOut {
   double byte_cost = 0;                 // expected candidates per byte under the byte-frequency prior
 };
 
+// The Thompson NFA of one substitution rule, for the capture pass (cf::pike_captures in scan_core.h): three words per
+// instruction {op | arg << 8, x, y}: N_CHAR (arg = set, x = next), N_SPLIT (x preferred, y), N_ASSERT (arg = kind, x),
+// N_SAVE (arg = slot, x), N_MATCH.  setbits[set * wpc + (cls >> 5)] bit (cls & 31): the set contains code-point class cls.
+struct NfaOut {
+  std::vector<uint32_t> code;
+  std::vector<uint32_t> setbits;
+  uint32_t ninst = 0, start = 0, wpc = 1, ngroups = 0;
+};
+
 struct PatternInfo {
-  bool nullable_always = false;   // matches the empty string with no assertion -> matches every unit
+  bool nullable_always = false;   // matches the empty string with no assertion (or: substitution rule that can match "") -> bit set for every unit
   uint32_t min_len_chars = 0;     // minimum match length in code points
 };
 
@@ -63,6 +74,7 @@ struct CompileOut {
   FilterOut filter;                     // prefilter for `search`
   std::vector<DfaOut> ordered;          // one leftmost-first DFA per pattern flagged `want_ordered`
   std::vector<FilterOut> ordered_filter;// per-ordered-pattern prefilter (own bucket 0)
+  std::vector<NfaOut> ordered_nfa;      // per-ordered-pattern NFA (group captures for replacement templates)
   std::vector<PatternInfo> info;
   std::vector<uint64_t> always_bits;    // W words: patterns that match every unit
 };

@@ -48,6 +48,7 @@ struct DfaTables {
   uint32_t ncols;
   uint32_t W;                   // u64 words per verdict bitmap
   uint32_t start_state[4];      // indexed by previous-character context
+  uint32_t start_adv[4];        // ordered DFAs only: the same, but a zero-length match at the start position does not count
 };
 
 // Decode one UTF-8 scalar (generalised: surrogates ED A0..BF xx are accepted, Python's
@@ -110,10 +111,13 @@ CF_HD uint32_t verify_search(const DfaTables& t, const uint8_t* s, uint64_t usta
 // bit 16 = "a match ends before this character".  Returns the match end (byte offset) or
 // UINT64_MAX when nothing matches at p.  This is Python's backtracking preference order
 // (plugins/regex_filter/search_replace.py:130 -> re.Pattern.sub).
+// `must_advance`: the match may not be empty (what `re.sub` asks for at the position right after an empty match:
+// Modules/_sre/sre.c pattern_subx `state.must_advance = (state.ptr == state.start)`); a lower-priority non-empty
+// alternative is then taken if there is one, exactly like sre's backtracking.
 CF_HD uint64_t match_first(const DfaTables& t, const uint8_t* s, uint64_t ustart, uint64_t uend,
-                           uint64_t p) {
+                           uint64_t p, bool must_advance = false) {
   uint32_t ctx = (p == ustart) ? (uint32_t)P_START : prev_context(t, s, ustart, p);
-  uint32_t S = t.start_state[ctx];
+  uint32_t S = must_advance ? t.start_adv[ctx] : t.start_state[ctx];
   uint64_t q = p, last = ~0ull;
   while (S != DEAD) {
     uint32_t col, len = 0;
@@ -126,6 +130,118 @@ CF_HD uint64_t match_first(const DfaTables& t, const uint8_t* s, uint64_t ustart
     q += len;
   }
   return last;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Capture pass for replacement templates with group references (`\\1`, `\\g<name>`): a Pike VM over the rule's Thompson NFA
+// (re_backend.h NfaOut), anchored at p — the start the ordered DFA found — with the DFA's own character classes, assertion
+// semantics (previous-character context + class of the next character) and priority order, so it finds the very match the
+// DFA found and, with it, the group spans Python's backtracking matcher reports for it (a group inside a repeat keeps the span
+// of its last participating iteration; a group that never took part stays unset -> "" in the template, Python >= 3.5).
+// One thread per NFA instruction and position at most: O(match length x NFA size), no backtracking.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { N_CHAR = 0, N_SPLIT = 1, N_ASSERT = 2, N_MATCH = 3, N_SAVE = 4 };
+static const uint32_t CAP_UNSET = 0xFFFFFFFFu;
+struct NfaView {
+  const uint32_t* code;       // 3 words per instruction
+  const uint32_t* setbits;
+  uint32_t ninst, start, wpc, nslots;   // nslots = 2 * (groups + 1); slots 0/1 = the whole match
+};
+CF_HD uint64_t pike_scratch_words(uint32_t ninst, uint32_t nslots) { return (uint64_t)ninst * (1 + 2 + 2ull * nslots + 6) + nslots; }
+
+CF_HD bool assert_holds(uint32_t kind, uint32_t P, uint32_t col, uint32_t eot_col, const uint8_t* cls_ctx) {
+  const bool eot = col == eot_col;
+  const bool nw = !eot && cls_ctx[col] == P_WORD, nnl = !eot && cls_ctx[col] == P_NL;
+  switch (kind) {
+    case 1: return (P == P_WORD) != nw;                                   // \b
+    case 2: if (P == P_START && eot) return false; return (P == P_WORD) == nw;   // \B (sre: never on an empty string)
+    case 3: return P == P_START;                                          // \A
+    case 4: return P == P_START || P == P_NL;                             // ^ (MULTILINE)
+    case 5: case 7: return eot;                                           // \Z
+    case 6: return eot || nnl;                                            // $ (MULTILINE)
+  }
+  return false;
+}
+
+// Threads of one position: pcs[k], caps[k * nslots ..].  `add` follows the epsilon edges from pc in priority order.
+struct PikeList { uint32_t* pcs; uint32_t* caps; uint32_t n; };
+CF_HD void pike_add(const DfaTables& t, const NfaView& N, PikeList& L, uint32_t pc0, uint32_t pos, uint32_t P, uint32_t col,
+                    uint32_t* cur, uint32_t* visited, uint32_t stamp, uint32_t* stack) {
+  uint32_t sp = 0;
+  stack[sp++] = pc0; stack[sp++] = CAP_UNSET;                 // {pc, CAP_UNSET} = explore, {slot, old value + marker} = restore
+  while (sp) {
+    const uint32_t b = stack[--sp], a = stack[--sp];
+    if (b != CAP_UNSET) { cur[a] = b == CAP_UNSET - 1 ? CAP_UNSET : b; continue; }      // restore a capture slot
+    if (visited[a] == stamp) continue;
+    visited[a] = stamp;
+    const uint32_t w = N.code[3 * a], op = w & 0xFF, arg = w >> 8, x = N.code[3 * a + 1], y = N.code[3 * a + 2];
+    switch (op) {
+      case N_CHAR: case N_MATCH: {
+        L.pcs[L.n] = a;
+        for (uint32_t k = 0; k < N.nslots; ++k) L.caps[(uint64_t)L.n * N.nslots + k] = cur[k];
+        ++L.n;
+        break;
+      }
+      case N_SPLIT: stack[sp++] = y; stack[sp++] = CAP_UNSET; stack[sp++] = x; stack[sp++] = CAP_UNSET; break;
+      case N_ASSERT: if (assert_holds(arg, P, col, t.ncols - 1, t.cls_ctx)) { stack[sp++] = x; stack[sp++] = CAP_UNSET; } break;
+      case N_SAVE:
+        stack[sp++] = arg; stack[sp++] = cur[arg] == CAP_UNSET ? CAP_UNSET - 1 : cur[arg];
+        cur[arg] = pos;
+        stack[sp++] = x; stack[sp++] = CAP_UNSET;
+        break;
+    }
+  }
+}
+
+// caps_out[0 .. nslots): byte offsets relative to the unit (CAP_UNSET = group did not take part).  Returns false when nothing
+// matches at p (cannot happen for a start the DFA accepted).  Offsets must fit 32 bits (units are < 4 GB).
+CF_HD bool pike_captures(const DfaTables& t, const NfaView& N, const uint8_t* s, uint64_t ustart, uint64_t uend, uint64_t p,
+                         bool must_advance, uint32_t* scratch, uint32_t* caps_out) {
+  uint32_t* visited = scratch;
+  PikeList A, B;
+  A.pcs = visited + N.ninst; B.pcs = A.pcs + N.ninst;
+  A.caps = B.pcs + N.ninst; B.caps = A.caps + (uint64_t)N.ninst * N.nslots;
+  uint32_t* stack = B.caps + (uint64_t)N.ninst * N.nslots;
+  uint32_t* cur = stack + 6ull * N.ninst;
+  for (uint32_t k = 0; k < N.ninst; ++k) visited[k] = 0;
+  for (uint32_t k = 0; k < N.nslots; ++k) cur[k] = CAP_UNSET;
+  uint32_t stamp = 0;
+  uint32_t P = (p == ustart) ? (uint32_t)P_START : prev_context(t, s, ustart, p);
+  uint64_t q = p;
+  uint32_t len = 0;
+  uint32_t col = q >= uend ? t.ncols - 1 : classify(t, utf8_decode(s, q, uend, &len));
+  A.n = 0;
+  cur[0] = (uint32_t)(p - ustart);
+  pike_add(t, N, A, N.start, (uint32_t)(q - ustart), P, col, cur, visited, ++stamp, stack);
+  bool matched = false;
+  while (A.n) {
+    const uint64_t q2 = q + len;
+    uint32_t len2 = 0, col2 = t.ncols - 1, P2 = P_OTHER;
+    if (col != t.ncols - 1) {
+      P2 = t.cls_ctx[col];
+      if (q2 < uend) col2 = classify(t, utf8_decode(s, q2, uend, &len2));
+    }
+    B.n = 0;
+    ++stamp;
+    for (uint32_t k = 0; k < A.n; ++k) {
+      const uint32_t pc = A.pcs[k], w = N.code[3 * pc], op = w & 0xFF;
+      if (op == N_MATCH) {
+        if (must_advance && q == p) continue;               // sre: an empty match at the start fails SUCCESS and backtracks
+        for (uint32_t j = 0; j < N.nslots; ++j) caps_out[j] = A.caps[(uint64_t)k * N.nslots + j];
+        caps_out[1] = (uint32_t)(q - ustart);
+        matched = true;
+        break;                                              // lower-priority threads are cut
+      }
+      if (col != t.ncols - 1 && ((N.setbits[(uint64_t)(w >> 8) * N.wpc + (col >> 5)] >> (col & 31)) & 1u)) {
+        for (uint32_t j = 0; j < N.nslots; ++j) cur[j] = A.caps[(uint64_t)k * N.nslots + j];
+        pike_add(t, N, B, N.code[3 * pc + 1], (uint32_t)(q2 - ustart), P2, col2, cur, visited, stamp, stack);
+      }
+    }
+    if (col == t.ncols - 1) break;
+    PikeList T = A; A = B; B = T;
+    q = q2; len = len2; P = P2; col = col2;
+  }
+  return matched;
 }
 
 // Prefilter.  Five 5-bit fields per byte value, five pattern buckets per field:

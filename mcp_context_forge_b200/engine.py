@@ -107,12 +107,20 @@ class Program:
         """`word in unit` existence bit (deny_filter)."""
         return self._add(fe.literal_ast(word), N.CF_PAT_SEARCH)
 
-    def add_sub(self, pattern: str, flags: int, replacement: str) -> int:
-        """One regex_filter rule: `re.compile(pattern, flags).sub(replacement, unit)` with a literal
-        replacement (template already expanded by the caller)."""
-        idx = self._add(fe.compile_ast(pattern, flags, "sub"), N.CF_PAT_ORDERED)
-        r = encode_unit(replacement)
-        self._check_b(self.lib.cf_builder_set_replacement(self.b, idx, r, len(r)), "set_replacement")
+    def add_sub(self, pattern: str, flags: int, replacement) -> int:
+        """One regex_filter rule: `re.compile(pattern, flags).sub(replacement, unit)`.  `replacement` is the EXPANDED template:
+        a literal string, or the flat list of literal strings and group indices `regex_frontend.template_parts` returns."""
+        if isinstance(replacement, str):
+            replacement = [replacement] if replacement else []
+        refs = any(isinstance(p, int) for p in replacement)
+        idx = self._add(fe.compile_ast(pattern, flags, "sub", groups=refs), N.CF_PAT_ORDERED)
+        if refs:
+            lit, parts = fe.encode_template(replacement)
+            pa = np.asarray(parts, dtype=np.uint32)
+            self._check_b(self.lib.cf_builder_set_template(self.b, idx, lit, len(lit), pa.ctypes.data, len(pa) // 3), "set_template")
+        else:
+            r = encode_unit("".join(replacement))
+            self._check_b(self.lib.cf_builder_set_replacement(self.b, idx, r, len(r)), "set_replacement")
         self.n_ordered += 1
         return idx
 
@@ -138,6 +146,24 @@ class Program:
             if self.h:
                 self.lib.cf_free_prog(self.h)
             self.lib.cf_builder_free(self.b)
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host memory (cf_host_alloc) as a numpy uint8 array: the D2H of the produced texts runs at the PCIe rate
+    instead of through the driver's bounce buffer."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx = ctx
+        self.p = c_void_p()
+        with ctx.lock:
+            ctx.check(ctx.lib.cf_host_alloc(ctx.h, nbytes, byref(self.p)), "cf_host_alloc")
+        self.array = np.ctypeslib.as_array(ctypes.cast(self.p, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,))
+
+    def __del__(self):
+        try:
+            self.ctx.lib.cf_host_free(self.ctx.h, self.p)
         except Exception:
             pass
 
@@ -245,11 +271,13 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
     W = prog.words if prog is not None else 1
     full = np.zeros(n * W, dtype=np.uint64) if want_full_bitmaps else None
     need = c_uint64(0)
-    # the output buffer lives with the Batch and only grows (a fresh np.empty per call costs a page fault per 4 KiB of output)
-    out = getattr(batch, "_out", None)
-    cap = max(nbytes, 1 << 12) if out is None else len(out)
-    if out is None or len(out) < min(nbytes, 1 << 12):
-        out = batch._out = np.empty(cap, dtype=np.uint8)
+    # the output buffer lives with the Batch, is page-locked and only grows.  NOTE: the returned `out` is a view of it — it is
+    # overwritten by the next run_batch on this Batch (callers slice/copy what they keep).
+    pin = getattr(batch, "_out_pin", None)
+    cap = max(nbytes, 1 << 12) if pin is None else len(pin.array)
+    if pin is None:
+        pin = batch._out_pin = PinnedBuffer(ctx, cap)
+    out = pin.array
     if stream is None:                                   # resident run: the batch already holds these units
         sp = None
     else:
@@ -259,7 +287,10 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
         us = np.ascontiguousarray(unit_stages, dtype=np.uint8)
     while True:
         if len(out) < cap:
-            out = batch._out = np.empty(cap, dtype=np.uint8)
+            batch._out_pin = None                          # free before growing
+            pin = batch._out_pin = PinnedBuffer(ctx, cap + cap // 4)
+            out = pin.array
+            cap = len(out)
         with ctx.lock:
             rc = ctx.lib.cf_run_batch(ctx.h, prog.h if prog is not None else None, batch.h, sp, nbytes, offsets.ctypes.data, n, stage_mask,
                                       us.ctypes.data if us is not None else None, toon_flags, mask_max_depth, verdicts.ctypes.data,

@@ -30,7 +30,7 @@ from . import engine
 from ._native import CF_STAGE_SCAN, CF_STAGE_SUB, CF_STAGE_TOON, CF_V_REWRITTEN, CF_V_TOON
 from .framework import (GlobalContext, OnError, PluginContext, PluginError, PluginErrorModel, PluginManager, PluginMode, PluginResult,
                         PluginViolationError)
-from .cpex_compat.framework import _effective_mode, _hook_name, payload_matches  # same helpers the sequential executor uses
+from .cpex_compat.framework import _effective_mode, _hook_name, fast_construct, payload_matches  # same helpers the sequential executor uses
 
 logger = logging.getLogger(__name__)
 
@@ -49,6 +49,7 @@ class _Chain:
         self.hook = hook
         self.refs = refs
         self.prog = engine.Program()
+        self.uuids = [h.plugin_ref.uuid for h in refs]   # PluginRef.uuid formats a UUID on every access
         self.member = {}                      # ref.uuid -> plugin speaks the protocol for this hook
         self.toon_flags = 0
         n_pat = 0
@@ -157,10 +158,10 @@ class BatchedPluginManager(PluginManager):
         hook = chain.hook
         for payload, gctx, _lc, _vae, _fut in wave:
             plan = {}
-            for href in chain.refs:
-                ref = href.plugin_ref
-                if not chain.member[ref.uuid]:
+            for href, uid in zip(chain.refs, chain.uuids):
+                if not chain.member[uid]:
                     continue
+                ref = href.plugin_ref
                 if ref.conditions and not payload_matches(payload, hook, ref.conditions, gctx):
                     continue
                 plug = ref.plugin
@@ -178,7 +179,7 @@ class BatchedPluginManager(PluginManager):
                     else:
                         stages[k] |= st
                     idx.append(k)
-                plan[ref.uuid] = (us, idx)
+                plan[uid] = (us, idx)
             plans.append(plan)
         return units, stages, plans
 
@@ -253,18 +254,18 @@ class BatchedPluginManager(PluginManager):
         metadata: dict[str, Any] = {}
         retry_delay_ms = 0
         fail_all = bool(self._config and self._config.plugin_settings.fail_on_plugin_error)
-        for href in chain.refs:
+        for href, uid in zip(chain.refs, chain.uuids):
             ref = href.plugin_ref
             mode, on_error = _effective_mode(ref)
             if mode == PluginMode.DISABLED:
                 continue
             if ref.conditions and not payload_matches(current, hook, ref.conditions, global_context):
                 continue
-            key = global_context.request_id + ref.uuid
-            ctx = (local_contexts or {}).get(key) or PluginContext.model_construct(state={}, global_context=global_context, metadata={})
+            key = global_context.request_id + uid
+            ctx = (local_contexts or {}).get(key) or fast_construct(PluginContext, {"state": {}, "global_context": global_context, "metadata": {}})
             contexts[key] = ctx
             try:
-                spec = plan.get(ref.uuid)
+                spec = plan.get(uid)
                 result = None
                 if spec is not None:
                     us, idx = spec
@@ -306,5 +307,5 @@ class BatchedPluginManager(PluginManager):
                     return (PluginResult(continue_processing=False, modified_payload=current if changed else None, violation=result.violation, metadata=metadata,
                                          retry_delay_ms=retry_delay_ms), contexts)
                 logger.warning("Plugin %s (%s) reported a violation in %s; continuing", ref.name, mode.value, hook)
-        return (PluginResult.model_construct(continue_processing=True, modified_payload=current if changed else None, violation=None, metadata=metadata,
-                                             retry_delay_ms=retry_delay_ms), contexts)
+        return (fast_construct(PluginResult, {"continue_processing": True, "modified_payload": current if changed else None, "violation": None,
+                                              "metadata": metadata, "retry_delay_ms": retry_delay_ms}), contexts)

@@ -20,7 +20,8 @@ from .. import engine
 from ..batching import GpuBatcher
 from ..framework import (Plugin, PluginConfig, PluginContext, PromptPosthookPayload, PromptPosthookResult, PromptPrehookPayload, PromptPrehookResult,
                          ToolPostInvokePayload, ToolPostInvokeResult, ToolPreInvokePayload, ToolPreInvokeResult)
-from ..regex_frontend import UnsupportedPattern
+from ..cpex_compat.framework import fast_copy
+from ..regex_frontend import UnsupportedPattern, template_parts  # noqa: F401
 
 
 class SearchReplace(BaseModel):
@@ -32,20 +33,10 @@ class SearchReplaceConfig(BaseModel):
     words: list[SearchReplace]
 
 
-def literal_replacement(template: str, pattern: "re.Pattern[str]") -> str:
-    """Expand a `re.sub` replacement template that has no group references to its literal text
-    (escape processing by sre's own template parser).  Group references need capture positions,
-    which the DFA engine does not produce -> UnsupportedPattern."""
-    parts = _sre_parser.parse_template(template, pattern)
-    if isinstance(parts, tuple):
-        # Python 3.11 (the reference supports >= 3.11): (groups, literals) with None where a group goes
-        groups, literals = parts
-        if groups:
-            raise UnsupportedPattern(f"replacement template {template!r} references groups")
-        return "".join(x for x in literals if x is not None)
-    if any(not isinstance(p, str) for p in parts):                    # Python 3.12+: flat [str | group index, ...]
-        raise UnsupportedPattern(f"replacement template {template!r} references groups")
-    return "".join(parts)
+def replacement_parts(template: str, pattern: "re.Pattern[str]"):
+    """The `re.sub` replacement template of a rule, expanded by sre's own template parser: literal strings and group indices
+    (group references are resolved on the GPU by a capture pass over the match, csrc/scan_core.h pike_captures)."""
+    return template_parts(template, pattern)
 
 
 class SearchReplacePlugin(Plugin):
@@ -59,8 +50,7 @@ class SearchReplacePlugin(Plugin):
                 compiled = re.compile(word.search)
             except re.error:
                 continue                                    # reference :73-75
-            repl = literal_replacement(word.replace, compiled)
-            bit = self._prog.add_sub(word.search, 0, repl)
+            bit = self._prog.add_sub(word.search, 0, replacement_parts(word.replace, compiled))
             self._rule_mask |= 1 << bit
         if self._rule_mask:
             self._prog.compile_host()
@@ -81,7 +71,7 @@ class SearchReplacePlugin(Plugin):
                 compiled = re.compile(word.search)
             except re.error:
                 continue
-            self._chain_mask |= 1 << prog.add_sub(word.search, 0, literal_replacement(word.replace, compiled))
+            self._chain_mask |= 1 << prog.add_sub(word.search, 0, replacement_parts(word.replace, compiled))
         return True
 
     def chain_stage(self) -> int:
@@ -105,13 +95,13 @@ class SearchReplacePlugin(Plugin):
             r = payload.result
             if r and isinstance(r, dict):
                 it = iter(new)
-                payload = payload.model_copy(update={"result": {k: (next(it) if isinstance(v, str) else v) for k, v in r.items()}})
+                payload = fast_copy(payload, {"result": {k: (next(it) if isinstance(v, str) else v) for k, v in r.items()}})
             elif r and isinstance(r, str):
-                payload = payload.model_copy(update={"result": new[0]})
+                payload = fast_copy(payload, {"result": new[0]})
             return ToolPostInvokeResult(modified_payload=payload)
         if payload.args:
             it = iter(new)
-            payload = payload.model_copy(update={"args": {k: (next(it) if isinstance(v, str) else v) for k, v in payload.args.items()}})
+            payload = fast_copy(payload, {"args": {k: (next(it) if isinstance(v, str) else v) for k, v in payload.args.items()}})
         return (PromptPrehookResult if hook == "prompt_pre_fetch" else ToolPreInvokeResult)(modified_payload=payload)
 
     async def _apply(self, values: List[str]) -> List[str]:

@@ -25,10 +25,10 @@ import re._compiler as _compiler  # type: ignore[import]
 import re._constants as _k  # type: ignore[import]
 import re._parser as _parser  # type: ignore[import]
 from functools import lru_cache
-from typing import List, Sequence, Tuple
+from typing import List, Sequence, Tuple, Union
 
 # AST opcodes — keep in sync with csrc/re_backend.h
-A_EMPTY, A_SET, A_CAT, A_ALT, A_REPEAT, A_ASSERT = 0, 1, 2, 3, 4, 5
+A_EMPTY, A_SET, A_CAT, A_ALT, A_REPEAT, A_ASSERT, A_GROUP = 0, 1, 2, 3, 4, 5, 6
 AS_WORD_B, AS_NOT_WORD_B, AS_BEGIN_STRING, AS_BEGIN_LINE, AS_END_STRING, AS_END_LINE, AS_END_DOLLAR = 1, 2, 3, 4, 5, 6, 7
 REPEAT_INF = 0xFFFFFFFF
 MAX_CP = 0x10FFFF
@@ -102,15 +102,15 @@ def _combine_flags(flags: int, add: int, delete: int) -> int:
     return (flags | add) & ~delete
 
 
-def _emit_seq(out: List[int], items: Sequence, flags: int, mode: str, tail: bool) -> None:
+def _emit_seq(out: List[int], items: Sequence, flags: int, mode: str, tail: bool, groups: bool = False) -> None:
     items = list(items)
     out.append(A_CAT)
     out.append(len(items))
     for i, node in enumerate(items):
-        _emit_node(out, node, flags, mode, tail and i == len(items) - 1)
+        _emit_node(out, node, flags, mode, tail and i == len(items) - 1, groups)
 
 
-def _emit_node(out: List[int], node, flags: int, mode: str, tail: bool) -> None:
+def _emit_node(out: List[int], node, flags: int, mode: str, tail: bool, groups: bool = False) -> None:
     op, av = node
     if op in (_k.LITERAL, _k.NOT_LITERAL, _k.IN, _k.ANY):
         ranges = _atom_ranges(node, flags)
@@ -120,18 +120,21 @@ def _emit_node(out: List[int], node, flags: int, mode: str, tail: bool) -> None:
         out.append(A_ALT)
         out.append(len(alts))
         for alt in alts:
-            _emit_seq(out, alt, flags, mode, tail)
+            _emit_seq(out, alt, flags, mode, tail, groups)
     elif op is _k.SUBPATTERN:
         _group, add, delete, sub = av
-        _emit_seq(out, sub, _combine_flags(flags, add, delete), mode, tail)
+        if groups and _group is not None:
+            out.extend((A_GROUP, _group))          # capture spans for replacement templates with group references
+        _emit_seq(out, sub, _combine_flags(flags, add, delete), mode, tail, groups)
     elif op in (_k.MAX_REPEAT, _k.MIN_REPEAT):
         # sre ends an unbounded loop on a zero-width iteration; the priority closure of the ordered automaton would go on into
         # the body's lower-priority branch instead (r'(?:c)+(?:(?:s)*?)+' and friends).  Existence (search) is unaffected.
-        if mode == "sub" and av[1] == _k.MAXREPEAT and av[2].getwidth()[0] == 0:
-            raise UnsupportedPattern("unbounded repeat of a sub-pattern that can match the empty string (substitution mode)")
+        # Bounded loops share the rule (an empty iteration ends the loop once `min` is reached), which decides extents and group spans.
+        if mode == "sub" and av[1] > 1 and av[2].getwidth()[0] == 0:
+            raise UnsupportedPattern("repeat of a sub-pattern that can match the empty string (substitution mode)")
         mn, mx, sub = av
         out.extend((A_REPEAT, mn, REPEAT_INF if mx == _k.MAXREPEAT else mx, 1 if op is _k.MAX_REPEAT else 0))
-        _emit_seq(out, sub, flags, mode, False)
+        _emit_seq(out, sub, flags, mode, False, groups)
     elif op is _k.AT:
         if flags & _k.SRE_FLAG_LOCALE:
             raise UnsupportedPattern("LOCALE flag")
@@ -171,7 +174,7 @@ def _emit_node(out: List[int], node, flags: int, mode: str, tail: bool) -> None:
         raise UnsupportedPattern(f"sre node {op}")
 
 
-def compile_ast(pattern: str, flags: int = 0, mode: str = "search") -> List[int]:
+def compile_ast(pattern: str, flags: int = 0, mode: str = "search", groups: bool = False) -> List[int]:
     """Parse `pattern` exactly as `re.compile(pattern, flags)` would and serialize it.
 
     mode: "search" (existence, any match)   or   "sub" (leftmost-first extents).
@@ -187,7 +190,7 @@ def compile_ast(pattern: str, flags: int = 0, mode: str = "search") -> List[int]
     if not (final_flags & _k.SRE_FLAG_ASCII):
         final_flags |= _k.SRE_FLAG_UNICODE
     out: List[int] = []
-    _emit_seq(out, parsed, final_flags, mode, True)
+    _emit_seq(out, parsed, final_flags, mode, True, groups)
     return out
 
 
@@ -197,3 +200,31 @@ def literal_ast(text: str) -> List[int]:
     for ch in text:
         out.extend((A_SET, 1, ord(ch), ord(ch)))
     return out
+
+
+def template_parts(template: str, pattern: "re.Pattern[str]") -> List[Union[str, int]]:
+    """A `re.sub` replacement template as a flat list of literal strings and group indices, parsed by sre's own template parser
+    (escape processing, `\\1`, `\\g<name>`, `\\g<0>`; bad templates raise `re.error` exactly like `pattern.sub` would)."""
+    parts = _parser.parse_template(template, pattern)
+    if isinstance(parts, tuple):
+        # Python 3.11 (the reference supports >= 3.11): (groups, literals) — literals[i] is None where groups say (i, group)
+        groups, literals = parts
+        lits = list(literals)
+        for i, g in groups:
+            lits[i] = g
+        parts = lits
+    return [p for p in parts if p is not None and p != ""]
+
+
+def encode_template(parts: Sequence[Union[str, int]]):
+    """-> (literal bytes, uint32 triples {kind, a, b}) for cf_builder_set_template."""
+    lit = bytearray()
+    out: List[int] = []
+    for p in parts:
+        if isinstance(p, int):
+            out.extend((1, p, 0))
+        else:
+            b = p.encode("utf-8", "surrogatepass")
+            out.extend((0, len(lit), len(b)))
+            lit += b
+    return bytes(lit), out

@@ -20,7 +20,7 @@ static cf::DfaTables tables_of(const cfre::DfaOut& d) {
   t.nranges = (uint32_t)d.range_start.size();
   t.ncols = d.ncols;
   t.W = d.W;
-  for (int i = 0; i < 4; ++i) t.start_state[i] = d.start_state[i];
+  for (int i = 0; i < 4; ++i) { t.start_state[i] = d.start_state[i]; t.start_adv[i] = d.start_adv[i]; }
   return t;
 }
 
@@ -85,6 +85,42 @@ int cfh_sub(cf_builder* b, uint32_t ordered_index, const uint8_t* unit, uint64_t
     if (o + k <= cap) memcpy(out + o, p, k);
     o += k;
   };
+  // the replacement of one match: the literal, or the template with this match's group texts (the same cf::pike_captures the
+  // kernel's lane 0 runs)
+  const std::vector<uint32_t>& tm = b->tmpl[pat];
+  const cfre::NfaOut& nf = b->out.ordered_nfa[ordered_index];
+  cf::NfaView nv;
+  nv.code = nf.code.data(); nv.setbits = nf.setbits.data(); nv.ninst = nf.ninst; nv.start = nf.start; nv.wpc = nf.wpc; nv.nslots = 2 * (nf.ngroups + 1);
+  std::vector<uint32_t> pike(cf::pike_scratch_words(nv.ninst, nv.nslots)), caps(nv.nslots);
+  auto put_repl = [&](uint64_t sp, bool adv) {
+    if (tm.empty()) { put(repl.data(), repl.size()); return; }
+    for (auto& c : caps) c = cf::CAP_UNSET;
+    cf::pike_captures(t, nv, s, 0, len, sp, adv, pike.data(), caps.data());
+    for (size_t k = 0; k + 2 < tm.size(); k += 3) {
+      if (tm[k] == 0) put(repl.data() + tm[k + 1], tm[k + 2]);
+      else if (caps[2 * tm[k + 1]] != cf::CAP_UNSET && caps[2 * tm[k + 1] + 1] != cf::CAP_UNSET && caps[2 * tm[k + 1] + 1] >= caps[2 * tm[k + 1]])
+        put(s + caps[2 * tm[k + 1]], caps[2 * tm[k + 1] + 1] - caps[2 * tm[k + 1]]);
+    }
+  };
+  if (b->out.info[pat].min_len_chars == 0) {
+    // a rule that can match "": the sequential statement of sub_kernel's nullable branch (= sre's pattern_subx loop)
+    bool adv = false;
+    for (uint64_t sp = 0; sp <= len;) {
+      if (sp < len && (s[sp] & 0xC0) == 0x80) { ++sp; continue; }
+      uint64_t e = cf::match_first(t, s, 0, len, sp, adv);
+      if (e == ~0ull) { adv = false; ++sp; continue; }
+      put(s + cur, sp - cur);
+      put_repl(sp, adv);
+      ++nm;
+      cur = e;
+      adv = (e == sp);
+      sp = e;            // after an empty match the same position is tried again with must_advance
+    }
+    put(s + cur, len - cur);
+    *out_len = o;
+    if (n_matches) *n_matches = nm;
+    return o <= cap ? CF_OK : CF_E_CAPACITY;
+  }
   uint32_t acc = 0;
   for (int64_t p = -(int64_t)cf::F_LOOKBACK; p < (int64_t)len + (int64_t)cf::F_START_OFF; ++p) {
     acc = cf::filter_step(acc, E[s[p]]);
@@ -96,7 +132,7 @@ int cfh_sub(cf_builder* b, uint32_t ordered_index, const uint8_t* unit, uint64_t
     uint64_t e = cf::match_first(t, s, 0, len, (uint64_t)start);
     if (e == ~0ull) continue;
     put(s + cur, (uint64_t)start - cur);
-    put(repl.data(), repl.size());
+    put_repl((uint64_t)start, false);
     cur = e;
     ++nm;
   }

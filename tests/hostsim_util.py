@@ -53,14 +53,20 @@ class HostProgram:
         idx = ctypes.c_uint32()
         rc = self.L.cf_builder_add_pattern(self.b, a.ctypes.data_as(ctypes.c_void_p), len(a), 1 if ordered else 0, ctypes.byref(idx))
         assert rc == 0, self.err()
-        if ordered:
+        if ordered and isinstance(repl, list):            # template parts: literal strings and group indices
+            lit, parts = self.fe.encode_template(repl)
+            pa = np.array(parts, dtype=np.uint32)
+            rc = self.L.cf_builder_set_template(self.b, idx, lit, len(lit), pa.ctypes.data_as(ctypes.c_void_p), len(pa) // 3)
+            assert rc == 0, self.err()
+        elif ordered:
             r = (repl or "").encode("utf-8", "surrogatepass")
             assert self.L.cf_builder_set_replacement(self.b, idx, r, len(r)) == 0
         self.n += 1
         return idx.value
 
     def add(self, pattern, flags=0, ordered=False, repl=None):
-        return self.add_ast(self.fe.compile_ast(pattern, flags, "sub" if ordered else "search"), ordered, repl)
+        groups = isinstance(repl, list) and any(isinstance(p, int) for p in repl)
+        return self.add_ast(self.fe.compile_ast(pattern, flags, "sub" if ordered else "search", groups=groups), ordered, repl)
 
     def err(self):
         return self.L.cf_builder_last_error(self.b).decode()

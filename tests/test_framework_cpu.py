@@ -138,8 +138,14 @@ def test_gpu_plugins_construct_and_reject_unsupported():
 
     p = SearchReplacePlugin(fw.PluginConfig(name="a", kind="x", config={"words": [{"search": "crap", "replace": "crud"}, {"search": "(bad", "replace": "x"}, {"search": "crud", "replace": r"y\\n"}]}))
     assert bin(p._rule_mask).count("1") == 2          # the invalid pattern is skipped like the reference does
+    g = SearchReplacePlugin(fw.PluginConfig(name="a", kind="x", config={"words": [{"search": "(a)b", "replace": r"\1"}, {"search": "x*", "replace": "-"}]}))
+    assert bin(g._rule_mask).count("1") == 2          # group references and empty matches are part of the engine
     with pytest.raises(UnsupportedPattern):
-        SearchReplacePlugin(fw.PluginConfig(name="a", kind="x", config={"words": [{"search": "(a)b", "replace": r"\1"}]}))
+        SearchReplacePlugin(fw.PluginConfig(name="a", kind="x", config={"words": [{"search": r"(a)\1", "replace": "x"}]}))      # back-reference in the pattern
+    with pytest.raises(UnsupportedPattern):
+        SearchReplacePlugin(fw.PluginConfig(name="a", kind="x", config={"words": [{"search": r"(?:a?){2}", "replace": "x"}]}))   # repeat of a nullable body
+    with pytest.raises(re.error):
+        SearchReplacePlugin(fw.PluginConfig(name="a", kind="x", config={"words": [{"search": "(a)b", "replace": r"\2"}]}))       # bad template: as pattern.sub raises
     with pytest.raises(UnsupportedPattern):
         HarmfulContentDetectorPlugin(fw.PluginConfig(name="a", kind="x", config={"categories": {"c": [r"(?<=x)y"]}}))
     with pytest.raises(re.error):

@@ -38,6 +38,24 @@ def test_regex_filter_golden(gold):
     assert n >= 200
 
 
+def test_regex_filter_templates_golden():
+    """Rules that can match "" and templates with group references (the reference hands `replace` to `pattern.sub` as is)."""
+    with open(os.path.join(GOLD, "regex_filter_templates.json"), encoding="utf-8") as f:
+        blocks = json.load(f)
+    n = 0
+    for block in blocks:
+        rules = ref.regex_compile_rules(block["words"])
+        for c in block["cases"]:
+            if c["hook"] == "tool_pre_invoke":
+                assert (ref.regex_apply_dict(rules, c["args"]) if c["args"] else c["args"]) == c["out_args"]
+            else:
+                res = c["result"]
+                got = ref.regex_apply_dict(rules, res) if res and isinstance(res, dict) else ref.regex_apply_str(rules, res) if res and isinstance(res, str) else res
+                assert got == c["out_result"]
+            n += 1
+    assert n >= 300
+
+
 def test_deny_filter_golden(gold):
     n = 0
     for block in gold["deny_filter"]:

@@ -30,8 +30,16 @@ def gold():
         return json.load(f)
 
 
-def test_regex_filter_matches_reference_golden(gold):
-    for block in gold["regex_filter"]:
+def _templates_gold():
+    with open(os.path.join(GOLD, "regex_filter_templates.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("which", ["plain", "templates"])
+def test_regex_filter_matches_reference_golden(gold, which):
+    """`templates`: rules that can match "" and replacement templates with group references (tests/golden/regex_filter_templates.json,
+    recorded from the reference's plugin file)."""
+    for block in (gold["regex_filter"] if which == "plain" else _templates_gold()):
         plug = SearchReplacePlugin(fw.PluginConfig(name="rf", kind="x", hooks=["tool_pre_invoke", "tool_post_invoke"], config={"words": block["words"]}))
 
         async def all_cases():
@@ -99,6 +107,27 @@ def test_sub_engine_vs_oracle_fuzz_and_sizes():
         bad = [(u[:80], g[:80], e[:80]) for u, g, e in zip(units, got, exp) if g != e]
         assert not bad, (rules, bad[:2])
     assert GpuBatcher.get().launches > 0
+
+
+def test_sub_engine_empty_matches_and_group_templates_fuzz():
+    """The substitution kernel's nullable branch (every position a candidate, must_advance after an empty match) and the capture
+    pass (Pike VM on lane 0) against CPython `re.sub`, on short fuzz texts and on long units (window boundaries, many matches)."""
+    from test_regex_engine_cpu import GROUP_RULES, NULLABLE_RULES, rand_text
+    from mcp_context_forge_b200 import synth
+
+    rng = random.Random(31)
+    rule_sets = [[(p, t)] for p, f, t in GROUP_RULES if f == 0] + [[(p, r.replace("\\", "\\\\"))] for p, f, r in NULLABLE_RULES if f == 0]
+    rule_sets += [[(r"(\w+)@(\w+)", r"\2 at \1"), (r"x*", "-"), (r"(-)(-)?", r"\2\1")], [(r"\b", "|"), (r"(\|)(\w)", r"\2\1")]]
+    for rules in rule_sets:
+        words = [{"search": s, "replace": r} for s, r in rules]
+        plug = SearchReplacePlugin(fw.PluginConfig(name="rf", kind="x", config={"words": words}))
+        comp = ref.regex_compile_rules(words)
+        units = [rand_text(rng, rng.randint(0, 30)) for _ in range(300)]
+        units += ["", "x", "abxd", "a" * 700 + "b", "xy" * 400, synth.payload("C", 6000, seed=7), "user@host " * 200, "é日" * 300]
+        got = run(plug._apply(units))
+        exp = [ref.regex_apply_str(comp, u) for u in units]
+        bad = [(u[:60], g[:80], e[:80]) for u, g, e in zip(units, got, exp) if g != e]
+        assert not bad, (rules, bad[:2])
 
 
 def test_chain_through_plugin_manager_yaml(tmp_path):

@@ -136,10 +136,71 @@ def test_unsupported_and_invalid():
         compile_ast(r"(unclosed")
     with pytest.raises(UnsupportedPattern):
         compile_ast(r"a$b")
+    with pytest.raises(UnsupportedPattern):
+        compile_ast(r"(?:a*)*b", 0, "sub")     # unbounded repeat of a nullable body: sre's empty-iteration rule is not expressible
+
+
+NULLABLE_RULES = [
+    (r"x*", 0, "-"), (r"x*?", 0, "-"), (r"", 0, "·"), (r"\b", 0, "|"), (r"^", re.M, "> "), (r"$", re.M, ";"), (r"[ \t]*$", re.M, "!"), (r"\s*\Z", 0, ""), (r"^\s*", 0, ""),
+    (r"a?", 0, "<>"), (r"a??", 0, "[]"), (r"(?:ab)?", 0, "é"), (r"\B", 0, "_"), (r"x*|y", 0, "#"), (r"|x", 0, "#"), (r"x|", 0, "#"), (r"\d*", 0, "N"),
+    (r"(?:x|xy)?", 0, "Q"), (r"\Z", 0, "END"), (r"\A\s*", 0, "^"), (r"[ \t]*(?:\n|\Z)", 0, "/"), (r"k*\b", re.I, "."), (r"\w{0,2}", 0, "w"),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(NULLABLE_RULES)))
+def test_sub_rules_that_can_match_the_empty_string(idx):
+    """`re.sub` with empty matches (Python >= 3.7: an empty match adjacent to a previous match is replaced; after an empty match
+    the same position is retried with must_advance, Modules/_sre/sre.c pattern_subx)."""
+    pat, flags, repl = NULLABLE_RULES[idx]
+    rng = random.Random(900 + idx)
     hp = HostProgram()
-    hp.add(r"x*", 0, ordered=True, repl="-")
+    hp.add(pat, flags, ordered=True, repl=repl)
+    c = re.compile(pat, flags)
+    frag = ["x", "xx", "y", "a", "ab", "b", " ", "  ", "\n", "\t", "1", "23", "k", "K", "é", "日", "-", "_", "xy", "\n\n", " \n"]
+    units = ["", "x", "abxd", "xxx", "\n", "a\n", "\na", " ", "ab ab"] + ["".join(rng.choice(frag) for _ in range(rng.randint(0, 14))) for _ in range(700)]
+    for u in units:
+        got, n = hp.sub(0, u)
+        exp, en = c.subn(repl.replace("\\", "\\\\"), u)
+        assert got == exp and n == en, (pat, u, got, exp)
+
+
+GROUP_RULES = [
+    (r"(\w+)@(\w+)", 0, r"\2 at \1"), (r"(a)(b)?", 0, r"[\1|\2]"), (r"(?P<k>k\w*)", re.I, r"<\g<k>>"), (r"(x+)(y*)", 0, r"\g<0>\g<0>"),
+    (r"(?:(a)|b)+", 0, r"{\1}"), (r"(a|ab)(c|bcd)(d*)", 0, r"\3-\2-\1"), (r"(\d+)-(\d+)", 0, r"\2-\1"), (r"(\s*)(\S+)", 0, r"\2\1"),
+    (r"(x*)", 0, r"(\1)"), (r"(a?)(b?)", 0, r"<\1\2>"), (r"\b(\w)(\w*)", 0, r"\2\1ay"), (r"((a)|(b))+?c", 0, r"\1\2\3"),
+    (r"(é|日)(.)", re.S, r"\2\1"), (r"^(\s*)#(.*)$", re.M, r"\1//\2"), (r"(a+)(a*)", 0, r"\1,\2"), (r"(a+?)(a*)", 0, r"\1,\2"),
+    (r"(?:(x)|(y)|(z)){2,3}", 0, r"\1\2\3"), (r"(a(b(c)?)?)", 0, r"\3\2\1"), (r"(?i:(k))(?:-(\d))?", 0, r"\2\1"),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(GROUP_RULES)))
+def test_sub_templates_with_group_references(idx):
+    """`pattern.sub(template, text)` with `\\1` / `\\g<name>` / `\\g<0>` references: the ordered DFA finds the match, a Pike-VM pass over
+    the rule's NFA (cf::pike_captures, the same function the kernel runs) finds the group spans of that match."""
+    from mcp_context_forge_b200.regex_frontend import template_parts
+
+    pat, flags, tmpl = GROUP_RULES[idx]
+    rng = random.Random(1300 + idx)
+    c = re.compile(pat, flags)
+    hp = HostProgram()
+    hp.add(pat, flags, ordered=True, repl=template_parts(tmpl, c))
+    frag = ["a", "b", "c", "d", "ab", "abc", "bcd", "x", "xx", "y", "z", "k", "K", "-", "1", "23", "@", " ", "  ", "\n", "#", "é", "日", "w0", "_"]
+    units = ["", "a", "ab", "abcd", "abcdd", "xxyy", "k-1", "user@host", " # c\n#d"] + ["".join(rng.choice(frag) for _ in range(rng.randint(0, 14))) for _ in range(700)]
+    for u in units:
+        got, n = hp.sub(0, u)
+        exp, en = c.subn(tmpl, u)
+        assert got == exp and n == en, (pat, tmpl, u, got, exp)
+
+
+def test_template_errors_are_loud():
+    from mcp_context_forge_b200.regex_frontend import template_parts
+
+    with pytest.raises(re.error):
+        template_parts(r"\2", re.compile(r"(a)"))            # invalid group reference, as pattern.sub would raise
+    hp = HostProgram()
+    hp.add_ast(hp.fe.compile_ast(r"(a)", 0, "sub", groups=False), True, ["x", 1])    # the AST carries no group 1
     with pytest.raises(RuntimeError):
-        hp.compile()  # empty-matching substitution rule -> CF_E_UNSUPPORTED
+        hp.compile()
 
 
 def _big_rule_set(n_words, seed=0):

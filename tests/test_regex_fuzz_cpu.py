@@ -102,3 +102,55 @@ def test_random_patterns_agree_with_cpython(mode, monkeypatch):
         assert not bad, bad[:3]
         n += k
     assert n >= 30
+
+
+# ---- substitution: random rules (capturing groups, patterns that can match "", templates with group references) vs re.subn
+def sub_pattern(rng):
+    p = seq(rng, 2).replace("(?:", "(" if rng.random() < 0.7 else "(?:")
+    fl = 0
+    for f in (re.I, re.M, re.S):
+        if rng.random() < 0.2:
+            fl |= f
+    return p, fl
+
+
+def sub_round(seed):
+    from mcp_context_forge_b200.regex_frontend import template_parts
+
+    rng = random.Random(seed)
+    checked, bad = 0, []
+    for _ in range(12):
+        p, fl = sub_pattern(rng)
+        try:
+            c = re.compile(p, fl)
+        except re.error:
+            continue
+        tmpl = "".join(rng.choice(["-", "<", ">", "é", "\\\\", ""] + [f"\\{g}" for g in range(1, c.groups + 1)] + ["\\g<0>"]) for _ in range(rng.randint(0, 4)))
+        hp = HostProgram()
+        try:
+            hp.add(p, fl, ordered=True, repl=template_parts(tmpl, c))
+            hp.compile()
+        except UnsupportedPattern:
+            continue
+        except RuntimeError as exc:
+            if "too large" in str(exc):
+                continue
+            raise
+        checked += 1
+        for _ in range(60):
+            u = "".join(rng.choice(ALPH) for _ in range(rng.randint(0, 16)))
+            got, n = hp.sub(0, u)
+            exp, en = c.subn(tmpl, u)
+            if (got, n) != (exp, en):
+                bad.append((p, fl, tmpl, u, got, exp))
+                break
+    return checked, bad
+
+
+def test_random_substitution_rules_agree_with_cpython():
+    n = 0
+    for rd in range(25):
+        k, bad = sub_round(9100 + rd)
+        assert not bad, bad[:3]
+        n += k
+    assert n >= 100

@@ -413,9 +413,50 @@ def gen_sql_sanitizer():
 _SQL_DEFAULT = [r"\bDROP\b", r"\bTRUNCATE\b", r"\bALTER\b", r"\bGRANT\b", r"\bREVOKE\b"]
 
 
+# ------------------------------------------------------------------------------------------------
+def gen_regex_filter_templates():
+    """plugins/regex_filter/search_replace.py with rules whose patterns can match "" and whose replacements reference groups
+    (SURVEY Appendix A-1): recorded from the reference's own plugin file."""
+    from cpex.framework import GlobalContext, PluginConfig, PluginContext, ToolPostInvokePayload, ToolPreInvokePayload
+    from plugins.regex_filter.search_replace import SearchReplacePlugin
+
+    ctx = PluginContext(global_context=GlobalContext(request_id="golden"))
+    rng = random.Random(777)
+    rule_sets = [
+        [{"search": r"(\w+)@(\w+)\.com", "replace": r"\2 at \1"}, {"search": r"\b(\d{3})-(\d{4})\b", "replace": r"***-\2"}],
+        [{"search": r"(?P<word>crap|crud)", "replace": r"[\g<word>]"}, {"search": r"\[(\w+)\]", "replace": r"\1\1"}],
+        [{"search": r"x*", "replace": "-"}, {"search": r"-+", "replace": "~"}],
+        [{"search": r"^\s*", "replace": ""}, {"search": r"\s*\Z", "replace": ""}, {"search": r"(\S+)\s+(\S+)", "replace": r"\2 \1"}],
+        [{"search": r"\b", "replace": "|"}, {"search": r"(a)|b", "replace": r"<\1>"}],
+        [{"search": r"(?i)(kill)\s+(\w+)", "replace": r"\1 [\2]"}, {"search": r"(é+)(日?)", "replace": r"\2\1"}, {"search": r"", "replace": "."}],
+    ]
+    words = ["user@example.com", "bob@corp.com", "555-1234", "12-3456", "crap", "crud", "[x]", "xx", "x", "yxxy", "-", "--", "kill him", "KILL  them", "é", "éé日",
+             "日", "a", "b", "ab", " ", "  ", "\n", "\t", "word", "two words", "", "_", "1", "naïve"]
+    out = []
+    for rules in rule_sets:
+        plug = SearchReplacePlugin(PluginConfig(name="rf", kind="x", hooks=["tool_pre_invoke", "tool_post_invoke"], config={"words": rules}))
+        cases = []
+        for i in range(60):
+            def text():
+                return rng.choice(["", " ", "\n"]).join(rng.choice(words) for _ in range(rng.randint(0, 6)))
+            if i % 3:
+                args = {f"k{j}": text() for j in range(rng.randint(0, 4))}
+                if i % 4 == 0:
+                    args["n"] = 7
+                r = run(plug.tool_pre_invoke(ToolPreInvokePayload(name="t", args=args), ctx))
+                cases.append({"hook": "tool_pre_invoke", "args": args, "out_args": r.modified_payload.args})
+            else:
+                res = text() if i % 2 else {"a": text(), "content": [{"type": "text", "text": "x"}], "b": text()}
+                r = run(plug.tool_post_invoke(ToolPostInvokePayload(name="t", result=res), ctx))
+                cases.append({"hook": "tool_post_invoke", "result": res, "out_result": r.modified_payload.result})
+        out.append({"words": rules, "cases": cases})
+    dump("regex_filter_templates.json", out)
+
+
 if __name__ == "__main__":
     install_shims()
     only = sys.argv[1:]
-    for name, fn in (("pattern_plugins", gen_pattern_plugins), ("toon", gen_toon), ("masking", gen_masking), ("sql_sanitizer", gen_sql_sanitizer)):
+    for name, fn in (("pattern_plugins", gen_pattern_plugins), ("toon", gen_toon), ("masking", gen_masking), ("sql_sanitizer", gen_sql_sanitizer),
+                     ("regex_filter_templates", gen_regex_filter_templates)):
         if not only or name in only:
             fn()
