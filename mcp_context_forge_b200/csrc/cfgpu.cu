@@ -151,7 +151,7 @@ __device__ __noinline__ void verify_candidate(const ScanParams& P, const cf::Dfa
   if ((b0 & 0xC0) == 0x80) return;                     // not a character boundary
   uint32_t ctx;
   if (s[start - 1] == cf::TERM) ctx = cf::P_START;     // FRONT_PAD makes s[-1] valid for unit 0
-  else ctx = cf::prev_context(t, s, start - 4, start); // backward scan stops at any non-continuation byte
+  else ctx = cf::prev_context(t, s, start >= 4 ? start - 4 : 0, start); // backward scan stops at any non-continuation byte (no wrap-around in unit 0)
   uint32_t S = t.start_state[ctx];
   uint64_t q = start;
   const bool small = t.W <= 2;

@@ -177,3 +177,19 @@ def test_large_rule_sets_pair_prefilter_kernel(n_extra, monkeypatch):
     exp = ref.scan_bitmaps(units, HARMFUL, DENY + words, [(q, f) for q, f, _ in SUBS])
     assert got == exp
     assert sum(1 for v in exp if v) > 600
+
+
+def test_word_boundary_after_a_multibyte_character_at_the_very_start_of_the_stream():
+    """The character before a candidate is decoded by walking back over continuation bytes; for a candidate within the first four
+    bytes of unit 0 that walk must stop at the stream start (regression: the look-back bound wrapped around and the boundary
+    assertion saw the continuation byte as a non-word character)."""
+    p = engine.Program()
+    p.add_search(r"\bDROP\b", re.I)
+    p.add_search(r"\Bkill", re.I)
+    p.compile(engine.Context.get())
+    comp = [re.compile(r"\bDROP\b", re.I), re.compile(r"\Bkill", re.I)]
+    for first in ["İDROP TABLE users", "éDROP x", "日DROP", "\U0001F600DROP", "aDROP", "DROP", "İkill", "日kill", "é kill"]:
+        units = [first, "x DROP y", "İDROP"]
+        got = engine.scan_units(p, units)
+        exp = [sum(1 << i for i, c in enumerate(comp) if c.search(u)) for u in units]
+        assert got == exp, (first, got, exp)
