@@ -211,6 +211,10 @@ int cf_toon_host(cf_ctx* ctx, cf_batch* b, uint32_t flags, const uint8_t* stream
 #define CF_V_MASKED 4u
 #define CF_V_RESUBMIT 8u
 #define CF_TOON_SKIPPED 8       /* status of a unit whose unit_stages excluded CF_STAGE_TOON */
+#define CF_RUN_OUTPUTS_RESIDENT 32u /* toon_flags of cf_run_batch: leave the produced texts in HBM — gathered at out_offsets in one device
+                                     * buffer (cf_run_batch_device_output), rewritten units included — instead of copying them to out_bytes
+                                     * (which may then be NULL).  Verdicts and out_offsets come back as usual; the call returns when the
+                                     * device work is done.  For consumers that keep working on the device, and bench.py's `value`. */
 typedef struct cf_verdict {
   uint64_t match_bitmap;  /* bit i = pattern i matched (first 64 patterns) */
   uint32_t flags;         /* CF_V_* */
@@ -221,6 +225,10 @@ typedef struct cf_verdict {
 int cf_run_batch(cf_ctx* ctx, cf_prog* prog /* may be NULL without SCAN/SUB */, cf_batch* b, const uint8_t* stream, uint64_t stream_bytes,
                  const uint64_t* offsets, uint32_t n_units, uint32_t stage_mask, const uint8_t* unit_stages, uint32_t toon_flags, int mask_max_depth,
                  cf_verdict* verdicts, uint64_t* bitmaps_full, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_needed);
+/* the device buffer of the last CF_RUN_OUTPUTS_RESIDENT call of this ctx (valid until the next cf_run_batch / *_host call) */
+int cf_run_batch_device_output(cf_ctx* ctx, const uint8_t** d_out, uint64_t* bytes);
+/* synchronous copy of `bytes` device bytes to a host buffer (for callers without a CUDA runtime binding of their own) */
+int cf_copy_to_host(cf_ctx* ctx, void* host_dst, const void* device_src, uint64_t bytes);
 /* device-resident, asynchronous on cuda_stream: CF_STAGE_SCAN and/or CF_STAGE_TOON over the batch already uploaded (what
  * bench.py times with the batch resident in HBM).  d_unit_stages may be NULL. */
 int cf_chain(cf_ctx* ctx, cf_prog* prog, cf_batch* b, uint32_t stage_mask, uint32_t toon_flags, uint64_t* d_bitmaps, const uint8_t* d_unit_stages,

@@ -13,6 +13,7 @@ CF_OK = 0
 CF_E_CUDA, CF_E_BADARG, CF_E_UNSUPPORTED, CF_E_TOO_LARGE, CF_E_CAPACITY, CF_E_NOGPU, CF_E_NOMEM = -1, -2, -3, -4, -5, -6, -7
 CF_PAT_SEARCH, CF_PAT_ORDERED = 0, 1
 CF_STAGE_SCAN, CF_STAGE_SUB, CF_STAGE_MASK, CF_STAGE_TOON = 1, 2, 4, 8
+CF_RUN_OUTPUTS_RESIDENT = 32
 CF_V_REWRITTEN, CF_V_TOON, CF_V_MASKED, CF_V_RESUBMIT = 1, 2, 4, 8
 ERR_NAMES = {-1: "CF_E_CUDA", -2: "CF_E_BADARG", -3: "CF_E_UNSUPPORTED", -4: "CF_E_TOO_LARGE", -5: "CF_E_CAPACITY", -6: "CF_E_NOGPU", -7: "CF_E_NOMEM"}
 
@@ -45,6 +46,8 @@ _SIGS = {
     "cf_prog_patterns": (c_uint32, [c_void_p]),
     "cf_batch_create": (c_int, [c_void_p, c_uint64, c_uint32, POINTER(c_void_p)]),
     "cf_batch_free": (None, [c_void_p]),
+    "cf_run_batch_device_output": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64)]),
+    "cf_copy_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64]),
     "cf_host_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p)]),
     "cf_host_free": (None, [c_void_p, c_void_p]),
     "cf_batch_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),

@@ -36,6 +36,8 @@ struct cf_ctx {
   DevBuf d_tok, d_ntok;             // structural index of the current batch (json_index_kernel)
   void* h_stage = nullptr;          // pinned host staging for gathered results
   size_t h_stage_bytes = 0;
+  const uint8_t* run_out = nullptr;   // device buffer of the last CF_RUN_OUTPUTS_RESIDENT call
+  uint64_t run_out_bytes = 0;
   // optional per-launch timing of the dominant kernel (bench.py roofline): event pairs
   std::vector<cudaEvent_t> prof_ev;
   uint32_t prof_used = 0;

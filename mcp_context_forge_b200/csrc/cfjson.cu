@@ -402,7 +402,7 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
     if ((rc = cf_dev_reserve(ctx, ctx->tmp[0], stream_bytes + 16))) return rc;
     if ((rc = cf_dev_reserve(ctx, ctx->tmp[1], (size_t)n_units * 4))) return rc;
     if ((rc = cf_dev_reserve(ctx, ctx->tmp[2], (size_t)n_units * 4))) return rc;
-    if ((rc = toon_launch(ctx, b, toon_flags & ~(CF_TOON_PARSE_ONLY | CF_TOON_SEQUENTIAL), (uint8_t*)ctx->tmp[0].p, (uint32_t*)ctx->tmp[1].p, (int32_t*)ctx->tmp[2].p, d_us, 0))) return rc;
+    if ((rc = toon_launch(ctx, b, toon_flags & ~(CF_TOON_PARSE_ONLY | CF_TOON_SEQUENTIAL | CF_RUN_OUTPUTS_RESIDENT), (uint8_t*)ctx->tmp[0].p, (uint32_t*)ctx->tmp[1].p, (int32_t*)ctx->tmp[2].p, d_us, 0))) return rc;
   }
   nvtxRangePop();
   // ---- results of the launches
@@ -475,7 +475,10 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
   for (uint32_t i = 0; i < n_units; ++i) { out_offsets[i] = total; total += verdicts[i].out_len; }
   out_offsets[n_units] = total;
   if (out_needed) *out_needed = total;
-  if (total > out_cap || (!out_bytes && total)) { ctx->err = "output buffer too small"; return CF_E_CAPACITY; }
+  const bool keep = (toon_flags & CF_RUN_OUTPUTS_RESIDENT) != 0;
+  ctx->run_out = nullptr; ctx->run_out_bytes = 0;
+  if (!keep && (total > out_cap || (!out_bytes && total))) { ctx->err = "output buffer too small"; return CF_E_CAPACITY; }
+  if (keep && total && (rc = cf_dev_reserve(ctx, ctx->tmp[4], total))) return rc;
   if ((stage_mask & CF_STAGE_TOON) && total) {
     // gather the TOON texts on the device AT THEIR FINAL OFFSETS (rewritten units leave holes), then ONE D2H straight into out_bytes
     std::vector<uint32_t> glen(n_units);
@@ -489,16 +492,36 @@ int cf_run_batch(cf_ctx* ctx, cf_prog* prog, cf_batch* b, const uint8_t* stream,
       compact_kernel<<<n_units, 128>>>((const uint8_t*)ctx->tmp[0].p, 1, 0, b->d_offsets, (const uint32_t*)ctx->tmp[1].p, (const uint64_t*)ctx->tmp[3].p, (uint8_t*)ctx->tmp[4].p, n_units);
       ctx->launches++;
       CF_CUDA(ctx, cudaGetLastError());
-      CF_CUDA(ctx, cudaMemcpy(out_bytes, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
+      if (!keep) CF_CUDA(ctx, cudaMemcpy(out_bytes, ctx->tmp[4].p, total, cudaMemcpyDeviceToHost));
     }
   }
   for (size_t k = 0; k < dirty.size(); ++k) {
     const uint32_t i = dirty[k];
-    if (verdicts[i].out_len) memcpy(out_bytes + out_offsets[i], sub_bytes.data() + sub_off[k], verdicts[i].out_len);
+    if (!verdicts[i].out_len) continue;
+    // resident outputs: the rewritten text is still in the substitution call's device buffer (ctx->tmp[14], packed at sub_off)
+    if (keep) CF_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->tmp[4].p + out_offsets[i], (const uint8_t*)ctx->tmp[14].p + sub_off[k], verdicts[i].out_len, cudaMemcpyDeviceToDevice, 0));
+    else memcpy(out_bytes + out_offsets[i], sub_bytes.data() + sub_off[k], verdicts[i].out_len);
+  }
+  if (keep) {
+    CF_CUDA(ctx, cudaStreamSynchronize(0));
+    ctx->run_out = total ? (const uint8_t*)ctx->tmp[4].p : nullptr;
+    ctx->run_out_bytes = total;
   }
   return CF_OK;
 }
 
+int cf_run_batch_device_output(cf_ctx* ctx, const uint8_t** d_out, uint64_t* bytes) {
+  if (!ctx || !d_out || !bytes) return CF_E_BADARG;
+  *d_out = ctx->run_out;
+  *bytes = ctx->run_out_bytes;
+  return CF_OK;
+}
+
+int cf_copy_to_host(cf_ctx* ctx, void* host_dst, const void* device_src, uint64_t bytes) {
+  if (!ctx || (bytes && (!host_dst || !device_src))) return CF_E_BADARG;
+  if (bytes) CF_CUDA(ctx, cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+  return CF_OK;
+}
 
 int cf_profile_collect_each(cf_ctx* ctx, double* ms, uint32_t cap, uint32_t* n_launches) {
   if (!ctx || !ms || !n_launches) return CF_E_BADARG;

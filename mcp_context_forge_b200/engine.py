@@ -260,9 +260,10 @@ VERDICT_DTYPE = np.dtype([("match_bitmap", "<u8"), ("flags", "<u4"), ("out_len",
 
 
 def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray, stage_mask: int, unit_stages: Optional[np.ndarray] = None,
-              toon_flags: int = 0, mask_max_depth: int = 10, want_full_bitmaps: bool = False):
+              toon_flags: int = 0, mask_max_depth: int = 10, want_full_bitmaps: bool = False, outputs_resident: bool = False):
     """cf_run_batch: ONE upload of the packed stream, every requested stage on the resident batch, verdicts + only the produced
-    texts back.  Returns (verdicts[VERDICT_DTYPE], out uint8[], out_offsets uint64[n+1], full bitmaps or None)."""
+    texts back.  Returns (verdicts[VERDICT_DTYPE], out uint8[], out_offsets uint64[n+1], full bitmaps or None).
+    `outputs_resident`: the produced texts stay in HBM (CF_RUN_OUTPUTS_RESIDENT; `out` is None, fetch with device_output())."""
     ctx = batch.ctx
     n = len(offsets) - 1
     nbytes = int(offsets[-1])
@@ -271,6 +272,15 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
     W = prog.words if prog is not None else 1
     full = np.zeros(n * W, dtype=np.uint64) if want_full_bitmaps else None
     need = c_uint64(0)
+    if outputs_resident:
+        sp = None if stream is None else (stream.ctypes.data if isinstance(stream, np.ndarray) else ctypes.cast(ctypes.c_char_p(stream), c_void_p))
+        us = np.ascontiguousarray(unit_stages, dtype=np.uint8) if unit_stages is not None else None
+        with ctx.lock:
+            rc = ctx.lib.cf_run_batch(ctx.h, prog.h if prog is not None else None, batch.h, sp, nbytes, offsets.ctypes.data, n, stage_mask,
+                                      us.ctypes.data if us is not None else None, toon_flags | N.CF_RUN_OUTPUTS_RESIDENT, mask_max_depth, verdicts.ctypes.data,
+                                      full.ctypes.data if full is not None else None, None, 0, out_offs.ctypes.data, byref(need))
+        ctx.check(rc, "cf_run_batch")
+        return verdicts, None, out_offs, full
     # the output buffer lives with the Batch, is page-locked and only grows.  NOTE: the returned `out` is a view of it — it is
     # overwritten by the next run_batch on this Batch (callers slice/copy what they keep).
     pin = getattr(batch, "_out_pin", None)
@@ -301,6 +311,18 @@ def run_batch(prog: Optional[Program], batch: Batch, stream, offsets: np.ndarray
         ctx.check(rc, "cf_run_batch")
         break
     return verdicts, out, out_offs, full
+
+
+def device_output(ctx: Context) -> np.ndarray:
+    """Host copy of the device buffer the last `run_batch(..., outputs_resident=True)` of this context left in HBM."""
+    p = c_void_p()
+    nb = c_uint64(0)
+    with ctx.lock:
+        ctx.check(ctx.lib.cf_run_batch_device_output(ctx.h, byref(p), byref(nb)), "cf_run_batch_device_output")
+        out = np.empty(nb.value, dtype=np.uint8)
+        if nb.value:
+            ctx.check(ctx.lib.cf_copy_to_host(ctx.h, out.ctypes.data, p, nb.value), "cf_copy_to_host")
+    return out
 
 
 def toon_host(batch: Batch, stream, offsets: np.ndarray, report_errors: bool = True):
