@@ -38,6 +38,14 @@ plugins:
       words:
         - {search: crap, replace: crud}
         - {search: crud, replace: yikes}
+        - {search: '(?i)(kill) (him|her)', replace: '\\2 <\\1>'}
+  - name: "SQLSanitizer"
+    kind: "mcp_context_forge_b200.plugins.sql_sanitizer.SQLSanitizerPlugin"
+    hooks: ["prompt_pre_fetch", "tool_pre_invoke"]
+    mode: "sequential"
+    priority: 45
+    config:
+      block_on_violation: false
   - name: "ToonEncoder"
     kind: "mcp_context_forge_b200.plugins.toon_encoder.ToonEncoderPlugin"
     hooks: ["tool_post_invoke"]
@@ -72,7 +80,8 @@ def norm(res):
 
 def payloads(n, seed):
     rng = random.Random(seed)
-    words = ["hello", "crap", "crud", "innovative", "kill him", "suicide", "normal text", "Kill her", "revolutionary idea", "I want to die", "racial slur", "fine"]
+    words = ["hello", "crap", "crud", "innovative", "kill him", "suicide", "normal text", "Kill her", "revolutionary idea", "I want to die", "racial slur", "fine",
+             "DROP table t -- crap", "select 1 /* c */", "delete from t"]
     pre, tpre, post = [], [], []
     for i in range(n):
         args = {f"k{j}": " ".join(rng.choice(words) for _ in range(rng.randint(1, 6))) for j in range(rng.randint(0, 3))}
@@ -112,8 +121,8 @@ def test_batched_chain_equals_sequential_chain(harm_mode, regex_prio):
         # something of everything happened
         if regex_prio == 50:
             assert bat.slow_path_calls > 0                  # regex_filter ran first and rewrote values: the plugins behind it ran their own hook
-        else:
-            assert bat.slow_path_calls == 0                 # nothing behind regex_filter reads what it rewrote: every verdict came from the fused launch
+        # (regex_prio == 150: only SQLSanitizer — a plugin without the chain protocol — and the plugins behind it on the requests whose
+        #  args it changed run their own hook; everything else is served from the fused launch)
         assert bat.slow_path_calls < 6 * 160 * 3
         loop.run_until_complete(seq.shutdown())
         loop.run_until_complete(bat.shutdown())
