@@ -496,11 +496,52 @@ def main():
             if int(v_res["match_bitmap"][i]) != expb or (not dirty and got != exp) or not same:
                 raise SystemExit(f"bench.py: parity check failed at unit {i} (resident==cabi: {same})")
 
+    # ---- variants on a smaller batch (same call as `value`): hit rates 0 / 1e-2 and a large rule set (256 deny literals + 32 regexes)
+    variants = None
+    if rank == 0 and world == 1:
+        variants = {}
+        nv = min(n, 8192)
+
+        def run_variant(vprog, vpayloads):
+            vunits = [vpayloads[i % len(vpayloads)] for i in range(nv)]
+            vs, vo = engine.pack_units(vunits)
+            vb = engine.Batch(ctx, len(vs), nv)
+            vb.upload(np.frombuffer(vs, dtype=np.uint8), vo)
+            for _ in range(2):
+                vv, _o, _oo, _f = engine.run_batch(vprog, vb, None, vo, STAGES, outputs_resident=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                vv, _o, _oo, _f = engine.run_batch(vprog, vb, None, vo, STAGES, outputs_resident=True)
+            dt = (time.perf_counter() - t0) / 3
+            return {"payloads_per_s": nv / dt, "ms_per_step": dt * 1e3, "units": nv, "rewritten_units": int(((vv["flags"] & CF_V_REWRITTEN) != 0).sum()),
+                    "flagged_units": int((vv["match_bitmap"] != 0).sum()), "toon_converted_units": int(((vv["flags"] & CF_V_TOON) != 0).sum())}
+
+        variants["hit_rate_0"] = run_variant(prog, make_payloads(hit_rate=0.0))
+        variants["hit_rate_1e-2"] = run_variant(prog, make_payloads(hit_rate=1e-2))
+        sp = engine.Program()
+        for pats in DEFAULT_LEXICONS.values():
+            for pat in pats:
+                sp.add_search(pat, re.I)
+        import random as _random
+        rr = _random.Random(5)
+        syll = ["zor", "quix", "vald", "brem", "tosk", "jiv", "plun", "gax", "merv", "dwil", "skob", "frey", "hux", "nolt", "crim", "yast"]
+        for k in range(256):
+            sp.add_literal("".join(rr.choice(syll) for _ in range(3)) + str(k))
+        for k in range(32 - 9):
+            sp.add_search(r"\b" + rr.choice(syll) + r"[a-z]{2,5}" + rr.choice(syll) + r"\d+\b", re.I)
+        for s_, f_, r_ in SUBS:
+            sp.add_sub(s_, f_, r_)
+        sp.compile(ctx)
+        variants["stress_rule_set_256_literals_32_regexes"] = run_variant(sp, payloads)
+        variants["stress_rule_set_256_literals_32_regexes"]["prefilter"] = "pair" if sp.compile_host().prefilter else "byte"
+
     # ---- end to end through the plugin API (host objects in, PluginResult out), one worker
     api = None
     if True:
         reqs = 2048
-        workers = max(1, min(8, host_cores() // world - 1))
+        # one gateway worker process per host core the rank may use (one core left to the launcher); at N > 1 at most 8 per rank
+        workers = max(1, min(15 if world == 1 else 8, host_cores() // world - 1))
         api_val, api_h2d, api_d2h, api_stats = hook_api_e2e(reqs, 3, local_rank, workers, args.hit_rate)
         if world > 1:
             t = torch.tensor([api_val], dtype=torch.float64, device="cuda")
@@ -552,6 +593,7 @@ def main():
                    "other_ms_per_step": ms_step - scan_k - toon_k,
                    "value_definition": "cf_run_batch(stream=NULL, CF_RUN_OUTPUTS_RESIDENT): batch resident in HBM, scan + TOON (+ hand-over) kernels, verdict D2H (24 B/unit), "
                                        "regex_filter rewriting of the matched units, gather of the produced texts into one device buffer; texts stay in HBM"},
+        "variants": variants,
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }

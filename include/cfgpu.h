@@ -94,7 +94,12 @@ typedef struct cf_compile_stats {
 } cf_compile_stats;
 int cf_builder_compile_host(cf_builder* b, cf_compile_stats* out);
 
-/* ---------------- device context / program ---------------- */
+/* ---------------- device context / program ----------------
+ * Threading: a cf_builder belongs to one thread at a time.  A cf_ctx owns a device, its scratch pools and the default
+ * stream's work: calls on ONE cf_ctx must be serialised by the caller (the Python binding holds a lock per context; a gateway
+ * worker has one context and one launching thread).  Different cf_ctx objects — one per worker process or per GPU — are
+ * independent.  A compiled cf_prog is immutable and may be used by any call of the ctx that compiled it; a cf_batch holds ONE
+ * upload at a time.  The asynchronous entry points (cf_scan, cf_toon, cf_chain) only enqueue on the given stream and return. */
 int cf_init(int device_ordinal, cf_ctx** out);
 void cf_shutdown(cf_ctx* ctx);
 const char* cf_last_error(cf_ctx* ctx);

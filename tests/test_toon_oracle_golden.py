@@ -64,3 +64,24 @@ def test_plugin_item_decision_matches_reference(gold):
                     conv += 1
             n += 1
     assert n > 300 and conv > 50
+
+
+def test_orjson_probe_pins_the_restated_integer_and_overflow_rules():
+    """The reference parses with orjson (toon_encoder.py:281); it is not installable in the build container, so its two observable
+    differences from stdlib json on this path are restated in `toon_ref.loads_strict`.  Wherever orjson IS importable (probed at
+    test time, e.g. on the GPU box) the restatement is held to the real thing."""
+    orjson = pytest.importorskip("orjson")
+    from oracle import toon_ref
+
+    cases = ["18446744073709551615", "18446744073709551616", "-9223372036854775808", "-9223372036854775809", "123456789012345678901234567890",
+             "[1e308, 1e-400]", '{"a": 12345678901234567890123}', "1e309", "[1E400]", "-1e999", "NaN", "[Infinity]", '{"x": -0}', "-0.0", "1.0e+2"]
+    for text in cases:
+        try:
+            exp = ("ok", orjson.loads(text))
+        except orjson.JSONDecodeError:
+            exp = ("err", None)
+        try:
+            got = ("ok", toon_ref.loads_strict(text))
+        except (ValueError, TypeError):
+            got = ("err", None)
+        assert repr(got) == repr(exp), (text, got, exp)
