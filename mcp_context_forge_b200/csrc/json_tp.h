@@ -169,7 +169,11 @@ TP_FN uint32_t byte_class(uint32_t b) {
   return k;
 }
 
+#ifdef __CUDACC__
+TP_FN uint32_t bits_below(uint32_t i) { return __funnelshift_lc(0xFFFFFFFFu, 0u, i); }   // bits 0..i-1 (one SHF; the shift clamps at 32)
+#else
 TP_FN uint32_t bits_below(uint32_t i) { return i >= 32 ? 0xFFFFFFFFu : ((1u << i) - 1u); }   // bits 0..i-1
+#endif
 TP_FN uint32_t range_mask(uint32_t lo, uint32_t hi) { return bits_below(hi) & ~bits_below(lo); }   // bits lo..hi-1
 TP_FN uint32_t sat3(uint32_t v) { return v > 3u ? 3u : v; }
 

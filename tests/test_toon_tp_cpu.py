@@ -184,3 +184,17 @@ def test_long_escaped_strings_whole_warp_escape_check():
             assert b[0] == 7 or a == b, (d[:160], a, b)
             n_checked += b[0] != 7
     assert n_checked > 900
+
+
+def test_duplicate_keys_are_handed_over_wherever_they_sit():
+    """The duplicate-key screen (FNV hashes of an open object's keys on a stack in shared memory): a repeated
+    key in the same run, behind a nested container, 40 members later, inside a nested object or a table row hands the unit to the
+    sequential encoder (status 7); no false alarm for equal keys in DIFFERENT objects."""
+    dup = ['{"a":1,"b":2,"a":3}', '{"a":1,"n":{"x":1},"a":3}', '{"a":1,' + ",".join(f'"k{i}":{i}' for i in range(40)) + ',"a":2}',
+           '{"o":{"p":1,"q":2,"p":3},"z":1}', '[{"a":1,"b":2},{"a":1,"a":2}]']
+    ok = ['{"a":1,"n":{"a":1},"b":{"a":2}}', "{" + ",".join(f'"k{i}":{{"a":{i}}}' for i in range(50)) + "}"]
+    for order in (0, 1):
+        for t in dup:
+            assert hs.toon_tp(t, order=order)[0] == 7, t
+        for t in ok:
+            assert hs.toon_tp(t, order=order) == hs.toon_host(t), t
