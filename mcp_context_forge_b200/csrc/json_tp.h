@@ -279,7 +279,7 @@ TP_FN bool is_reserved(const uint8_t* b, uint32_t len) {
   return false;
 }
 // escapes other than \" \\ \n \r \t need transcoding (the TOON text differs from the JSON text)
-TP_FN bool has_complex_escape(const uint8_t* b, uint32_t len) {
+TP_SLOW bool has_complex_escape(const uint8_t* b, uint32_t len) {
   for (uint32_t i = 0; i + 1 < len; ++i)
     if (b[i] == '\\') {
       const uint32_t e = b[i + 1];
@@ -295,7 +295,7 @@ TP_FN uint32_t fnv1a(const uint8_t* b, uint32_t len) {
 }
 
 // decoded length / bytes of a string that needs transcoding (JSON escapes -> TOON text), quoted or not
-TP_FN uint32_t escx_len(const uint8_t* b, uint32_t len, bool quoted) {
+TP_SLOW uint32_t escx_len(const uint8_t* b, uint32_t len, bool quoted) {       // cold (strings with escapes): out of line, the kernel's hot code stays small
   cfj::StrIter it{b, b + len};
   uint32_t n = quoted ? 2u : 0u;
   while (!it.done()) {
@@ -336,7 +336,7 @@ struct Emit {
     else if (c < 0x10000) { put(0xE0 | (c >> 12)); put(0x80 | ((c >> 6) & 63)); put(0x80 | (c & 63)); }
     else { put(0xF0 | (c >> 18)); put(0x80 | ((c >> 12) & 63)); put(0x80 | ((c >> 6) & 63)); put(0x80 | (c & 63)); }
   }
-  TP_FN void escx(const uint8_t* b, uint32_t len, bool quoted) {
+  TP_SLOW void escx(const uint8_t* b, uint32_t len, bool quoted) {
     cfj::StrIter it{b, b + len};
     if (quoted) put('"');
     while (!it.done()) {
@@ -387,7 +387,7 @@ TP_SLOW bool string_slow(const uint8_t* s, uint32_t n, uint32_t pos, uint32_t le
 // continuation byte exactly when one of the three bytes before it is a lead that reaches it, leads are C2..F4, and the second
 // byte of E0 / ED / F0 / F4 sequences is range-checked (no overlongs, no surrogates, nothing above U+10FFFF) — what
 // cfj::parse_string checks one code point at a time.  The byte behind the string is its closing quote: a truncated tail fails.
-TP_FN bool warp_utf8_valid(const uint8_t* s, uint32_t a, uint32_t len) {
+TP_SLOW bool warp_utf8_valid(const uint8_t* s, uint32_t a, uint32_t len) {
   const uint32_t l = tpw::lane();
   bool bad = false;
   for (uint32_t base = 0; base <= len; base += 32) {
@@ -419,7 +419,7 @@ static const uint32_t LONG_HI = 96;      // non-ASCII / escaped strings at least
 // Returns a bit set: 1 invalid escape, 2 some \u escape, 4 an escape TOON writes differently (\/ \b \f), 8 \b or \f (a control
 // character toon._quote_string rejects).
 enum : uint32_t { XE_BAD = 1, XE_U = 2, XE_COMPLEX = 4, XE_CTRL = 8 };
-TP_FN uint32_t warp_escapes(const uint8_t* s, uint32_t a, uint32_t len) {
+TP_SLOW uint32_t warp_escapes(const uint8_t* s, uint32_t a, uint32_t len) {
   const uint32_t l = tpw::lane();
   uint32_t res = 0, e_in = 0, pend = 0;                 // e_in: the chunk's first byte is escaped; pend: it is an escape's code character
   for (uint32_t base = 0; base < len; base += 32) {
