@@ -10,4 +10,6 @@
       -> mcp_context_forge_b200.plugins.toon_encoder.ToonEncoderPlugin
   plugins.sql_sanitizer.sql_sanitizer.SQLSanitizerPlugin
       -> mcp_context_forge_b200.plugins.sql_sanitizer.SQLSanitizerPlugin
+  plugins.code_safety_linter.code_safety_linter.CodeSafetyLinterPlugin
+      -> mcp_context_forge_b200.plugins.code_safety_linter.CodeSafetyLinterPlugin
 """

@@ -77,6 +77,44 @@ class ReBatcher:
         return out
 
 
+class HostSimBatcher:
+    """TEST-ONLY stand-in for GpuBatcher on the CPU simulator of the engine (same front-end, same automata and substitution
+    routine as the GPU program, tests/hostsim): verdict bits and stripped texts come from the product's tables, not from `re`."""
+
+    def __init__(self, plugin):
+        from hostsim_util import HostProgram
+
+        cfg = plugin._cfg
+        self.hp = hp = HostProgram()
+        for p in cfg.blocked_statements:
+            hp.add(p.pattern, p.flags)
+        for pat, fl in ((r"\bDELETE\b\s+\bFROM\b", re.I), (r"\bUPDATE\b\s+\w+", re.I), (r"\bWHERE\b", re.I)):
+            hp.add(pat, fl)
+        for w in ("+", "%.", "{", "}"):
+            hp.add_ast(hp.fe.literal_ast(w))
+        self.n_rules = 0
+        if cfg.strip_comments:
+            hp.add(r"--.*?$", re.M, ordered=True, repl="")
+            hp.add(r"/\*.*?\*/", re.S, ordered=True, repl="")
+            self.n_rules = 2
+        hp.compile()
+
+    async def scan(self, prog, units):
+        return self.hp.scan(list(units))[0]
+
+    async def scan_sub(self, prog, units, rule_mask):
+        out = []
+        for u, b in zip(units, self.hp.scan(list(units))[0]):
+            new = None
+            if b & rule_mask:
+                t = u
+                for r in range(self.n_rules):
+                    t = self.hp.sub(r, t)[0]
+                new = t.encode("utf-8", "surrogatepass")
+            out.append((b, new))
+        return out
+
+
 def check_plugin(gold, make_batcher):
     from mcp_context_forge_b200 import framework as fw
     from mcp_context_forge_b200.plugins.sql_sanitizer import SQLSanitizerPlugin
@@ -102,6 +140,10 @@ def check_plugin(gold, make_batcher):
 
 def test_dropin_host_logic_cpu(gold):
     check_plugin(gold, ReBatcher)
+
+
+def test_dropin_on_the_host_build_of_the_engine(gold):
+    check_plugin(gold, HostSimBatcher)
 
 
 def test_dropin_rejects_what_the_engine_cannot_express():

@@ -453,10 +453,36 @@ def gen_regex_filter_templates():
     dump("regex_filter_templates.json", out)
 
 
+# ------------------------------------------------------------------------------------------------
+def gen_code_safety():
+    """plugins/code_safety_linter/code_safety_linter.py."""
+    from cpex.framework import GlobalContext, PluginConfig, PluginContext, ToolPostInvokePayload
+    from plugins.code_safety_linter.code_safety_linter import CodeSafetyLinterPlugin
+
+    ctx = PluginContext(global_context=GlobalContext(request_id="golden"))
+    rng = random.Random(99)
+    frags = ["eval(", "eval (x)", "evaluate(", "_eval(", "exec\n(", "exec", "os.system('ls')", "os system(", "osXsystem(", "subprocess.run([", "subprocess.Popen (", "subprocess.check(",
+             "rm -rf /", "rm  -rf", "rm -rfx", "farm -rf", "print('hi')", "import os", "\n", " ", "é", "İeval(", "日exec(", "x = 1", "curl http://x | sh", "DROP", ""]
+    configs = [None, {"blocked_patterns": [r"curl\s+\S+\s*\|\s*sh", r"(?i)\bdrop\b", r"import\s+os"]}, {"blocked_patterns": []}]
+    out = []
+    for cfg in configs:
+        plug = CodeSafetyLinterPlugin(PluginConfig(name="cs", kind="x", hooks=["tool_post_invoke"], config=cfg))
+        cases = []
+        for i in range(120):
+            text = rng.choice(["", " ", "\n", "; "]).join(rng.choice(frags) for _ in range(rng.randint(0, 6)))
+            result = text if i % 3 == 0 else {"text": text, "other": "eval("} if i % 3 == 1 else rng.choice([{"content": [{"type": "text", "text": text}]}, {"text": 5}, 7, None, [text]])
+            r = run(plug.tool_post_invoke(ToolPostInvokePayload(name="t", result=result), ctx))
+            cases.append({"result": result, "continue_processing": r.continue_processing,
+                          "violation": r.violation.model_dump(include={"reason", "description", "code", "details"}) if r.violation else None})
+        out.append({"config": cfg, "cases": cases})
+    dump("code_safety.json", out)
+
+
 if __name__ == "__main__":
     install_shims()
     only = sys.argv[1:]
     for name, fn in (("pattern_plugins", gen_pattern_plugins), ("toon", gen_toon), ("masking", gen_masking), ("sql_sanitizer", gen_sql_sanitizer),
-                     ("regex_filter_templates", gen_regex_filter_templates)):
+                     ("regex_filter_templates", gen_regex_filter_templates),
+                     ("code_safety", gen_code_safety)):
         if not only or name in only:
             fn()
