@@ -704,19 +704,65 @@ CF_HD void emit_string(Ctx& c, const JNode& nd, bool force_quote) {
   c.out.put('"');
 }
 
-// object key: unquoted iff ^[A-Za-z_][A-Za-z0-9_.]*$ (where `$` admits one final "\n") and not reserved;
-// `raw` = columnar header, never quoted (toon.py:501)
-CF_HD void emit_key(Ctx& c, const JNode& k, bool raw) {
+// object key: unquoted iff ^[A-Za-z_][A-Za-z0-9_.]*$ (where `$` admits one final "\n") and not reserved.
+// Such a key carries its newline RAW into the output.  The reference builds nested text as strings and re-splits them on "\n" at
+// every enclosing level (toon.py:369, :421, :432, :559), so whatever follows the newline is a line of its own and receives the
+// prefixes of the enclosing levels — `pre` spaces — but not the indentation the emitting level wrote in front of the key.
+CF_HD void emit_key(Ctx& c, const JNode& k, uint32_t pre) {
   const uint8_t* b = c.s + k.off;
   const uint8_t* e = b + k.len;
-  if (raw || (k.t & JF_KEYOK)) {
+  if (k.t & JF_KEYOK) {
     if (!(k.t & JF_ESC)) { c.out.put_span(b, k.len); return; }
     StrIter it{b, e};
-    while (!it.done()) c.out.put_cp(it.next());
+    while (!it.done()) { const uint32_t cp = it.next(); c.out.put_cp(cp); if (cp == '\n') c.out.spaces(pre); }
     return;
   }
   emit_string(c, k, true);
 }
+
+// The header "[n]{k1,k2}:" of a columnar array.  Its fields are never quoted (toon.py:501), so they may carry raw newlines anywhere.
+// What follows one is, as above, a line of its own: `hdr_pre` spaces in front — or, when the array is the first field of a list item
+// (toon.py:405-413 splits the columnar text and treats every line but the first as "a row"), the line is stripped on both sides
+// (str.strip) and indented like the rows (`row_pre`).
+struct HeaderSink {
+  Ctx& c;
+  uint32_t hdr_pre, row_pre;
+  bool strip;
+  uint32_t piece, ws_tail;
+  bool at_start;
+  CF_HD void cp(uint32_t x) {
+    if (x == '\n') {
+      if (strip) {
+        if (piece && !c.out.over) c.out.n -= ws_tail;             // rstrip of the line that ends here
+        c.out.put('\n'); c.out.spaces(row_pre);
+      } else { c.out.put('\n'); c.out.spaces(hdr_pre); }
+      ++piece; ws_tail = 0; at_start = true;
+      return;
+    }
+    if (strip && piece) {
+      if (is_pyspace(x)) {
+        if (at_start) return;                                      // lstrip
+        const uint32_t before = c.out.n;
+        c.out.put_cp(x);
+        ws_tail += c.out.n - before;
+        return;
+      }
+      at_start = false; ws_tail = 0;
+    }
+    c.out.put_cp(x);
+  }
+  CF_HD void key(const JNode& k) {
+    const uint8_t* b = c.s + k.off;
+    if (!(k.t & JF_ESC)) {
+      if (!(strip && piece)) { c.out.put_span(b, k.len); return; }  // no escapes: no raw newline, no whitespace handling needed on line 0
+      StrIter raw{b, b + k.len};                                    // (without escapes StrIter is a plain UTF-8 decoder)
+      while (!raw.done()) cp(raw.next());
+      return;
+    }
+    StrIter it{b, b + k.len};
+    while (!it.done()) cp(it.next());
+  }
+};
 
 // Python's float formatting as used by toon._encode_float, from the exact binary value.
 CF_HD void emit_double(Ctx& c, const Dbl& d) {
@@ -933,13 +979,14 @@ CF_HD int columnar_check(const Ctx& c, uint32_t arr) {
 }
 
 // "[n]{k1,k2}:" then one row per element at `row_pre` spaces
-CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre, bool aligned) {
+CF_HD void emit_columnar(Ctx& c, uint32_t arr, uint32_t row_pre, bool aligned, uint32_t hdr_pre, bool strip) {
   const JNode* N = c.nodes;
   uint32_t first = N[arr].off;
   c.out.put('['); c.out.put_uint(N[arr].len); c.out.put(']'); c.out.put('{');
+  HeaderSink hs{c, hdr_pre, row_pre, strip, 0, 0, false};
   bool f0 = true;
-  for (uint32_t k = N[first].off; k; k = N[k].next) { if (!f0) c.out.put(','); f0 = false; emit_key(c, N[k], true); }
-  c.out.put('}'); c.out.put(':');
+  for (uint32_t k = N[first].off; k; k = N[k].next) { if (!f0) hs.cp(','); f0 = false; hs.key(N[k]); }
+  hs.cp('}'); hs.cp(':');
   for (uint32_t x = first; x && !c.err && !(c.out.over && c.stop_on_over); x = N[x].next) {
     newline(c, row_pre);
     bool f1 = true;
@@ -977,7 +1024,7 @@ CF_HD bool begin_array(Ctx& c, uint32_t arr, uint32_t pre, uint32_t indent, Fram
   }
   if (all_obj) {
     const int cc = columnar_check(c, arr);
-    if (cc >= COL_YES) { emit_columnar(c, arr, pre + 2, cc == COL_YES_ALIGNED); return false; }
+    if (cc >= COL_YES) { emit_columnar(c, arr, pre + 2, cc == COL_YES_ALIGNED, pre, false); return false; }
   }
   c.out.put('['); c.out.put_uint(n); c.out.put(']'); c.out.put(':');
   if (all_simple) {
@@ -1007,7 +1054,7 @@ CF_HD void toon_emit(Ctx& c, uint32_t root) {
       f.cur = N[k].next;
       uint32_t pre = f.pre, indent = f.indent;
       newline(c, pre);
-      emit_key(c, N[k], false);
+      emit_key(c, N[k], pre);
       uint32_t vt = N[v].t & J_TYPE;
       if (vt == J_ARR) begin_array(c, v, pre, indent, st, &sp);
       else if (vt == J_OBJ) {
@@ -1033,13 +1080,13 @@ CF_HD void toon_emit(Ctx& c, uint32_t root) {
       uint32_t pre = f.pre, indent = f.indent, ind = 2 * indent, fi = 2 * (indent + 1);
       newline(c, pre + (i == 0 ? ind : fi));
       if (i == 0) { c.out.put('-'); c.out.put(' '); }
-      emit_key(c, N[k], false);
+      emit_key(c, N[k], pre);
       uint32_t vt = N[v].t & J_TYPE;
       if (vt == J_ARR && N[v].len) {
         if (i == 0) {
           int cc = columnar_check(c, v);
           if (cc == COL_CRASH) { c.err = TS_ATTR_ERROR; break; }
-          if (cc >= COL_YES) { emit_columnar(c, v, pre + fi + 2, cc == COL_YES_ALIGNED); continue; }
+          if (cc >= COL_YES) { emit_columnar(c, v, pre + fi + 2, cc == COL_YES_ALIGNED, pre, true); continue; }
         }
         c.out.put(':');
         newline(c, pre + fi + 2);

@@ -129,6 +129,14 @@ def columnar(arr: list) -> Optional[Tuple[str, List[str]]]:
     return header, [",".join(enc_prim(o[k]) for k in keys) for o in arr]
 
 
+def _nl(text: str, pre: str) -> str:
+    """A key the reference emits unquoted may contain a raw newline (its `$` admits one final "\\n", toon.py:299-306; columnar header
+    fields are never quoted, :501).  The reference builds nested text as strings and re-splits them on "\\n" at every enclosing level
+    (:369, :421, :432, :559), so what follows such a newline is a line of its own and receives the prefixes of the ENCLOSING levels —
+    `pre` here — but not the indentation the emitting level wrote in front of the key itself."""
+    return text.replace("\n", "\n" + pre) if "\n" in text else text
+
+
 def emit_array(out: List[str], arr: list, pre: str, indent: int, prefix: str, first_prefix: Optional[str] = None) -> None:
     """Lines of one array.  `pre` = spaces contributed by enclosing blocks; `indent` = the
     reference's indent argument (absolute!), `first_prefix` overrides `pre` for the first line
@@ -140,7 +148,7 @@ def emit_array(out: List[str], arr: list, pre: str, indent: int, prefix: str, fi
     if all(isinstance(x, dict) for x in arr):
         col = columnar(arr)
         if col is not None:
-            out.append(f"{p0}{prefix}{col[0]}")
+            out.append(f"{p0}{prefix}{_nl(col[0], pre)}")
             out.extend(f"{pre}  {r}" for r in col[1])
             return
     if all(simple(x) for x in arr):
@@ -164,14 +172,17 @@ def emit_list_item(out: List[str], obj: dict, pre: str, indent: int) -> None:
     ind = " " * (2 * indent)
     fi = " " * (2 * (indent + 1))
     for i, (k, v) in enumerate(obj.items()):
-        ek = enc_key(k)
+        ek = _nl(enc_key(k), pre)
         lead = f"{pre}{ind}- " if i == 0 else f"{pre}{fi}"
         if isinstance(v, list) and v:
             if i == 0:
                 col = columnar(v)
                 if col is not None:
-                    out.append(f"{lead}{ek}{col[0]}")
-                    out.extend(f"{pre}{fi}  {r.strip()}" for r in col[1])
+                    # toon.py:405-413: the columnar text is split on "\n"; line 0 is "the header", every other line — the rest of a
+                    # header with a raw newline included — is "a row": stripped and indented like one
+                    hdr = col[0].split("\n")
+                    out.append(f"{lead}{ek}{hdr[0]}")
+                    out.extend(f"{pre}{fi}  {r.strip()}" for r in hdr[1:] + col[1])
                     continue
             out.append(f"{lead}{ek}:")
             emit_array(out, v, f"{pre}{fi}  ", indent + 2, "")
@@ -185,7 +196,7 @@ def emit_list_item(out: List[str], obj: dict, pre: str, indent: int) -> None:
 
 def emit_object(out: List[str], obj: dict, pre: str, indent: int) -> None:
     for k, v in obj.items():
-        ek = enc_key(k)
+        ek = _nl(enc_key(k), pre)
         if isinstance(v, list):
             emit_array(out, v, pre, indent, ek)
         elif isinstance(v, dict):

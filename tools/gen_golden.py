@@ -247,8 +247,16 @@ def gen_toon():
         [{"a": 1, "b": [1]}, {"a": 2, "b": [2]}], {"k": "ctrl\x01"}, ["ctrl\x02"], {"ctrl\x03k": 1}, [{"c": "ok"}, {"c": "bad\x04"}],
         [1.0, 2.5, -0.0, 1e21, 1e-7], {"f": 1.7976931348623157e308}, {"t": (1, 2)}, [True, 1, 1.0, "1"],
     ]
+    # keys the reference emits unquoted with a RAW newline (its `$` admits a final "\n"; columnar header fields are never quoted): what follows
+    # the newline is re-indented by every enclosing level that re-splits the nested text
+    newline_keys = [
+        {"x": {"abc\n": 1}}, {"x": [[{"a\nb": 1}, {"a\nb": 2}]]}, {"x": {"y": [{"k\n": 1}, {"k\n": 2}]}}, {"a": {"b\nc": {"d\ne": 2}}}, [{"abc\n": 1, "z\n": {"q\n": 2}}],
+        [{"k": [{"a\n b ": 1, "c": 2}, {"a\n b ": 3, "c": 4}], "m\n": [1, 2]}], {"p": [{"t\n": [{"u\nv": 1}, {"u\nv": 2}]}]}, {"o\n": {"i\n": {"j\n": [1, {"k\n": 2}]}}},
+        [[{"h\n\nh": "v"}], {"w\n  y\t\n z ": 1}], {"L": [{"first": [{"\u00a0x\n\u2003y ": 1}], "second\n": 2}]},
+    ]
     for _ in range(700):
         inputs.append(rand_json(rng, rng.randint(1, 5)))
+    inputs += newline_keys          # appended: the vectors recorded in earlier rounds keep their positions
     enc_cases = []
     for obj in inputs:
         try:
