@@ -30,8 +30,11 @@ class GpuBatcher:
         self.window_us = window_us
         self.max_units = max_units
         self._batch: Optional[engine.Batch] = None
-        self._pending: Dict[tuple, tuple] = {}   # (id(prog), op, arg) -> (prog, op, arg, [(units, future)])
-        self._scheduled = False
+        # per event loop (a process may run several, e.g. one per thread): (id(prog), op, arg) -> (prog, op, arg, [(units, future)]).
+        # A wave is flushed on the loop that owns its futures; the launches themselves (which share the device batch) are serialised.
+        self._pending: Dict[int, Dict[tuple, tuple]] = {}
+        self._scheduled: Dict[int, bool] = {}
+        self._launch_lock = threading.RLock()
         self.launches = 0
         self.units_seen = 0
 
@@ -159,36 +162,51 @@ class GpuBatcher:
         loop = asyncio.get_running_loop()
         fut: asyncio.Future = loop.create_future()
         key = (id(prog) if prog is not None else 0, op, arg)
-        if key not in self._pending:
-            self._pending[key] = (prog, op, arg, [])
-        self._pending[key][3].append((list(units), fut))
-        if not self._scheduled:
-            self._scheduled = True
+        lid = id(loop)
+        mine = self._pending.setdefault(lid, {})
+        if key not in mine:
+            mine[key] = (prog, op, arg, [])
+        mine[key][3].append((list(units), fut))
+        if not self._scheduled.get(lid):
+            self._scheduled[lid] = True
             if self.window_us > 0:
-                loop.call_later(self.window_us / 1e6, self._flush)
+                loop.call_later(self.window_us / 1e6, self._flush, lid)
             else:
-                loop.call_soon(self._flush)
+                loop.call_soon(self._flush, lid)
         return await fut
 
-    def _flush(self) -> None:
-        self._scheduled = False
-        pending, self._pending = self._pending, {}
+    def _dispatch(self, prog, op: str, arg: int, groups):
+        with self._launch_lock:                      # the launches share the device batch: one at a time
+            if op == "scan":
+                return self.scan_groups(prog, groups)
+            if op == "sub":
+                return self.sub_groups(prog, groups, arg)
+            if op == "scan_sub":
+                return self.scan_sub_groups(prog, groups, arg)
+            return self.toon_groups(groups, bool(arg))
+
+    def _flush(self, lid: int) -> None:
+        self._scheduled[lid] = False
+        pending = self._pending.pop(lid, {})
         for prog, op, arg, waiters in pending.values():
-            try:
-                groups = [w[0] for w in waiters]
-                if op == "scan":
-                    results = self.scan_groups(prog, groups)
-                elif op == "sub":
-                    results = self.sub_groups(prog, groups, arg)
-                elif op == "scan_sub":
-                    results = self.scan_sub_groups(prog, groups, arg)
-                else:
-                    results = self.toon_groups(groups, bool(arg))
-            except Exception as exc:  # surface the failure to every caller (no silent fallback)
-                for _, fut in waiters:
+            # a wave never outgrows max_units: split it between callers (one caller's units stay together)
+            chunks, cur, cur_n = [], [], 0
+            for w in waiters:
+                if cur and cur_n + len(w[0]) > self.max_units:
+                    chunks.append(cur)
+                    cur, cur_n = [], 0
+                cur.append(w)
+                cur_n += len(w[0])
+            if cur:
+                chunks.append(cur)
+            for chunk in chunks:
+                try:
+                    results = self._dispatch(prog, op, arg, [w[0] for w in chunk])
+                except Exception as exc:  # surface the failure to every caller (no silent fallback)
+                    for _, fut in chunk:
+                        if not fut.done():
+                            fut.set_exception(exc)
+                    continue
+                for (_, fut), res in zip(chunk, results):
                     if not fut.done():
-                        fut.set_exception(exc)
-                continue
-            for (_, fut), res in zip(waiters, results):
-                if not fut.done():
-                    fut.set_result(res)
+                        fut.set_result(res)

@@ -17,6 +17,7 @@ limits raise RuntimeError — never a silent different answer.
 """
 from __future__ import annotations
 
+import threading
 from typing import Any, Dict, List, Optional, Sequence
 
 from . import engine
@@ -27,8 +28,18 @@ NESTED_TOO_DEEP = "<nested too deep>"
 _RUST_WHITE_SPACE = frozenset("\t\n\x0b\x0c\r \x85\xa0                　")
 
 
+_own_batch: Optional[engine.Batch] = None
+_own_lock = threading.RLock()
+
+
 def _batch(nbytes: int, nunits: int) -> engine.Batch:
-    return GpuBatcher.get()._ensure_batch(nbytes, nunits)
+    """The masker's OWN device batch (the plugins' GpuBatcher has its own): a logging middleware thread and the hook chain's event
+    loop never overwrite each other's upload.  Callers hold `_own_lock` for the upload + launch + download of one call."""
+    global _own_batch
+    b = _own_batch
+    if b is None or nbytes > b.max_bytes or nunits > b.max_units:
+        _own_batch = b = engine.Batch(GpuBatcher.get().ctx, max(nbytes * 2, 1 << 20, b.max_bytes if b else 0), max(nunits * 2, 1024, b.max_units if b else 0))
+    return b
 
 
 def mask_sensitive_json_bytes_batch(payloads: Sequence[bytes], max_depth: Optional[int] = None) -> List[Optional[bytes]]:
@@ -37,7 +48,8 @@ def mask_sensitive_json_bytes_batch(payloads: Sequence[bytes], max_depth: Option
         return []
     depth = 10 if max_depth is None else int(max_depth)
     stream, offs = engine.pack_units(list(payloads))
-    status, outs = engine.mask_host(_batch(len(stream), len(payloads)), stream, offs, depth)
+    with _own_lock:
+        status, outs = engine.mask_host(_batch(len(stream), len(payloads)), stream, offs, depth)
     res: List[Optional[bytes]] = []
     for st, o in zip(status, outs):
         if st == engine.MASK_OK:
@@ -98,7 +110,9 @@ def _classify(keys: Dict[str, bool]) -> None:
         return
     enc = [n.encode("utf-8", "surrogatepass") for n in names]
     nbytes = sum(len(e) + 1 for e in enc)
-    for n, s in zip(names, engine.classify_keys_host(_batch(nbytes, len(enc)), enc)):
+    with _own_lock:
+        flags = engine.classify_keys_host(_batch(nbytes, len(enc)), enc)
+    for n, s in zip(names, flags):
         keys[n] = s
 
 

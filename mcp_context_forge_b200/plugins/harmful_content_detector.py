@@ -27,9 +27,10 @@ DEFAULT_LEXICONS: Dict[str, List[str]] = {
 
 
 class HarmfulContentConfig(BaseModel):
-    """reference :55-89 (patterns are kept as source text; compilation targets the GPU engine)."""
+    """reference :55-89 (string patterns are kept as source text and compiled with IGNORECASE for the GPU engine; a pre-compiled
+    `re.Pattern` keeps ITS OWN flags, like the reference's `p if not isinstance(p, str)` :72-75)."""
 
-    categories: Dict[str, List[str]] = {}
+    categories: Dict[str, List[Any]] = {}
     block_on: List[str] = ["self_harm", "violence", "hate"]
     redact: bool = False
     redaction_text: str = "[REDACTED]"
@@ -38,8 +39,10 @@ class HarmfulContentConfig(BaseModel):
         if "categories" not in data:
             data["categories"] = {c: list(p) for c, p in DEFAULT_LEXICONS.items()}
         else:
-            data["categories"] = {c: [p if isinstance(p, str) else p.pattern for p in pats] for c, pats in data["categories"].items()}
+            data["categories"] = {c: list(pats) for c, pats in data["categories"].items()}
         super().__init__(**data)
+
+    model_config = {"arbitrary_types_allowed": True}
 
 
 def _iter_strings(value: Any) -> Iterable[Tuple[str, str]]:
@@ -62,11 +65,17 @@ class HarmfulContentDetectorPlugin(Plugin):
         self._cfg = HarmfulContentConfig(**(config.config or {}))
         self._bits: List[Tuple[str, str]] = []          # bit index -> (category, pattern source)
         self._prog = engine.Program()
+        self._flags: List[int] = []
         for cat, pats in self._cfg.categories.items():
             for p in pats:
-                re.compile(p, re.IGNORECASE)            # same validation (and re.error) as the reference :76,85
-                self._prog.add_search(p, re.IGNORECASE)  # raises UnsupportedPattern loudly; no CPU fallback
-                self._bits.append((cat, p))
+                if isinstance(p, str):
+                    re.compile(p, re.IGNORECASE)        # same validation (and re.error) as the reference :76,85
+                    src, fl = p, int(re.IGNORECASE)
+                else:
+                    src, fl = p.pattern, int(p.flags)   # a pre-compiled pattern is used as it is (reference :72-75)
+                self._prog.add_search(src, fl)          # raises UnsupportedPattern loudly; no CPU fallback
+                self._bits.append((cat, src))
+                self._flags.append(fl)
         self._prog.compile_host()
         self._batcher: GpuBatcher | None = None
 
@@ -74,7 +83,7 @@ class HarmfulContentDetectorPlugin(Plugin):
     CHAIN_HOOKS = ("prompt_pre_fetch", "tool_post_invoke")
 
     def chain_register(self, prog: engine.Program) -> bool:
-        self._chain_bits = [prog.add_search(p, re.IGNORECASE) for _, p in self._bits]
+        self._chain_bits = [prog.add_search(p, fl) for (_, p), fl in zip(self._bits, self._flags)]
         self._chain_mask = 0
         for b in self._chain_bits:
             self._chain_mask |= 1 << b
