@@ -161,7 +161,7 @@ __device__ __noinline__ void verify_candidate(const ScanParams& P, const cf::Dfa
     uint32_t col, len = 0;
     const bool eot = s[q] == cf::TERM;
     if (eot) col = t.ncols - 1;
-    else col = cf::classify(t, cf::utf8_decode(s, q, q + 4, &len));
+    else col = cf::final_nl(t, cf::classify(t, cf::utf8_decode(s, q, q + 4, &len)), s[q + 1] == cf::TERM);
     uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
     uint32_t a = e >> cf::ACC_SHIFT;
     if (a) {
@@ -799,6 +799,7 @@ static int upload_dfa(cf_ctx* ctx, const cfre::DfaOut& d, DevDfa& o) {
   o.t.ncols = d.ncols;
   o.t.W = d.W;
   for (int i = 0; i < 4; ++i) { o.t.start_state[i] = d.start_state[i]; o.t.start_adv[i] = d.start_adv[i]; }
+  o.t.nl_cls = d.nl_cls; o.t.nlf_cls = d.nlf_cls;
   return CF_OK;
 }
 

@@ -168,6 +168,7 @@ struct Prog {
 // ---------------------------------------------------------------------------------------------
 struct Classes {
   uint32_t ncls = 0;
+  uint32_t nl_cls = 0, nlf_cls = 0xFFFFFFFFu;   // class of '\n'; class of "the '\n' that is the unit's last character" (only when some `$` needs it)
   std::vector<uint16_t> ascii_cls;
   std::vector<uint32_t> range_start;
   std::vector<uint16_t> range_cls;
@@ -246,6 +247,20 @@ static int build_classes(const Prog& prog, const CharSet& word, Classes& C, std:
   if (C.range_start.empty() || C.range_start[0] != 0x80) {
     if (err) *err = "internal: class ranges"; return CF_E_BADARG;
   }
+  C.nl_cls = C.ascii_cls['\n'];
+  // A non-MULTILINE `$` (AS_END_DOLLAR) holds at the end of the text AND before a final "\n".  The automata see one character of
+  // look-ahead, so "a newline that is the last character" becomes a character class of its own: it behaves like '\n' everywhere,
+  // the matchers substitute it for '\n' at the last position (scan_core.h), and `$` tests for it.  Only built when some `$` needs it.
+  bool need_nlf = false;
+  for (auto& in : prog.insts) if (in.op == I_ASSERT && in.kind == AS_END_DOLLAR) need_nlf = true;
+  if (need_nlf) {
+    C.nlf_cls = C.ncls++;
+    C.cls_ctx.push_back(cf::P_NL);
+    for (size_t s = 0; s < nsets; ++s) C.set_has[s].push_back(C.set_has[s][C.nl_cls]);
+    C.ascii_members.push_back(std::vector<uint8_t>(128, 0));
+    C.ascii_members.back()['\n'] = 1;
+    for (int L = 2; L <= 4; ++L) C.lead[L].push_back(std::vector<uint8_t>(256, 0));
+  }
   return 0;
 }
 
@@ -314,7 +329,8 @@ struct DfaBuilder {
       case AS_NOT_WORD_B: if (P == cf::P_START && eot) return false; return (P == cf::P_WORD) == nw;
       case AS_BEGIN_STRING: return P == cf::P_START;
       case AS_BEGIN_LINE: return P == cf::P_START || P == cf::P_NL;
-      case AS_END_STRING: case AS_END_DOLLAR: return eot;
+      case AS_END_STRING: return eot;
+      case AS_END_DOLLAR: return eot || col == C.nlf_cls;
       case AS_END_LINE: return eot || nnl;
     }
     return false;
@@ -424,6 +440,7 @@ struct DfaBuilder {
     o.ascii_cls = C.ascii_cls; o.range_start = C.range_start; o.range_cls = C.range_cls;
     o.cls_ctx = C.cls_ctx; o.trans = trans; o.accsets = accsets;
     o.ncols = C.ncls + 1; o.nstates = (uint32_t)states.size(); o.W = W;
+    o.nl_cls = C.nl_cls; o.nlf_cls = C.nlf_cls;
     for (int i = 0; i < 4; ++i) o.start_state[i] = start_state[i];
   }
 };

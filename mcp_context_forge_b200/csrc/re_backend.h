@@ -42,6 +42,7 @@ struct DfaOut {
   std::vector<uint32_t> trans;        // nstates * ncols
   std::vector<uint64_t> accsets;      // naccs * W
   uint32_t ncols = 0, nstates = 0, W = 1;
+  uint32_t nl_cls = 0, nlf_cls = 0xFFFFFFFFu;   // see cf::DfaTables
   uint32_t start_state[4] = {0, 0, 0, 0};
   uint32_t start_adv[4] = {0, 0, 0, 0};   // ordered DFAs: start states that do not accept a zero-length match (re.sub's must_advance)
 };

@@ -49,7 +49,12 @@ struct DfaTables {
   uint32_t W;                   // u64 words per verdict bitmap
   uint32_t start_state[4];      // indexed by previous-character context
   uint32_t start_adv[4];        // ordered DFAs only: the same, but a zero-length match at the start position does not count
+  uint32_t nl_cls, nlf_cls;     // class of '\n'; class that stands for "the '\n' that is the unit's LAST character" (a non-MULTILINE `$`
+                                // holds in front of it) or NO_CLS when no pattern needs the distinction
 };
+static const uint32_t NO_CLS = 0xFFFFFFFFu;
+// column of the character that was just classified: the final newline of the unit gets its own class when the program asks for it
+CF_HD uint32_t final_nl(const DfaTables& t, uint32_t col, bool last_char) { return (col == t.nl_cls && last_char && t.nlf_cls != NO_CLS) ? t.nlf_cls : col; }
 
 // Decode one UTF-8 scalar (generalised: surrogates ED A0..BF xx are accepted, Python's
 // 'surrogatepass').  `p < end` is required.  Never reads at or beyond `end`.
@@ -95,7 +100,7 @@ CF_HD uint32_t verify_search(const DfaTables& t, const uint8_t* s, uint64_t usta
   while (S != DEAD) {
     uint32_t col, len = 0;
     if (q >= uend) col = t.ncols - 1;
-    else col = classify(t, utf8_decode(s, q, uend, &len));
+    else col = final_nl(t, classify(t, utf8_decode(s, q, uend, &len)), q + 1 == uend);
     uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
     uint32_t a = e >> ACC_SHIFT;
     if (a) for (uint32_t w = 0; w < t.W; ++w) bits[w] |= t.accsets[(uint64_t)a * t.W + w];
@@ -122,7 +127,7 @@ CF_HD uint64_t match_first(const DfaTables& t, const uint8_t* s, uint64_t ustart
   while (S != DEAD) {
     uint32_t col, len = 0;
     if (q >= uend) col = t.ncols - 1;
-    else col = classify(t, utf8_decode(s, q, uend, &len));
+    else col = final_nl(t, classify(t, utf8_decode(s, q, uend, &len)), q + 1 == uend);
     uint32_t e = t.trans[(uint64_t)S * t.ncols + col];
     if (e >> ACC_SHIFT) last = q;
     S = e & 0xFFFFu;
@@ -149,7 +154,7 @@ struct NfaView {
 };
 CF_HD uint64_t pike_scratch_words(uint32_t ninst, uint32_t nslots) { return (uint64_t)ninst * (1 + 2 + 2ull * nslots + 6) + nslots; }
 
-CF_HD bool assert_holds(uint32_t kind, uint32_t P, uint32_t col, uint32_t eot_col, const uint8_t* cls_ctx) {
+CF_HD bool assert_holds(uint32_t kind, uint32_t P, uint32_t col, uint32_t eot_col, const uint8_t* cls_ctx, uint32_t nlf_cls) {
   const bool eot = col == eot_col;
   const bool nw = !eot && cls_ctx[col] == P_WORD, nnl = !eot && cls_ctx[col] == P_NL;
   switch (kind) {
@@ -157,7 +162,8 @@ CF_HD bool assert_holds(uint32_t kind, uint32_t P, uint32_t col, uint32_t eot_co
     case 2: if (P == P_START && eot) return false; return (P == P_WORD) == nw;   // \B (sre: never on an empty string)
     case 3: return P == P_START;                                          // \A
     case 4: return P == P_START || P == P_NL;                             // ^ (MULTILINE)
-    case 5: case 7: return eot;                                           // \Z
+    case 5: return eot;                                                   // \Z
+    case 7: return eot || col == nlf_cls;                                 // $ without MULTILINE: also before a final newline
     case 6: return eot || nnl;                                            // $ (MULTILINE)
   }
   return false;
@@ -183,7 +189,7 @@ CF_HD void pike_add(const DfaTables& t, const NfaView& N, PikeList& L, uint32_t 
         break;
       }
       case N_SPLIT: stack[sp++] = y; stack[sp++] = CAP_UNSET; stack[sp++] = x; stack[sp++] = CAP_UNSET; break;
-      case N_ASSERT: if (assert_holds(arg, P, col, t.ncols - 1, t.cls_ctx)) { stack[sp++] = x; stack[sp++] = CAP_UNSET; } break;
+      case N_ASSERT: if (assert_holds(arg, P, col, t.ncols - 1, t.cls_ctx, t.nlf_cls)) { stack[sp++] = x; stack[sp++] = CAP_UNSET; } break;
       case N_SAVE:
         stack[sp++] = arg; stack[sp++] = cur[arg] == CAP_UNSET ? CAP_UNSET - 1 : cur[arg];
         cur[arg] = pos;
@@ -209,7 +215,7 @@ CF_HD bool pike_captures(const DfaTables& t, const NfaView& N, const uint8_t* s,
   uint32_t P = (p == ustart) ? (uint32_t)P_START : prev_context(t, s, ustart, p);
   uint64_t q = p;
   uint32_t len = 0;
-  uint32_t col = q >= uend ? t.ncols - 1 : classify(t, utf8_decode(s, q, uend, &len));
+  uint32_t col = q >= uend ? t.ncols - 1 : final_nl(t, classify(t, utf8_decode(s, q, uend, &len)), q + 1 == uend);
   A.n = 0;
   cur[0] = (uint32_t)(p - ustart);
   pike_add(t, N, A, N.start, (uint32_t)(q - ustart), P, col, cur, visited, ++stamp, stack);
@@ -219,7 +225,7 @@ CF_HD bool pike_captures(const DfaTables& t, const NfaView& N, const uint8_t* s,
     uint32_t len2 = 0, col2 = t.ncols - 1, P2 = P_OTHER;
     if (col != t.ncols - 1) {
       P2 = t.cls_ctx[col];
-      if (q2 < uend) col2 = classify(t, utf8_decode(s, q2, uend, &len2));
+      if (q2 < uend) col2 = final_nl(t, classify(t, utf8_decode(s, q2, uend, &len2)), q2 + 1 == uend);
     }
     B.n = 0;
     ++stamp;

@@ -149,11 +149,14 @@ def _emit_node(out: List[int], node, flags: int, mode: str, tail: bool, groups: 
             if multiline:
                 out.extend((A_ASSERT, AS_END_LINE))
             else:
-                # `$` == end of string, or just before a final "\n".  Expressed as
-                # (?:\Z|\n\Z), which is exact only when nothing can follow it.
-                if mode != "search" or not tail:
-                    raise UnsupportedPattern("'$' is supported only at the end of a search pattern")
-                out.extend((A_ALT, 2, A_ASSERT, AS_END_STRING, A_CAT, 2, A_SET, 1, 10, 10, A_ASSERT, AS_END_STRING))
+                # `$` == end of string, or just before a final "\n".  At the end of a SEARCH pattern that is (?:\Z|\n\Z) — exact for
+                # existence, and it keeps the automaton free of the extra character class.  Anywhere else, and in substitution rules
+                # (where consuming the newline would change the extent), it is the assertion AS_END_DOLLAR: the back-end gives "the
+                # newline that is the unit's last character" a class of its own and the assertion looks one character ahead.
+                if mode == "search" and tail:
+                    out.extend((A_ALT, 2, A_ASSERT, AS_END_STRING, A_CAT, 2, A_SET, 1, 10, 10, A_ASSERT, AS_END_STRING))
+                else:
+                    out.extend((A_ASSERT, AS_END_DOLLAR))
         elif av in (_k.AT_BOUNDARY, _k.AT_NON_BOUNDARY):
             if flags & _k.SRE_FLAG_ASCII:
                 raise UnsupportedPattern(r"ASCII-mode \b")

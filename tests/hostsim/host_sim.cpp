@@ -21,6 +21,7 @@ static cf::DfaTables tables_of(const cfre::DfaOut& d) {
   t.ncols = d.ncols;
   t.W = d.W;
   for (int i = 0; i < 4; ++i) { t.start_state[i] = d.start_state[i]; t.start_adv[i] = d.start_adv[i]; }
+  t.nl_cls = d.nl_cls; t.nlf_cls = d.nlf_cls;
   return t;
 }
 

@@ -72,6 +72,7 @@ FEATURE_PATTERNS = [
     (r"\bto\b.*\bdie\b", 0), (r"s(?i:UI)cide", 0), (r"[à-ÿ]+", re.I), (r"[kK]ill", 0), (r"ı|İ", re.I), (r"[^\W\d_]+", 0),
     (r"(?a)\w+\d", 0), (r"µ", re.I), (r"ͅ", re.I), (r"ǆ", re.I), (r"σ+", re.I), (r"[\U00010400-\U00010410]", re.I), (r"\.", 0),
     (r"", 0), (r"\b", 0), (r"\B", 0), (r"x?", 0), (r"(want|need) to (die|live)", 0), (r"[-_.]{2}", 0), (r"\x1c", 0), (r"\ud800", 0),
+    (r"die$\n", 0), (r"kill$.", re.S), (r"(?:die|kill$)\s", 0), (r"$\n\Z", 0),          # `$` inside a pattern: holds before the FINAL newline only
 ]
 
 
@@ -134,8 +135,7 @@ def test_unsupported_and_invalid():
             compile_ast(bad)
     with pytest.raises(re.error):
         compile_ast(r"(unclosed")
-    with pytest.raises(UnsupportedPattern):
-        compile_ast(r"a$b")
+    compile_ast(r"a$b")                        # a `$` in the middle is legal (and, without MULTILINE, can still hold before a final newline)
     with pytest.raises(UnsupportedPattern):
         compile_ast(r"(?:a*)*b", 0, "sub")     # unbounded repeat of a nullable body: sre's empty-iteration rule is not expressible
 
@@ -143,7 +143,7 @@ def test_unsupported_and_invalid():
 NULLABLE_RULES = [
     (r"x*", 0, "-"), (r"x*?", 0, "-"), (r"", 0, "·"), (r"\b", 0, "|"), (r"^", re.M, "> "), (r"$", re.M, ";"), (r"[ \t]*$", re.M, "!"), (r"\s*\Z", 0, ""), (r"^\s*", 0, ""),
     (r"a?", 0, "<>"), (r"a??", 0, "[]"), (r"(?:ab)?", 0, "é"), (r"\B", 0, "_"), (r"x*|y", 0, "#"), (r"|x", 0, "#"), (r"x|", 0, "#"), (r"\d*", 0, "N"),
-    (r"(?:x|xy)?", 0, "Q"), (r"\Z", 0, "END"), (r"\A\s*", 0, "^"), (r"[ \t]*(?:\n|\Z)", 0, "/"), (r"k*\b", re.I, "."), (r"\w{0,2}", 0, "w"),
+    (r"(?:x|xy)?", 0, "Q"), (r"$", 0, "!"), (r"\s*$", 0, ""), (r"x*$", 0, "E"), (r"$\n?", 0, "<>"), (r"(?:a|$)b?", 0, "~"), (r"\Z", 0, "END"), (r"\A\s*", 0, "^"), (r"[ \t]*(?:\n|\Z)", 0, "/"), (r"k*\b", re.I, "."), (r"\w{0,2}", 0, "w"),
 ]
 
 

@@ -25,7 +25,7 @@ def atom(rng, depth):
             items += "a-c"
         return "[" + ("^" if rng.random() < 0.3 else "") + items + "]"
     if r < 0.72:
-        return rng.choice([r"\b", r"\B", "^"])
+        return rng.choice([r"\b", r"\B", "^", "$"])
     if depth <= 0:
         return re.escape(rng.choice(ALPH))
     return "(?:" + "|".join(seq(rng, depth - 1) for _ in range(rng.randint(1, 3))) + ")"
@@ -35,7 +35,7 @@ def seq(rng, depth):
     out = []
     for _ in range(rng.randint(1, 4)):
         a = atom(rng, depth)
-        if a not in (r"\b", r"\B", "^") and rng.random() < 0.35:
+        if a not in (r"\b", r"\B", "^", "$") and rng.random() < 0.35:
             a += rng.choice(["*", "+", "?", "{2}", "{1,3}", "*?", "+?", "??"])
         out.append(a)
     return "".join(out)
