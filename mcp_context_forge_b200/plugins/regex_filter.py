@@ -4,8 +4,10 @@
 Same class name, config schema (`words: [{search, replace}]`) and hooks.  `pattern.sub(replacement,
 value)` applied rule after rule (reference :127-130, :147-155) runs on the GPU: one fused scan marks
 the values some rule matches, the substitution kernel rewrites only those (leftmost-first,
-non-overlapping, rules in order).  Invalid patterns are skipped exactly as the reference does
-(:73-75); valid patterns the GPU engine cannot express raise at construction (no CPU fallback).
+non-overlapping, rules in order; rules that can match "" follow `re.sub`'s empty-match rules, replacement
+templates may reference groups — `\\1`, `\\g<name>` — resolved by a capture pass on the GPU).  Invalid patterns are
+skipped exactly as the reference does (:73-75); valid patterns the GPU engine cannot express (back-references,
+look-around, a repeat of a nullable body) raise at construction (no CPU fallback).
 """
 from __future__ import annotations
 
