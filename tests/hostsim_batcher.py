@@ -1,0 +1,164 @@
+"""TEST-ONLY: the plugins' device interface (`GpuBatcher`, `engine.Program`, the manager's fused launch) on the CPU simulator of
+the engine (tests/hostsim: the same front-end, automata, substitution / capture routines and JSON->TOON encoder the kernels are
+built from).  With `install(monkeypatch)` the drop-in plugins and `BatchedPluginManager` run end to end in the `-m "not gpu"`
+suite: their host logic — unit extraction, verdict -> result assembly, speculate / replay — is the product's own code; only the
+launches are simulated.  Nothing here is reachable from the product package."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import hostsim_util as hs
+from mcp_context_forge_b200 import batching, engine, manager as mgr
+from mcp_context_forge_b200 import regex_frontend as fe
+
+
+class RecordingProgram(engine.Program):
+    """engine.Program that also remembers what was added, so that the same program can be rebuilt on the simulator's builder."""
+
+    def __init__(self):
+        super().__init__()
+        self.rec: List[tuple] = []
+
+    def add_search(self, pattern: str, flags: int = 0) -> int:
+        self.rec.append(("search", pattern, flags))
+        return super().add_search(pattern, flags)
+
+    def add_literal(self, word: str) -> int:
+        self.rec.append(("literal", word))
+        return super().add_literal(word)
+
+    def add_sub(self, pattern: str, flags: int, replacement) -> int:
+        self.rec.append(("sub", pattern, flags, replacement))
+        return super().add_sub(pattern, flags, replacement)
+
+    def compile(self, ctx):                       # no device here: the host half of compilation is what exists on a CPU box
+        self.compile_host()
+        self.h, self.ctx = object(), ctx
+        return self
+
+
+class SimProgram:
+    def __init__(self, rec: Sequence[tuple]):
+        self.hp = hp = hs.HostProgram()
+        self.rule_bits: List[int] = []
+        for r in rec:
+            if r[0] == "search":
+                hp.add(r[1], r[2])
+            elif r[0] == "literal":
+                hp.add_ast(fe.literal_ast(r[1]))
+            else:
+                repl = r[3]
+                if isinstance(repl, str):
+                    repl = [repl] if repl else []
+                refs = any(isinstance(p, int) for p in repl)
+                self.rule_bits.append(hp.add(r[1], r[2], ordered=True, repl=repl if refs else "".join(repl)))
+        self.empty = not rec
+        if rec:
+            hp.compile()
+
+    def scan(self, units: Sequence[str]) -> List[int]:
+        return [0] * len(units) if self.empty else self.hp.scan(list(units))[0]
+
+    def sub(self, text: str) -> str:
+        for r in range(len(self.rule_bits)):
+            text = self.hp.sub(r, text)[0]
+        return text
+
+    @property
+    def rule_mask(self) -> int:
+        m = 0
+        for b in self.rule_bits:
+            m |= 1 << b
+        return m
+
+
+_cache = {}
+
+
+def sim_of(prog) -> SimProgram:
+    key = (id(prog), len(prog.rec))
+    if key not in _cache:
+        _cache[key] = SimProgram(prog.rec)
+    return _cache[key]
+
+
+def _text(u) -> str:
+    return u if isinstance(u, str) else bytes(u).decode("utf-8", "surrogatepass")
+
+
+class SimBatcher(batching.GpuBatcher):
+    """GpuBatcher whose synchronous cores run on the simulator (the asyncio coalescing above them is the product's)."""
+
+    def __init__(self):
+        self.window_us, self.max_units = 0, 1 << 16
+        self._pending, self._scheduled = {}, {}
+        import threading
+
+        self._launch_lock = threading.RLock()
+        self.launches = self.units_seen = 0
+        self.ctx = None
+
+    def _account(self, groups):
+        self.launches += 1
+        self.units_seen += sum(len(g) for g in groups)
+
+    def scan_groups(self, prog, groups):
+        self._account(groups)
+        sp = sim_of(prog)
+        return [sp.scan([_text(u) for u in g]) for g in groups]
+
+    def sub_groups(self, prog, groups, rule_mask):
+        self._account(groups)
+        sp = sim_of(prog)
+        out = []
+        for g in groups:
+            ts = [_text(u) for u in g]
+            out.append([sp.sub(t).encode("utf-8", "surrogatepass") if b & rule_mask else None for t, b in zip(ts, sp.scan(ts))])
+        return out
+
+    def scan_sub_groups(self, prog, groups, rule_mask):
+        self._account(groups)
+        sp = sim_of(prog)
+        out = []
+        for g in groups:
+            ts = [_text(u) for u in g]
+            out.append([(b, sp.sub(t).encode("utf-8", "surrogatepass") if b & rule_mask else None) for t, b in zip(ts, sp.scan(ts))])
+        return out
+
+    def toon_groups(self, groups, report_errors: bool = True):
+        self._account(groups)
+        res = []
+        for g in groups:
+            row = []
+            for u in g:
+                st, txt = hs.toon_host(_text(u))
+                row.append((st, txt.encode("utf-8") if st == 0 else None))
+            res.append(row)
+        return res
+
+
+def sim_launch(self, chain, units, stages):
+    """BatchedPluginManager._launch on the simulator: the contract of cf_run_batch (include/cfgpu.h) per unit."""
+    sp = sim_of(chain.prog)
+    bms = sp.scan(units) if chain.has_patterns else [0] * len(units)
+    out = []
+    for u, st, bm in zip(units, stages, bms):
+        rew: Optional[str] = None
+        if (st & 2) and (bm & sp.rule_mask):
+            rew = sp.sub(u)
+        tstat, ttxt = 8, None                                   # CF_TOON_SKIPPED
+        if st & 8 and rew is None:
+            tstat, t = hs.toon_host(u)
+            ttxt = t.encode("utf-8") if tstat == 0 else None
+        out.append(mgr.UnitResult(bm, rew, tstat, ttxt))
+    return out
+
+
+def install(monkeypatch) -> SimBatcher:
+    sim = SimBatcher()
+    monkeypatch.setattr(engine, "Program", RecordingProgram)
+    monkeypatch.setattr(batching.GpuBatcher, "get", classmethod(lambda cls, device=0: sim))
+    monkeypatch.setattr(engine.Context, "get", classmethod(lambda cls, device=0: object()))
+    monkeypatch.setattr(mgr.BatchedPluginManager, "_launch", sim_launch)
+    _cache.clear()
+    return sim

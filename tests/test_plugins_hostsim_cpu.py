@@ -1,0 +1,127 @@
+"""The drop-in plugins and the chain-level manager END TO END on the CPU simulator of the engine (tests/hostsim_batcher.py): the
+plugins' own host logic and the manager's speculate / replay against the golden vectors recorded from the reference's plugin files and
+against the sequential executor.  The same checks run against the real kernels in tests/test_plugins_gpu.py / test_manager_gpu.py."""
+import asyncio
+import json
+import os
+import tempfile
+
+import pytest
+
+import hostsim_batcher
+from mcp_context_forge_b200 import framework as fw
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CTX = fw.PluginContext(global_context=fw.GlobalContext(request_id="t"))
+
+
+def run(coro):
+    return asyncio.new_event_loop().run_until_complete(coro)
+
+
+def load(name):
+    with open(os.path.join(GOLD, name), encoding="utf-8") as f:
+        return json.load(f)
+
+
+@pytest.fixture()
+def sim(monkeypatch):
+    return hostsim_batcher.install(monkeypatch)
+
+
+@pytest.mark.parametrize("which", ["pattern_plugins.json", "regex_filter_templates.json"])
+def test_regex_filter_golden(sim, which):
+    from mcp_context_forge_b200.plugins.regex_filter import SearchReplacePlugin
+
+    blocks = load(which)
+    blocks = blocks["regex_filter"] if isinstance(blocks, dict) else blocks
+    n = 0
+    for block in blocks:
+        plug = SearchReplacePlugin(fw.PluginConfig(name="rf", kind="x", hooks=["tool_pre_invoke", "tool_post_invoke"], config={"words": block["words"]}))
+
+        async def go():
+            return await asyncio.gather(*[plug.tool_pre_invoke(fw.ToolPreInvokePayload(name="t", args=c["args"]), CTX) if c["hook"] == "tool_pre_invoke"
+                                          else plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result=c["result"]), CTX) for c in block["cases"]])
+
+        for c, r in zip(block["cases"], run(go())):
+            if c["hook"] == "tool_pre_invoke":
+                assert r.modified_payload.args == c["out_args"], c
+            else:
+                assert r.modified_payload.result == c["out_result"], c
+            n += 1
+    assert n >= 200 and sim.launches > 0
+
+
+def test_deny_and_harmful_golden(sim):
+    from mcp_context_forge_b200.plugins.deny_filter import DenyListPlugin
+    from mcp_context_forge_b200.plugins.harmful_content_detector import HarmfulContentDetectorPlugin
+
+    gold = load("pattern_plugins.json")
+    for block in gold["deny_filter"]:
+        plug = DenyListPlugin(fw.PluginConfig(name="dl", kind="x", hooks=["prompt_pre_fetch"], config={"words": block["words"]}))
+        for c in block["cases"]:
+            r = run(plug.prompt_pre_fetch(fw.PromptPrehookPayload(prompt_id="p", args=c["args"]), CTX))
+            assert (not r.continue_processing) == c["blocked"], c
+            if c["violation"]:
+                assert r.violation.model_dump(include=set(c["violation"])) == c["violation"]
+    for block in gold["harmful"]:
+        plug = HarmfulContentDetectorPlugin(fw.PluginConfig(name="hc", kind="x", hooks=["tool_post_invoke"], config=block["config"]))
+        for c in block["cases"]:
+            r = run(plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result=c["result"]), CTX))
+            assert r.continue_processing == c["continue_processing"] and r.metadata == c["metadata"], c
+            got = json.loads(json.dumps(r.violation.model_dump(include=set(c["violation"])))) if r.violation else None     # tuples -> lists, like the recorded vectors
+            assert got == c["violation"], c
+
+
+def test_toon_encoder_plugin_golden(sim):
+    from mcp_context_forge_b200.plugins.toon_encoder import ToonEncoderPlugin
+
+    n = 0
+    for block in load("toon.json")["plugin"]:
+        if block["config"] and block["config"].get("skip_on_error") is False:
+            continue                                       # error reporting past the size cut-off is exercised on the GPU path
+        plug = ToonEncoderPlugin(fw.PluginConfig(name="te", kind="x", hooks=["tool_post_invoke"], config=block["config"]))
+        for c in block["cases"]:
+            if "raises" in c:
+                continue
+            r = run(plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result=c["result"]), CTX))
+            if c["modified"] is None:
+                assert r.modified_payload is None and r.continue_processing, c["result"]
+            else:
+                assert r.modified_payload.result == c["modified"], c["result"]
+                md = dict(r.metadata)
+                assert isinstance(md.pop("conversion_time_ms"), float)
+                assert md == c["metadata"]
+            n += 1
+        assert plug.get_stats() == block["stats"]
+    assert n >= 300
+
+
+def test_batched_manager_equals_sequential_manager(sim):
+    """BatchedPluginManager (one fused launch per wave, speculate / replay) == PluginManager (plugin after plugin) — on the simulator."""
+    import test_manager_gpu as tm
+    from mcp_context_forge_b200.manager import BatchedPluginManager
+
+    for harm_mode, regex_prio in (("sequential", 150), ("transform", 50)):
+        with tempfile.TemporaryDirectory() as td:
+            cfg = os.path.join(td, "plugins.yaml")
+            with open(cfg, "w") as f:
+                f.write(tm.YAML % {"harm_mode": harm_mode, "regex_prio": regex_prio})
+            seq, bat = fw.PluginManager(cfg, timeout=120, hook_policies=tm.POL), BatchedPluginManager(cfg, timeout=120, hook_policies=tm.POL)
+            loop = asyncio.new_event_loop()
+            loop.run_until_complete(seq.initialize())
+            loop.run_until_complete(bat.initialize())
+            pre, tpre, post = tm.payloads(60, 11)
+            gcs = [fw.GlobalContext(request_id=f"r{i}") for i in range(len(pre))]
+            for hook, pls in (("prompt_pre_fetch", pre), ("tool_pre_invoke", tpre), ("tool_post_invoke", post)):
+                for vae in (False, True):
+                    async def wave(m):
+                        return await asyncio.gather(*[m.invoke_hook(hook, p, g, None, vae) for p, g in zip(pls, gcs)], return_exceptions=True)
+                    a = loop.run_until_complete(wave(seq))
+                    before = bat.launch_calls
+                    b = loop.run_until_complete(wave(bat))
+                    assert bat.launch_calls - before == 1
+                    bad = [(i, tm.norm(x), tm.norm(y)) for i, (x, y) in enumerate(zip(a, b)) if tm.norm(x) != tm.norm(y)]
+                    assert not bad, (hook, vae, bad[:2])
+            if regex_prio == 50:
+                assert bat.slow_path_calls > 0
