@@ -15,6 +15,7 @@ from pydantic import BaseModel
 
 from .. import engine
 from ..batching import GpuBatcher
+from ..cpex_compat.framework import fast_construct
 from ..framework import (Plugin, PluginConfig, PluginContext, PluginViolation, PromptPrehookPayload, PromptPrehookResult,
                          ToolPostInvokePayload, ToolPostInvokeResult)
 
@@ -136,8 +137,11 @@ class HarmfulContentDetectorPlugin(Plugin):
             return cls(continue_processing=False,
                        violation=PluginViolation(reason="Harmful content", description=f"Detected categories: {', '.join(cats)}", code="HARMFUL_CONTENT",
                                                  details={"categories": cats, "findings": findings[:5]}))
-        return cls(metadata={"harmful_categories": cats}) if cats else cls.model_construct(continue_processing=True, modified_payload=None, violation=None, metadata={},
-                                                                                          retry_delay_ms=0)
+        if cats:
+            return cls(metadata={"harmful_categories": cats})
+        if not findings:         # the overwhelmingly common result: nothing found (same field values as `cls()`, without pydantic's generic constructor)
+            return fast_construct(cls, {"continue_processing": True, "modified_payload": None, "violation": None, "metadata": {}, "retry_delay_ms": 0})
+        return cls()
 
     async def prompt_pre_fetch(self, payload: PromptPrehookPayload, context: PluginContext) -> PromptPrehookResult:
         """reference :157-181."""

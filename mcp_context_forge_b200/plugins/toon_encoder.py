@@ -37,6 +37,8 @@ class ToonEncoderPlugin(Plugin):
         self._total_bytes_saved = 0
         self._items_unsupported = 0
         self._batcher: Optional[GpuBatcher] = None
+        self._elig_memo: Dict[int, tuple] = {}      # id(text) -> (text, eligibility) for non-ASCII texts (see _eligible)
+        self._elig_bytes = 0
 
     def _should_process_tool(self, tool_name: str) -> bool:
         if self._include_tools is not None:
@@ -53,10 +55,20 @@ class ToonEncoderPlugin(Plugin):
         if text.isascii():                  # len(text.encode("utf-8")) without the copy (the common case)
             n = len(text)
             return text if self._min_size_bytes <= n <= self._max_size_bytes else None
+        # non-ASCII: the size test needs the UTF-8 length.  The chain-level manager asks about the same `str` object up to three times
+        # per request (speculate, identity check, finish): remember the last answers by object identity.
+        memo = self._elig_memo
+        hit = memo.get(id(text))
+        if hit is not None and hit[0] is text:
+            return hit[1]
         raw = text.encode("utf-8")          # raises UnicodeEncodeError on lone surrogates, like the reference's len(text.encode("utf-8"))
-        if len(raw) < self._min_size_bytes or len(raw) > self._max_size_bytes:
-            return None
-        return raw
+        res = None if len(raw) < self._min_size_bytes or len(raw) > self._max_size_bytes else raw
+        self._elig_bytes += len(raw)
+        if self._elig_bytes > (32 << 20):   # bounded: a wave's worth of texts, never more than 32 MB of them
+            memo.clear()
+            self._elig_bytes = len(raw)
+        memo[id(text)] = (text, res)
+        return res
 
     def _new_item(self, item: Dict[str, Any], toon_text: str) -> Dict[str, Any]:
         """reference :305-324."""
