@@ -611,10 +611,34 @@ def payload_matches(payload: Any, hook_type: Any, conditions: list[PluginConditi
 _osa = object.__setattr__
 
 
+_defaults_cache: dict = {}
+
+
+def _missing_defaults(cls: type, given: dict) -> list:
+    """(name, is_factory, default) of the model fields `given` does not name; cached per (class, given key set)."""
+    key = (cls, frozenset(given))
+    hit = _defaults_cache.get(key)
+    if hit is None:
+        hit = []
+        for name, f in cls.model_fields.items():
+            if name in given:
+                continue
+            if f.default_factory is not None:
+                hit.append((name, True, f.default_factory))
+            else:
+                hit.append((name, False, None if f.is_required() else f.default))
+        _defaults_cache[key] = hit
+    return hit
+
+
 def fast_construct(cls: type, values: dict) -> Any:
-    """`cls.model_construct(**values)` for a model without private attributes when EVERY field is given (no defaults to fill,
-    no validation — the values come from our own code): four attribute stores instead of pydantic's generic path (≈ 4x faster;
-    the executor builds five such objects per request)."""
+    """`cls.model_construct(**values)` for a model without private attributes: no validation (the values come from our own code),
+    fields that are not given take their declared defaults (so the call stays correct when the installed cpex declares more fields
+    than the ones named here), four attribute stores instead of pydantic's generic path (≈ 4x faster; the executor builds five
+    such objects per request)."""
+    if len(values) != len(cls.model_fields):        # (the callers name every field of the stand-in models: the common case skips this)
+        for name, is_factory, d in _missing_defaults(cls, values):
+            values[name] = d() if is_factory else d
     m = cls.__new__(cls)
     _osa(m, "__dict__", values)
     _osa(m, "__pydantic_fields_set__", set(values))

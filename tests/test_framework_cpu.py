@@ -153,3 +153,28 @@ def test_gpu_plugins_construct_and_reject_unsupported():
     h = HarmfulContentDetectorPlugin(fw.PluginConfig(name="a", kind="x"))
     assert len(h._bits) == 9
     DenyListPlugin(fw.PluginConfig(name="a", kind="x", config={"words": ["a", ""]}))
+
+
+def test_fast_construct_and_copy_match_pydantic():
+    """The executor's constructor-free paths: same objects as `model_construct` / `model_copy`, also when the installed framework
+    declares more fields than the call names (a real cpex may)."""
+    from typing import Any, Optional
+
+    from pydantic import BaseModel, Field
+
+    from mcp_context_forge_b200.cpex_compat.framework import fast_construct, fast_copy
+
+    class Wider(BaseModel):
+        a: int
+        b: Optional[dict[str, Any]] = Field(default_factory=dict)
+        c: str = "dflt"
+        d: Optional[int] = None
+
+    x = fast_construct(Wider, {"a": 1})
+    assert x == Wider.model_construct(a=1) and x.model_dump() == {"a": 1, "b": {}, "c": "dflt", "d": None}
+    y = fast_construct(Wider, {"a": 2})
+    assert y.b is not x.b                                            # default factories run per object
+    z = fast_copy(x, {"c": "new"})
+    assert z == x.model_copy(update={"c": "new"}) and x.c == "dflt" and z.b is x.b
+    r = fast_construct(fw.PluginResult, {"continue_processing": True, "modified_payload": None, "violation": None, "metadata": {}, "retry_delay_ms": 0})
+    assert r == fw.PluginResult() and r.model_dump() == fw.PluginResult().model_dump()
