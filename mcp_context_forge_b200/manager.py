@@ -50,6 +50,7 @@ class _Chain:
         self.refs = refs
         self.prog = engine.Program()
         self.uuids = [h.plugin_ref.uuid for h in refs]   # PluginRef.uuid formats a UUID on every access
+        self.modes = [_effective_mode(h.plugin_ref) for h in refs]   # (mode, on_error) as configured; `ref.disabled` is checked per request
         self.member = {}                      # ref.uuid -> plugin speaks the protocol for this hook
         self.toon_flags = 0
         n_pat = 0
@@ -254,10 +255,9 @@ class BatchedPluginManager(PluginManager):
         metadata: dict[str, Any] = {}
         retry_delay_ms = 0
         fail_all = bool(self._config and self._config.plugin_settings.fail_on_plugin_error)
-        for href, uid in zip(chain.refs, chain.uuids):
+        for href, uid, (mode, on_error) in zip(chain.refs, chain.uuids, chain.modes):
             ref = href.plugin_ref
-            mode, on_error = _effective_mode(ref)
-            if mode == PluginMode.DISABLED:
+            if ref.disabled or mode == PluginMode.DISABLED:
                 continue
             if ref.conditions and not payload_matches(current, hook, ref.conditions, global_context):
                 continue

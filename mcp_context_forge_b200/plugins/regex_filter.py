@@ -22,7 +22,7 @@ from .. import engine
 from ..batching import GpuBatcher
 from ..framework import (Plugin, PluginConfig, PluginContext, PromptPosthookPayload, PromptPosthookResult, PromptPrehookPayload, PromptPrehookResult,
                          ToolPostInvokePayload, ToolPostInvokeResult, ToolPreInvokePayload, ToolPreInvokeResult)
-from ..cpex_compat.framework import fast_copy
+from ..cpex_compat.framework import fast_construct, fast_copy
 from ..regex_frontend import UnsupportedPattern, template_parts  # noqa: F401
 
 
@@ -100,7 +100,7 @@ class SearchReplacePlugin(Plugin):
                 payload = fast_copy(payload, {"result": {k: (next(it) if isinstance(v, str) else v) for k, v in r.items()}})
             elif r and isinstance(r, str):
                 payload = fast_copy(payload, {"result": new[0]})
-            return ToolPostInvokeResult(modified_payload=payload)
+            return fast_construct(ToolPostInvokeResult, {"continue_processing": True, "modified_payload": payload, "violation": None, "metadata": {}, "retry_delay_ms": 0})
         if payload.args:
             it = iter(new)
             payload = fast_copy(payload, {"args": {k: (next(it) if isinstance(v, str) else v) for k, v in payload.args.items()}})

@@ -15,6 +15,7 @@ from typing import Any, Dict, List, Optional
 
 from .. import engine
 from ..batching import GpuBatcher
+from ..cpex_compat.framework import fast_construct
 from ..framework import Plugin, PluginConfig, PluginContext, ToolPostInvokePayload, ToolPostInvokeResult
 
 logger = logging.getLogger(__name__)
@@ -188,11 +189,14 @@ class ToonEncoderPlugin(Plugin):
             duration_ms = (time.monotonic() - start_time) * 1000
             savings_pct = (bytes_saved / total_original * 100) if total_original > 0 else 0
             new_result = {**result, "content": new_content}
-            return ToolPostInvokeResult(
-                modified_payload=ToolPostInvokePayload(name=tool_name, result=new_result),
-                metadata={"toon_encoded": True, "bytes_saved": bytes_saved, "savings_percent": round(savings_pct, 2), "conversion_time_ms": round(duration_ms, 2)},
-            )
-        return ToolPostInvokeResult(continue_processing=True)
+            # (constructor-free: every value is ours and well-typed; same objects as ToolPostInvokePayload(name=, result=) / ...Result(...))
+            return fast_construct(ToolPostInvokeResult, {
+                "continue_processing": True,
+                "modified_payload": fast_construct(ToolPostInvokePayload, {"name": tool_name, "result": new_result}),
+                "violation": None,
+                "metadata": {"toon_encoded": True, "bytes_saved": bytes_saved, "savings_percent": round(savings_pct, 2), "conversion_time_ms": round(duration_ms, 2)},
+                "retry_delay_ms": 0})
+        return fast_construct(ToolPostInvokeResult, {"continue_processing": True, "modified_payload": None, "violation": None, "metadata": {}, "retry_delay_ms": 0})
 
     def get_stats(self) -> Dict[str, Any]:
         """reference :328-363."""
