@@ -21,6 +21,21 @@ from . import engine
 Unit = Union[str, bytes]
 
 
+
+class _NoopResult:
+    """What a chain member returns from `chain_finish` when its hook would return the empty result (continue, no payload, no violation, no
+    metadata): one shared immutable stand-in instead of a model per request; the replay skips it like the executor skips an empty result."""
+    __slots__ = ()
+    continue_processing = True
+    modified_payload = None
+    violation = None
+    metadata: dict = {}
+    retry_delay_ms = 0
+
+
+NOOP_RESULT = _NoopResult()
+
+
 class GpuBatcher:
     _instances: Dict[int, "GpuBatcher"] = {}
     _ilock = threading.Lock()

@@ -14,7 +14,7 @@ from typing import Any, Dict, Iterable, List, Tuple
 from pydantic import BaseModel
 
 from .. import engine
-from ..batching import GpuBatcher
+from ..batching import NOOP_RESULT, GpuBatcher
 from ..cpex_compat.framework import fast_construct
 from ..framework import (Plugin, PluginConfig, PluginContext, PluginViolation, PromptPrehookPayload, PromptPrehookResult,
                          ToolPostInvokePayload, ToolPostInvokeResult)
@@ -110,6 +110,8 @@ class HarmfulContentDetectorPlugin(Plugin):
                 for i, sb in enumerate(self._chain_bits):
                     if (bm >> sb) & 1:
                         findings.append(self._bits[i])
+        if not findings:
+            return NOOP_RESULT
         return self._result(PromptPrehookResult if hook == "prompt_pre_fetch" else ToolPostInvokeResult, findings)
 
     def _gpu(self) -> GpuBatcher:

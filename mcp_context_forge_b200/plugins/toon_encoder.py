@@ -14,7 +14,7 @@ import time
 from typing import Any, Dict, List, Optional
 
 from .. import engine
-from ..batching import GpuBatcher
+from ..batching import NOOP_RESULT, GpuBatcher
 from ..cpex_compat.framework import fast_construct
 from ..framework import Plugin, PluginConfig, PluginContext, ToolPostInvokePayload, ToolPostInvokeResult
 
@@ -114,12 +114,12 @@ class ToonEncoderPlugin(Plugin):
         start_time = time.monotonic()
         content = self._content(payload)
         if content is None:
-            return ToolPostInvokeResult(continue_processing=True)
+            return NOOP_RESULT
         self._tools_processed += 1
         raws = [self._eligible(item) for item in content]
         it = iter(results)
         outcomes = {i: (r.toon_status, r.toon_text) for i, raw in enumerate(raws) if raw is not None for r in (next(it),)}
-        return self._finish(payload, content, raws, outcomes, start_time)
+        return self._finish(payload, content, raws, outcomes, start_time, NOOP_RESULT)
 
     async def tool_post_invoke(self, payload: ToolPostInvokePayload, _context: PluginContext) -> ToolPostInvokeResult:
         start_time = time.monotonic()
@@ -144,7 +144,7 @@ class ToonEncoderPlugin(Plugin):
                 outcomes[i] = oc
         return self._finish(payload, content, raws, outcomes, start_time)
 
-    def _finish(self, payload: ToolPostInvokePayload, content, raws, outcomes, start_time) -> ToolPostInvokeResult:
+    def _finish(self, payload: ToolPostInvokePayload, content, raws, outcomes, start_time, unchanged=None) -> ToolPostInvokeResult:
         """Everything after the per-item conversion (reference :285-326, :170-219): identical for the per-plugin and the chain path."""
         tool_name = payload.name
         result = payload.result
@@ -196,6 +196,8 @@ class ToonEncoderPlugin(Plugin):
                 "violation": None,
                 "metadata": {"toon_encoded": True, "bytes_saved": bytes_saved, "savings_percent": round(savings_pct, 2), "conversion_time_ms": round(duration_ms, 2)},
                 "retry_delay_ms": 0})
+        if unchanged is not None:           # (chain path: the manager's shared empty result)
+            return unchanged
         return fast_construct(ToolPostInvokeResult, {"continue_processing": True, "modified_payload": None, "violation": None, "metadata": {}, "retry_delay_ms": 0})
 
     def get_stats(self) -> Dict[str, Any]:
