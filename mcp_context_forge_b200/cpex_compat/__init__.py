@@ -50,7 +50,19 @@ def install_as_cpex(force: bool = False) -> bool:
                 ToolPreInvokeResult=fw.ToolPreInvokeResult, ToolPostInvokeResult=fw.ToolPostInvokeResult)
     prompts = mod("cpex.framework.hooks.prompts", PromptHookType=fw.PromptHookType, PromptPrehookPayload=fw.PromptPrehookPayload, PromptPosthookPayload=fw.PromptPosthookPayload,
                   PromptPrehookResult=fw.PromptPrehookResult, PromptPosthookResult=fw.PromptPosthookResult)
-    hooks.policies, hooks.tools, hooks.prompts = policies, tools, prompts
+    def names(prefix: str) -> dict:
+        return {k: getattr(fw, k) for k in fw.__all__ if k.startswith(prefix)}
+
+    resources = mod("cpex.framework.hooks.resources", **names("Resource"))
+    agents = mod("cpex.framework.hooks.agents", **names("Agent"))
+    http = mod("cpex.framework.hooks.http", **names("Http"))
+    hooks.policies, hooks.tools, hooks.prompts, hooks.resources, hooks.agents, hooks.http = policies, tools, prompts, resources, agents, http
+    # module paths the reference's tests import from (tests/integration/test_rate_limiter.py:44-46, tests/unit/plugins/test_sql_sanitizer.py:4)
+    manager = mod("cpex.framework.manager", PluginManager=fw.PluginManager, PluginExecutor=fw.PluginExecutor, TenantPluginManager=fw.TenantPluginManager)
+    base = mod("cpex.framework.base", Plugin=fw.Plugin, PluginRef=fw.PluginRef, HookRef=fw.HookRef)
+    errors = mod("cpex.framework.errors", PluginError=fw.PluginError, PluginViolationError=fw.PluginViolationError)
+    memory = mod("cpex.framework.memory", CopyOnWriteDict=fw.CopyOnWriteDict)
+    fw.manager, fw.base, fw.errors, fw.memory = manager, base, errors, memory
     constants = mod("cpex.framework.constants", GATEWAY_METADATA="gateway_metadata", TOOL_METADATA="tool_metadata")
     utils = mod("cpex.framework.utils", payload_matches=fw.payload_matches, get_attr=fw.get_attr)
     obs = mod("cpex.framework.observability", current_trace_id=__import__("contextvars").ContextVar("current_trace_id", default=None), ObservabilityProvider=fw.ObservabilityProvider)

@@ -31,7 +31,7 @@ from enum import Enum
 from typing import Any, Dict, Generic, List, Optional, Protocol, TypeVar, Union, runtime_checkable
 
 import yaml
-from pydantic import BaseModel, ConfigDict, Field, RootModel
+from pydantic import BaseModel, ConfigDict, Field, RootModel, field_validator
 
 logger = logging.getLogger("cpex_compat")
 
@@ -231,9 +231,40 @@ class PromptPrehookPayload(PluginPayload):
     args: Optional[dict[str, Any]] = Field(default_factory=dict)
 
 
+class _PromptText(BaseModel):
+    model_config = ConfigDict(extra="allow")
+    type: str = "text"
+    text: str
+
+
+class _PromptMessage(BaseModel):
+    model_config = ConfigDict(extra="allow")
+    role: Any
+    content: Union[_PromptText, Any]
+
+
+class PromptResult(BaseModel):
+    """A rendered prompt given as a plain mapping is read into a model (the reference's plugins address `result.messages[i].content.text` on
+    the payload they built from a dict: plugins/test_prompt_output_sentinel.py:79-111, its test :61-81); the gateway's own
+    `mcpgateway.common.models.PromptResult` instances pass through untouched."""
+    model_config = ConfigDict(extra="allow")
+    messages: List[_PromptMessage]
+    description: Optional[str] = None
+
+
 class PromptPosthookPayload(PluginPayload):
     prompt_id: str
     result: Any = None
+
+    @field_validator("result", mode="before")
+    @classmethod
+    def _mapping_to_model(cls, v: Any) -> Any:
+        if isinstance(v, dict) and isinstance(v.get("messages"), list):
+            try:
+                return PromptResult.model_validate(v)
+            except Exception:  # noqa: BLE001 - not a prompt result after all: keep the mapping
+                return v
+        return v
 
 
 class ResourcePreFetchPayload(PluginPayload):
@@ -607,6 +638,25 @@ def payload_matches(payload: Any, hook_type: Any, conditions: list[PluginConditi
     return False
 
 
+class CopyOnWriteDict(dict):
+    """cpex.framework.memory.CopyOnWriteDict as far as this tree shows it (tests/unit/plugins/test_sql_sanitizer.py:39-52 builds tool
+    arguments with it and the plugins walk them as a `dict`): a dict whose writes never reach the mapping it was made from — the items are
+    taken at construction, `original` keeps the wrapped mapping, `modified` names the keys written or deleted since."""
+
+    def __init__(self, original: Any = None, **kwargs: Any) -> None:
+        super().__init__(original or {}, **kwargs)
+        self.original = original if original is not None else {}
+        self.modified: set = set()
+
+    def __setitem__(self, key: Any, value: Any) -> None:
+        self.modified.add(key)
+        super().__setitem__(key, value)
+
+    def __delitem__(self, key: Any) -> None:
+        self.modified.add(key)
+        super().__delitem__(key)
+
+
 # --------------------------------------------------------------------------------------------- manager
 _osa = object.__setattr__
 
@@ -680,24 +730,145 @@ def _effective_mode(ref: PluginRef) -> tuple:
     return mode, on_error
 
 
+_mlog = logging.getLogger("cpex.framework.manager")        # the logger name the reference's tests listen on (tests/integration/test_rate_limiter.py:672)
+
+
+class PluginExecutor:
+    """cpex.framework.manager.PluginExecutor: the loop behind `PluginManager.invoke_hook`.  Pinned by reference-held tests of the real
+    cpex executor: tests/integration/test_rate_limiter.py:644-745 (`execute_plugin`: a TRANSFORM-mode violation is suppressed in the result
+    and logged as "... raised violation ..." at WARNING, a SEQUENTIAL one raises with `violations_as_exceptions`; `execute`: DISABLED plugins
+    are skipped) and tests/unit/mcpgateway/plugins/agent/test_agent_plugins.py (chaining, violations, contexts across hooks) — both run
+    unmodified against this class by tools/run_reference_tests.py; tests/test_executor_reference_cases.py restates them."""
+
+    def __init__(self, config: Optional[Config] = None, timeout: int = 30, observability: Optional[ObservabilityProvider] = None,
+                 hook_policies: Optional[dict[str, HookPayloadPolicy]] = None) -> None:
+        self.config = config
+        self.timeout = timeout
+        self.observability = observability
+        self.hook_policies = hook_policies
+
+    def apply_policy(self, hook: str, current: Any, modified: Any) -> Any:
+        """Only policy-writable fields of `modified` are accepted (mcpgateway/plugins/policy.py:24-45)."""
+        if modified is None or modified is current:
+            return current
+        policy = (self.hook_policies or {}).get(hook)
+        if policy is None or not isinstance(current, BaseModel) or type(modified) is not type(current):
+            return modified
+        key = (frozenset(policy.writable_fields), type(current))
+        fields = _policy_fields.get(key)
+        if fields is None:                          # the policy's writable fields this payload type declares (asked once per policy and type)
+            fields = _policy_fields[key] = tuple(f for f in policy.writable_fields if f in type(current).model_fields)
+        updates = {}
+        for f in fields:
+            v = getattr(modified, f)
+            if v is not getattr(current, f):
+                updates[f] = v
+        return fast_copy(current, updates) if updates else current
+
+    async def run_one(self, ref: PluginRef, hook: str, payload: Any, ctx: PluginContext) -> PluginResult:
+        fn = getattr(ref.plugin, hook)
+        return await asyncio.wait_for(fn(payload, ctx), timeout=self.timeout)
+
+    async def execute_plugin(self, hook_ref: HookRef, payload: Any, local_context: PluginContext, violations_as_exceptions: bool = False,
+                             global_context: Optional[GlobalContext] = None, combined_metadata: Optional[dict] = None) -> PluginResult:
+        """One plugin of a chain with its mode applied.  Returns what the chain may act on: a violation (or `continue_processing=False`)
+        is only left in the result of a blocking (SEQUENTIAL) plugin; the payload of an AUDIT / FIRE_AND_FORGET plugin is dropped; a
+        plugin that failed and may be skipped yields the empty result."""
+        ref = hook_ref.plugin_ref
+        hook = hook_ref.name
+        mode, on_error = _effective_mode(ref)
+        fail_all = bool(self.config and self.config.plugin_settings.fail_on_plugin_error)
+        try:
+            result = await self.run_one(ref, hook, payload, local_context)
+        except (PluginViolationError, PluginError):
+            raise
+        except Exception as exc:  # timeout or plugin bug
+            msg = f"Plugin {ref.name} exceeded {self.timeout}s timeout" if isinstance(exc, asyncio.TimeoutError) else str(exc)
+            _mlog.error("Plugin %s failed in %s: %s", ref.name, hook, msg)
+            if fail_all or (mode == PluginMode.SEQUENTIAL and on_error == OnError.FAIL):
+                raise PluginError(error=PluginErrorModel(message=msg, plugin_name=ref.name)) from exc
+            if on_error == OnError.DISABLE:
+                ref.disabled = True
+            return PluginResult(continue_processing=True)
+        if result is None:
+            return PluginResult(continue_processing=True)
+        if combined_metadata is not None and result.metadata:
+            combined_metadata.update(result.metadata)
+        drop_payload = result.modified_payload is not None and mode in (PluginMode.AUDIT, PluginMode.FIRE_AND_FORGET)
+        if not result.continue_processing or result.violation is not None:
+            if result.violation is not None:
+                result.violation.plugin_name = ref.name
+            if mode == PluginMode.SEQUENTIAL:
+                if violations_as_exceptions:
+                    v = result.violation
+                    raise PluginViolationError(f"{hook} blocked by plugin {ref.name}: {v.code} - {v.reason} ({v.description})" if v else f"{hook} blocked by plugin {ref.name}", violation=v)
+                return fast_copy(result, {"modified_payload": None}) if drop_payload else result
+            v = result.violation
+            _mlog.warning("Plugin %s (%s) raised violation in %s: %s; continuing", ref.name, mode.value, hook, f"{v.code} - {v.reason}" if v else "continue_processing=False")
+            return fast_copy(result, {"continue_processing": True, "violation": None, "modified_payload": None if drop_payload else result.modified_payload})
+        return fast_copy(result, {"modified_payload": None}) if drop_payload else result
+
+    async def execute(self, hook_refs: list, payload: Any, global_context: GlobalContext, hook_type: Any, local_contexts: Optional[PluginContextTable] = None,
+                      violations_as_exceptions: bool = False) -> tuple:
+        """The chain: ascending priority (the registry's order), payload chained through `modified_payload`, `(PluginResult, contexts)` out."""
+        hook = _hook_name(hook_type)
+        contexts: PluginContextTable = {}
+        current = payload
+        changed = False
+        metadata: dict[str, Any] = {}
+        retry_delay_ms = 0
+        for href in hook_refs:
+            ref = href.plugin_ref
+            if ref.mode == PluginMode.DISABLED:
+                continue
+            if ref.conditions and not payload_matches(current, hook, ref.conditions, global_context):
+                continue
+            key = global_context.request_id + ref.uuid
+            ctx = (local_contexts or {}).get(key) or PluginContext(global_context=global_context)
+            contexts[key] = ctx
+            result = await self.execute_plugin(href, current, ctx, violations_as_exceptions, global_context, metadata)
+            retry_delay_ms = max(retry_delay_ms, getattr(result, "retry_delay_ms", 0) or 0)
+            if result.modified_payload is not None:
+                new = self.apply_policy(hook, current, result.modified_payload)
+                if new is not current:
+                    current, changed = new, True
+            if not result.continue_processing or result.violation is not None:
+                return (PluginResult(continue_processing=False, modified_payload=current if changed else None, violation=result.violation, metadata=metadata,
+                                     retry_delay_ms=retry_delay_ms), contexts)
+        return (PluginResult(continue_processing=True, modified_payload=current if changed else None, violation=None, metadata=metadata, retry_delay_ms=retry_delay_ms), contexts)
+
+
 class PluginManager:
-    """Hook-chain executor: ascending priority, payload chained through `modified_payload`, writable
-    fields enforced by the hook policy, violations/errors handled per mode (see module docstring)."""
+    """Hook-chain executor front: configuration, plugin loading and registry; `invoke_hook` hands the hook's refs to a `PluginExecutor`
+    (ascending priority, payload chained through `modified_payload`, writable fields enforced by the hook policy, violations / errors
+    handled per mode — see the module docstring)."""
 
     def __init__(self, config: Union[str, Config] = "", timeout: int = 30, observability: Optional[ObservabilityProvider] = None,
                  hook_policies: Optional[dict[str, HookPayloadPolicy]] = None) -> None:
+        # cpex's manager is a Borg; what this tree pins of it (tests/unit/mcpgateway/plugins/test_observability_adapter.py:258-276): a bare
+        # `PluginManager()` is another reference to the state of the configured one, until `PluginManager.reset()`.  Managers that are
+        # given a configuration (and subclasses: the gateway builds one TenantPluginManager per context) own their state.
+        shared = PluginManager._shared
+        if type(self) is PluginManager and not config and observability is None and hook_policies is None and shared is not None:
+            self.__dict__ = shared
+            return
         self._config: Optional[Config] = ConfigLoader.load_config(config) if isinstance(config, str) and config else (config if isinstance(config, Config) else Config())
         self._timeout = timeout
         self._observability = observability
         self._hook_policies = hook_policies
         self._registry = PluginInstanceRegistry()
         self._loader = PluginLoader()
+        self._executor = PluginExecutor(self._config, timeout, observability, hook_policies)
         self._initialized = False
+        if type(self) is PluginManager:
+            PluginManager._shared = self.__dict__
 
     # -- lifecycle
+    _shared: Optional[dict] = None
+
     @classmethod
     def reset(cls) -> None:
-        return None
+        PluginManager._shared = None
 
     @property
     def config(self) -> Optional[Config]:
@@ -714,6 +885,11 @@ class PluginManager:
     @property
     def observability(self) -> Optional[ObservabilityProvider]:
         return self._observability
+
+    @observability.setter
+    def observability(self, provider: Optional[ObservabilityProvider]) -> None:     # (tests/unit/mcpgateway/plugins/test_observability_adapter.py assigns it)
+        self._observability = provider
+        self._executor.observability = provider
 
     def get_plugin(self, name: str) -> Optional[PluginRef]:
         return self._registry.get_plugin(name)
@@ -742,79 +918,15 @@ class PluginManager:
 
     # -- execution
     def _apply_policy(self, hook: str, current: Any, modified: Any) -> Any:
-        """Only policy-writable fields of `modified` are accepted (mcpgateway/plugins/policy.py:24-45)."""
-        if modified is None or modified is current:
-            return current
-        policy = (self._hook_policies or {}).get(hook)
-        if policy is None or not isinstance(current, BaseModel) or type(modified) is not type(current):
-            return modified
-        key = (frozenset(policy.writable_fields), type(current))
-        fields = _policy_fields.get(key)
-        if fields is None:                          # the policy's writable fields this payload type declares (asked once per policy and type)
-            fields = _policy_fields[key] = tuple(f for f in policy.writable_fields if f in type(current).model_fields)
-        updates = {}
-        for f in fields:
-            v = getattr(modified, f)
-            if v is not getattr(current, f):
-                updates[f] = v
-        return fast_copy(current, updates) if updates else current
+        return self._executor.apply_policy(hook, current, modified)
 
     async def _run_one(self, ref: PluginRef, hook: str, payload: Any, ctx: PluginContext) -> PluginResult:
-        fn = getattr(ref.plugin, hook)
-        return await asyncio.wait_for(fn(payload, ctx), timeout=self._timeout)
+        return await self._executor.run_one(ref, hook, payload, ctx)
 
     async def invoke_hook(self, hook_type: Any, payload: Any, global_context: GlobalContext, local_contexts: Optional[PluginContextTable] = None,
                           violations_as_exceptions: bool = False) -> tuple:
         hook = _hook_name(hook_type)
-        refs = self._registry.get_hook_refs_for_hook(hook)
-        contexts: PluginContextTable = {}
-        current = payload
-        changed = False
-        metadata: dict[str, Any] = {}
-        retry_delay_ms = 0
-        fail_all = bool(self._config and self._config.plugin_settings.fail_on_plugin_error)
-        for href in refs:
-            ref = href.plugin_ref
-            mode, on_error = _effective_mode(ref)
-            if mode == PluginMode.DISABLED:
-                continue
-            if ref.conditions and not payload_matches(current, hook, ref.conditions, global_context):
-                continue
-            key = global_context.request_id + ref.uuid
-            ctx = (local_contexts or {}).get(key) or PluginContext(global_context=GlobalContext(**global_context.model_dump()) if False else global_context)
-            contexts[key] = ctx
-            try:
-                result = await self._run_one(ref, hook, current, ctx)
-            except (PluginViolationError, PluginError):
-                raise
-            except Exception as exc:  # timeout or plugin bug
-                msg = f"Plugin {ref.name} exceeded {self._timeout}s timeout" if isinstance(exc, asyncio.TimeoutError) else str(exc)
-                logger.error("Plugin %s failed in %s: %s", ref.name, hook, msg)
-                if fail_all or (mode == PluginMode.SEQUENTIAL and on_error == OnError.FAIL):
-                    raise PluginError(error=PluginErrorModel(message=msg, plugin_name=ref.name)) from exc
-                if on_error == OnError.DISABLE:
-                    ref.disabled = True
-                continue
-            if result is None:
-                continue
-            if result.metadata:
-                metadata.update(result.metadata)
-            retry_delay_ms = max(retry_delay_ms, getattr(result, "retry_delay_ms", 0) or 0)
-            if result.modified_payload is not None and mode not in (PluginMode.AUDIT, PluginMode.FIRE_AND_FORGET):
-                new = self._apply_policy(hook, current, result.modified_payload)
-                if new is not current:
-                    current, changed = new, True
-            if not result.continue_processing or result.violation is not None:
-                if result.violation is not None:
-                    result.violation.plugin_name = ref.name
-                if mode == PluginMode.SEQUENTIAL:
-                    if violations_as_exceptions:
-                        v = result.violation
-                        raise PluginViolationError(f"{hook} blocked by plugin {ref.name}: {v.code} - {v.reason} ({v.description})" if v else f"{hook} blocked by plugin {ref.name}", violation=v)
-                    return (PluginResult(continue_processing=False, modified_payload=current if changed else None, violation=result.violation, metadata=metadata,
-                                         retry_delay_ms=retry_delay_ms), contexts)
-                logger.warning("Plugin %s (%s) reported a violation in %s; continuing", ref.name, mode.value, hook)
-        return (PluginResult(continue_processing=True, modified_payload=current if changed else None, violation=None, metadata=metadata, retry_delay_ms=retry_delay_ms), contexts)
+        return await self._executor.execute(self._registry.get_hook_refs_for_hook(hook), payload, global_context, hook, local_contexts, violations_as_exceptions)
 
     async def invoke_hook_for_plugin(self, name: str, hook_type: Any, payload: Any, context: Union[GlobalContext, PluginContext, None] = None,
                                      violations_as_exceptions: bool = False, payload_as_json: bool = False) -> PluginResult:
