@@ -536,6 +536,44 @@ def main():
         variants["stress_rule_set_256_literals_32_regexes"] = run_variant(sp, payloads)
         variants["stress_rule_set_256_literals_32_regexes"]["prefilter"] = "pair" if sp.compile_host().prefilter else "byte"
 
+        # BASELINE configs[2]: the pattern scan + request_logging_masking on ONE upload (cf_run_batch, SCAN | MASK): the same JSON payloads as
+        # request bodies; masked bodies come back to the host (they are what the middleware logs).  Last leg on this context, and it never
+        # takes the line down: a failure is reported in place.
+        def run_mask_variant():
+            from mcp_context_forge_b200._native import CF_STAGE_MASK, CF_V_MASKED
+            nm = min(n, 4096)
+            munits = [payloads[i % len(payloads)] for i in range(nm)]
+            ms_, mo = engine.pack_units(munits)
+            mb = engine.Batch(ctx, len(ms_), nm)
+            ms_np = np.frombuffer(ms_, dtype=np.uint8)
+            for _ in range(2):
+                mv, mout, moo, _f = engine.run_batch(prog, mb, ms_np, mo, CF_STAGE_SCAN | CF_STAGE_MASK)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                mv, mout, moo, _f = engine.run_batch(prog, mb, ms_np, mo, CF_STAGE_SCAN | CF_STAGE_MASK)
+            dt = (time.perf_counter() - t0) / 3
+            from oracle import mask_ref
+            ok = True
+            for i in (0, 1, 2, nm // 2, nm - 1):
+                got = mout[int(moo[i]):int(moo[i + 1])].tobytes() if mv["flags"][i] & CF_V_MASKED else None
+                try:
+                    exp = mask_ref.mask_json_bytes(munits[i] if isinstance(munits[i], bytes) else munits[i].encode(), 10)
+                except ValueError:
+                    exp = None
+                ok = ok and got == exp
+            n_out_m = int(moo[-1])
+            return {"payloads_per_s": nm / dt, "ms_per_step": dt * 1e3, "units": nm, "in_bytes": len(ms_), "masked_out_bytes": n_out_m,
+                    "masked_units": int(((mv["flags"] & CF_V_MASKED) != 0).sum()), "flagged_units": int((mv["match_bitmap"] != 0).sum()),
+                    "gb_per_s_in_plus_out": (len(ms_) + n_out_m) / dt / 1e9, "oracle_sample_ok": bool(ok),
+                    "what": "cf_run_batch(SCAN|MASK) with host buffers: H2D of the bodies, scan_kernel + mask_kernel (one lane per body, DESIGN 4.5) on the resident "
+                            "batch, verdicts + masked bodies D2H; max_depth 10"}
+
+        try:
+            variants["configs2_scan_plus_masking"] = run_mask_variant()
+        except Exception as exc:  # noqa: BLE001 - reported, never fatal for the headline line
+            variants["configs2_scan_plus_masking"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- end to end through the plugin API (host objects in, PluginResult out), one worker
     api = None
     if True:
