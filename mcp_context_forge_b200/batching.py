@@ -34,6 +34,7 @@ class _NoopResult:
 
 
 NOOP_RESULT = _NoopResult()
+RUN_HOOK = object()         # `chain_finish` -> "the fused launch does not settle this request: run my hook itself" (the manager awaits the plugin's own hook)
 
 
 class GpuBatcher:

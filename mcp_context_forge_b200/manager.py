@@ -28,7 +28,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 from . import engine
-from .batching import NOOP_RESULT
+from .batching import NOOP_RESULT, RUN_HOOK
 from ._native import CF_STAGE_SCAN, CF_STAGE_SUB, CF_STAGE_TOON, CF_V_REWRITTEN, CF_V_TOON
 from .framework import (GlobalContext, OnError, PluginContext, PluginError, PluginErrorModel, PluginManager, PluginMode, PluginResult,
                         PluginViolationError)
@@ -308,6 +308,8 @@ class BatchedPluginManager(PluginManager):
                             spec = None
                     if spec is not None:
                         result = plugin.chain_finish(hook, current, us, [results[k] for k in idx])
+                        if result is RUN_HOOK:                      # (json_repair: the text does not parse — its repair rounds are the hook's own launches)
+                            spec = None
                 if spec is None:
                     self.slow_path_calls += 1
                     result = await self._run_one(ref, hook, current, ctx)

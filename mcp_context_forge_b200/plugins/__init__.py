@@ -12,4 +12,6 @@
       -> mcp_context_forge_b200.plugins.sql_sanitizer.SQLSanitizerPlugin
   plugins.code_safety_linter.code_safety_linter.CodeSafetyLinterPlugin
       -> mcp_context_forge_b200.plugins.code_safety_linter.CodeSafetyLinterPlugin
+  plugins.json_repair.json_repair.JSONRepairPlugin
+      -> mcp_context_forge_b200.plugins.json_repair.JSONRepairPlugin
 """

@@ -486,11 +486,63 @@ def gen_code_safety():
     dump("code_safety.json", out)
 
 
+# ------------------------------------------------------------------------------------------------
+def gen_json_repair():
+    """plugins/json_repair/json_repair.py (tool_post_invoke; SURVEY §8 row f-2 names it as a consumer of the shared JSON parse).  Inputs stay
+    clear of the orjson / stdlib-json deltas of the stand-in (lone surrogate escapes, NaN literals, integers beyond 64 bits, nesting > 64)."""
+    from cpex.framework import GlobalContext, PluginConfig, PluginContext, ToolPostInvokePayload
+    from plugins.json_repair.json_repair import JSONRepairPlugin
+
+    ctx = PluginContext(global_context=GlobalContext(request_id="golden"))
+    rng = random.Random(4242)
+    plug = JSONRepairPlugin(PluginConfig(name="jr", kind="x", hooks=["tool_post_invoke"]))
+    fixed = [
+        "{'a': 1, 'b': 2,}",                                   # tests/unit/mcpgateway/plugins/plugins/json_repair/test_json_repair.py:31
+        "{'a': 1}", "['x', 'y']", "{'a': \"b\"}", "{'it''s': 1}", "('a')", "{'a': 1", "'a': 1}", "[1, 2, 3,]", "[1, 2, 3, ]", "{\"a\": 1,\n}", "{\"a\": [1, 2,], \"b\": {\"c\": 3,},}",
+        "[1,,]", "[,]", "{,}", "[1 ,\t\n ]", "[\"a, ]\", 1,]", "{\"k\": \"v, }\"}", "[\"a, ]\"]", "\"a\": 1", "\"a\": 1, \"b\": [1, 2]", "a: 1", "'a': 1", "\"a\": 1,", "\"a\": {\"b\": 1}",
+        "\"a\": 1}", "{\"a\": 1", "x: y: z", ":", "\"a\":", "  {\"a\": 1}  ", "\n[1, 2,]\n", "\u00a0{'a': 1}\u00a0", "\u2003[1,]\u2003", "\x0c[1,]", " 'a': 1 ", "\t\"k\": \"v\"\r\n",
+        "", " ", "null", "true", "123", "-0.5e3", "\"str\"", "nul", "[1] x", "[1]\n", "{\"a\": 1}\u00a0", "{}", "[]", "{ }", "[ ]", "{'': ''}", "['']", "{'a': 'b, }'}", "['a,]',]",
+        "{'a': 1,} ", "[\"\\u00e9\", 'x']", "{'é': 'ü',}", "['日本', '語',]", "{\"a\": 1,}trailing", "[1,]]", "[[1,],]", "{\"a\": {\"b\": [1,],},}", "'", "\"", "{'a': 'it\\'s'}",
+        "{'a': 1, \"b\": 2,}", "{\"a\": 'x',}", "[1,\u00a0]", "[1,\u2028]", "[1,\x0b]", "[1,\x1f]", "\"a\": \"x:y\"", "k: [1, 2,]", "\"k\": [1, 2,]", "\"a\": 1, \"a\": 2", "[1, 2}", "{\"a\": 1]",
+    ]
+    gens = []
+    for _ in range(260):
+        v = rand_json(rng, rng.randint(0, 3))
+        t = json.dumps(v, ensure_ascii=rng.random() < 0.5, separators=rng.choice([(",", ":"), (", ", ": "), (" ,\n", " : ")]))
+        k = rng.random()
+        if k < 0.2:
+            pass
+        elif k < 0.4:
+            t = t.replace('"', "'")
+        elif k < 0.6:
+            t = re.sub(r"([}\]])", lambda m: rng.choice([",", ", ", ",\n", ""]) + m.group(1), t)
+        elif k < 0.7:
+            t = re.sub(r"([}\]])", lambda m: rng.choice([",", ""]) + m.group(1), t.replace('"', "'"))
+        elif k < 0.8 and t.startswith("{") and t.endswith("}"):
+            t = t[1:-1]
+        elif k < 0.9:
+            i = rng.randrange(len(t) + 1)
+            t = t[:i] + rng.choice([",", "'", '"', "}", "]", ":", " ", "x", "\n"]) + t[i:]
+        else:
+            i = rng.randrange(len(t)) if t else 0
+            t = t[:i] + t[i + 1:]
+        gens.append(rng.choice(["", "", " ", "\n", "\u00a0"]) + t + rng.choice(["", "", " ", "\r\n", "\u3000"]))
+    others = [None, 5, {"text": "{'a': 1,}"}, ["{'a': 1,}"], {"content": [{"type": "text", "text": "[1,]"}]}, True, 1.5]
+    cases = []
+    for res in fixed + gens + others:
+        if isinstance(res, str) and any(ord(ch) >= 0xD800 and ord(ch) <= 0xDFFF for ch in res):
+            continue
+        r = run(plug.tool_post_invoke(ToolPostInvokePayload(name="t", result=res), ctx))
+        cases.append({"result": res, "continue_processing": r.continue_processing, "out_result": r.modified_payload.result if r.modified_payload is not None else None,
+                      "modified": r.modified_payload is not None, "metadata": r.metadata or {}})
+    dump("json_repair.json", {"cases": cases})
+
+
 if __name__ == "__main__":
     install_shims()
     only = sys.argv[1:]
     for name, fn in (("pattern_plugins", gen_pattern_plugins), ("toon", gen_toon), ("masking", gen_masking), ("sql_sanitizer", gen_sql_sanitizer),
                      ("regex_filter_templates", gen_regex_filter_templates),
-                     ("code_safety", gen_code_safety)):
+                     ("code_safety", gen_code_safety), ("json_repair", gen_json_repair)):
         if not only or name in only:
             fn()

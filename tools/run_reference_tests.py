@@ -37,6 +37,7 @@ DROPIN_TESTS = [
     "tests/unit/plugins/toon_encoder/test_toon_encoder.py",
     "tests/unit/plugins/test_sql_sanitizer.py",
     "tests/unit/mcpgateway/plugins/plugins/code_safety_linter/test_code_safety_linter.py",
+    "tests/unit/mcpgateway/plugins/plugins/json_repair/test_json_repair.py",
 ]
 
 
@@ -97,6 +98,7 @@ def install_shims(dropin: bool) -> None:
         for ref_mod, ours in (("plugins.toon_encoder.toon_encoder", "mcp_context_forge_b200.plugins.toon_encoder"),
                               ("plugins.sql_sanitizer.sql_sanitizer", "mcp_context_forge_b200.plugins.sql_sanitizer"),
                               ("plugins.code_safety_linter.code_safety_linter", "mcp_context_forge_b200.plugins.code_safety_linter"),
+                              ("plugins.json_repair.json_repair", "mcp_context_forge_b200.plugins.json_repair"),
                               ("plugins.regex_filter.search_replace", "mcp_context_forge_b200.plugins.regex_filter"),
                               ("plugins.deny_filter.deny", "mcp_context_forge_b200.plugins.deny_filter"),
                               ("plugins.harmful_content_detector.harmful_content_detector", "mcp_context_forge_b200.plugins.harmful_content_detector")):
