@@ -730,6 +730,17 @@ def _effective_mode(ref: PluginRef) -> tuple:
     return mode, on_error
 
 
+def _result_with(result: Any, updates: dict) -> Any:
+    """A copy of a plugin's result with `updates` applied (a result that is not one of the pydantic result models is rebuilt as a PluginResult)."""
+    try:
+        return fast_copy(result, updates)
+    except AttributeError:
+        base = {"continue_processing": getattr(result, "continue_processing", True), "modified_payload": getattr(result, "modified_payload", None),
+                "violation": getattr(result, "violation", None), "metadata": getattr(result, "metadata", None) or {}}
+        base.update(updates)
+        return PluginResult(**base)
+
+
 _mlog = logging.getLogger("cpex.framework.manager")        # the logger name the reference's tests listen on (tests/integration/test_rate_limiter.py:672)
 
 
@@ -802,11 +813,11 @@ class PluginExecutor:
                 if violations_as_exceptions:
                     v = result.violation
                     raise PluginViolationError(f"{hook} blocked by plugin {ref.name}: {v.code} - {v.reason} ({v.description})" if v else f"{hook} blocked by plugin {ref.name}", violation=v)
-                return fast_copy(result, {"modified_payload": None}) if drop_payload else result
+                return _result_with(result, {"modified_payload": None}) if drop_payload else result
             v = result.violation
             _mlog.warning("Plugin %s (%s) raised violation in %s: %s; continuing", ref.name, mode.value, hook, f"{v.code} - {v.reason}" if v else "continue_processing=False")
-            return fast_copy(result, {"continue_processing": True, "violation": None, "modified_payload": None if drop_payload else result.modified_payload})
-        return fast_copy(result, {"modified_payload": None}) if drop_payload else result
+            return _result_with(result, {"continue_processing": True, "violation": None, "modified_payload": None if drop_payload else result.modified_payload})
+        return _result_with(result, {"modified_payload": None}) if drop_payload else result
 
     async def execute(self, hook_refs: list, payload: Any, global_context: GlobalContext, hook_type: Any, local_contexts: Optional[PluginContextTable] = None,
                       violations_as_exceptions: bool = False) -> tuple:
