@@ -32,7 +32,7 @@ from .batching import NOOP_RESULT, RUN_HOOK
 from ._native import CF_STAGE_SCAN, CF_STAGE_SUB, CF_STAGE_TOON, CF_V_REWRITTEN, CF_V_TOON
 from .framework import (GlobalContext, OnError, PluginContext, PluginError, PluginErrorModel, PluginManager, PluginMode, PluginResult,
                         PluginViolationError)
-from .cpex_compat.framework import _effective_mode, _hook_name, fast_construct, payload_matches  # same helpers the sequential executor uses
+from .cpex_compat.framework import _effective_mode, _hook_name, _mlog, fast_construct, payload_matches  # same helpers the sequential executor uses
 
 logger = logging.getLogger(__name__)
 
@@ -344,6 +344,7 @@ class BatchedPluginManager(PluginManager):
                         raise PluginViolationError(f"{hook} blocked by plugin {ref.name}: {v.code} - {v.reason} ({v.description})" if v else f"{hook} blocked by plugin {ref.name}", violation=v)
                     return (PluginResult(continue_processing=False, modified_payload=current if changed else None, violation=result.violation, metadata=metadata,
                                          retry_delay_ms=retry_delay_ms), contexts)
-                logger.warning("Plugin %s (%s) reported a violation in %s; continuing", ref.name, mode.value, hook)
+                v = result.violation                  # (same record as the sequential executor's: logger `cpex.framework.manager`, "... raised violation ...")
+                _mlog.warning("Plugin %s (%s) raised violation in %s: %s; continuing", ref.name, mode.value, hook, f"{v.code} - {v.reason}" if v else "continue_processing=False")
         return (fast_construct(PluginResult, {"continue_processing": True, "modified_payload": current if changed else None, "violation": None,
                                               "metadata": metadata, "retry_delay_ms": retry_delay_ms}), contexts)
