@@ -72,14 +72,14 @@ class SimProgram:
         return m
 
 
-_cache = {}
 
 
 def sim_of(prog) -> SimProgram:
-    key = (id(prog), len(prog.rec))
-    if key not in _cache:
-        _cache[key] = SimProgram(prog.rec)
-    return _cache[key]
+    """The simulator's build of `prog`, kept ON the program object (an id()-keyed cache would hand a dead program's tables to a new one)."""
+    held = getattr(prog, "_sim", None)
+    if held is None or held[0] != len(prog.rec):
+        held = prog._sim = (len(prog.rec), SimProgram(prog.rec))
+    return held[1]
 
 
 def _text(u) -> str:
@@ -160,5 +160,4 @@ def install(monkeypatch) -> SimBatcher:
     monkeypatch.setattr(batching.GpuBatcher, "get", classmethod(lambda cls, device=0: sim))
     monkeypatch.setattr(engine.Context, "get", classmethod(lambda cls, device=0: object()))
     monkeypatch.setattr(mgr.BatchedPluginManager, "_launch", sim_launch)
-    _cache.clear()
     return sim

@@ -39,3 +39,12 @@ def test_committed_run_records_have_no_unexplained_failure():
         with open(os.path.join(ROOT, "tests", "golden", f"reference_tests_run_{name}.json")) as f:
             s = json.load(f)
         assert s["passed"] > 0 and all(v["bucket"] != "other" for v in s["not_passed_detail"].values())
+
+
+@pytest.mark.parametrize("tool,args", [("fuzz_vs_reference.py", ["5", "4000"]), ("fuzz_mask_vs_reference.py", ["5", "8000", "800"]), ("fuzz_json_repair_vs_reference.py", ["5", "4000"]),
+                                       ("fuzz_plugins_vs_reference.py", ["5", "12"]), ("fuzz_chain_vs_reference.py", ["5", "8", "40"])])
+def test_live_differential_fuzz_against_the_reference(tool, args):
+    """A short run of each container-only differential fuzzer (kernel source on the host build / warp emulator, drop-ins and the batched chain on
+    the CPU simulator) against the reference's own modules; the long runs of the round are recorded in DESIGN.md §5."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), *args], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and " bad=0" in p.stdout, (p.stdout[-2000:], p.stderr[-2000:])
