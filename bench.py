@@ -541,7 +541,7 @@ def main():
         # takes the line down: a failure is reported in place.
         def run_mask_variant():
             from mcp_context_forge_b200._native import CF_STAGE_MASK, CF_V_MASKED
-            nm = min(n, 4096)
+            nm = min(n, 32768)                  # the headline's batch: one lane per body needs a full batch to fill the GPU at all
             munits = [payloads[i % len(payloads)] for i in range(nm)]
             ms_, mo = engine.pack_units(munits)
             mb = engine.Batch(ctx, len(ms_), nm)
