@@ -154,8 +154,31 @@ def sim_launch(self, chain, units, stages):
     return out
 
 
+def sim_mask_host(batch, stream, offsets, max_depth: int = 10):
+    """engine.mask_host on the host build of csrc/json_mask.h: (status int32[n], masked bytes or None per unit)."""
+    import numpy as np
+
+    raw = bytes(stream)
+    st, outs = [], []
+    for i in range(len(offsets) - 1):
+        s, o = hs.mask_host(raw[int(offsets[i]):int(offsets[i + 1]) - 1], max_depth)
+        st.append(s)
+        outs.append(o if s == 0 else None)
+    return np.asarray(st, dtype=np.int32), outs
+
+
+def sim_classify_keys_host(batch, keys):
+    return [hs.key_sensitive_host(k if isinstance(k, str) else bytes(k).decode("utf-8", "surrogatepass")) for k in keys]
+
+
 def install(monkeypatch) -> SimBatcher:
     sim = SimBatcher()
+    from mcp_context_forge_b200 import masking
+
+    monkeypatch.setattr(engine, "mask_host", sim_mask_host)                       # the masking module's three launches, on the simulator
+    monkeypatch.setattr(engine, "classify_keys_host", sim_classify_keys_host)
+    monkeypatch.setattr(masking, "_batch", lambda nbytes, nunits: None)
+    monkeypatch.setattr(masking, "_fallback_prog", None)
     monkeypatch.setattr(engine, "Program", RecordingProgram)
     monkeypatch.setattr(batching.GpuBatcher, "get", classmethod(lambda cls, device=0: sim))
     monkeypatch.setattr(engine.Context, "get", classmethod(lambda cls, device=0: object()))

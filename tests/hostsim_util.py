@@ -177,5 +177,5 @@ def mask_host(payload: bytes, max_depth: int = 10, indexed: bool = False):
 
 
 def key_sensitive_host(key: str) -> bool:
-    b = key.encode("utf-8")
+    b = key.encode("utf-8", "surrogatepass")
     return bool(lib().cfh_key_sensitive(b, len(b)))

@@ -87,7 +87,51 @@ def main() -> int:
             bad += 1
             if bad <= 10:
                 print("BODY", body[:300], md, "\n  reference", json.dumps(exp)[:300], "\n  kernel   ", st, (out or b"")[:300], "\n  oracle   ", orc[:300])
-    print(f"seed={seed} keys={len(seen)} bodies={nb} bad={bad} time={time.time() - t0:.1f}s")
+    # ---- the module a gateway imports (request_logging_masking_native_extension -> mcp_context_forge_b200/masking.py): its host logic (key
+    # collection, cookie splitting, header walk, fallback probes) with the launches on the CPU simulator, against the twin's functions
+    import importlib
+
+    import pytest
+
+    import hostsim_batcher
+
+    hostsim_batcher.install(pytest.MonkeyPatch())
+    mod = importlib.import_module("request_logging_masking_native_extension")
+    from mcp_context_forge_b200 import masking
+
+    # (no U+001C..U+001F around cookie names: Python's str.strip() of the twin strips them, Rust's trim() of the crate — which the drop-in
+    # follows, lib.rs:199-231 — does not; tests/test_mask_gpu.py makes the same exclusion)
+    cookies = ["jwt_token=abc; theme=dark; session_id=xyz", "theme=dark", "", "a=b;c", " SESSION = 1 ;; x=y", "Auth=1;AUTHX=2;nope=3", "tokén=1; TOKEN=2", "noequals; jwt", "a=b=c; token=d=e",
+               "user=john; preference=light", "Bearer abc", "application/json", " \u00a0auth = 1\u3000; x = y ", "İauth=1; ſession=2; K=3"]
+    nm = 0
+    for _ in range(nbodies // 4):
+        obj = rand_obj(rng.randint(1, 6))
+        md = rng.choice([10, None, 3, 1, 0, 2])
+        exp = ns["mask_sensitive_data"](obj, 10 if md is None else md)
+        got = mod.mask_sensitive_data(obj, md)
+        h = {rng.choice(keys + ["Cookie", "cookie", "COOKIE", "CooKie", "Content-Type", "Accept"]): rng.choice(cookies) for _ in range(rng.randint(0, 6))}
+        hexp, hgot = ns["mask_sensitive_headers"](h), mod.mask_sensitive_headers(h)
+        nm += 2
+        if got != exp or hexp != hgot or masking.mask_sensitive_headers_batch([h, h])[1] != hexp:
+            bad += 1
+            if bad <= 10:
+                print("MODULE", repr(obj)[:200], md, "\n  reference", repr(exp)[:200], "\n  module   ", repr(got)[:200], "\n  headers", h, "\n  reference", hexp, "\n  module   ", hgot)
+    words = ["password", "PassWord", "pass phrase", "secret", "SECRET", "toKen", "\u212aey", "api_\u212aey", "api-key", "APIKEY", "apikey", "access_token", "refresh-token", "client_secret",
+             "Authorization", "auth_token", "jwt_token", "private_key", "private key", "İ", "ſecret", "hello", "x=1", "{", "\xff", "日本", " ", "&", "tok", "en"]
+    bodies = [("".join(rng.choice(words) + rng.choice(["", " ", "=", "&", "\n"]) for _ in range(rng.randint(0, 6)))).encode("utf-8", "ignore") + rng.choice([b"", b"\xfe", b"\xc3"]) for _ in range(nbodies // 4)]
+    lows = tuple(ns["SENSITIVE_KEYS"])
+    exp_fb = []
+    for b_ in bodies:
+        s_ = b_.decode("utf-8", errors="ignore")                      # request_logging_middleware.py:661-667
+        exp_fb.append("<contains sensitive data - masked>" if any(k in s_.lower() for k in lows) else s_)
+    got_fb = masking.non_json_fallback_batch(bodies)
+    for b_, e_, g_ in zip(bodies, exp_fb, got_fb):
+        nm += 1
+        if e_ != g_:
+            bad += 1
+            if bad <= 10:
+                print("FALLBACK", b_, "reference", repr(e_), "module", repr(g_))
+    print(f"seed={seed} keys={len(seen)} bodies={nb} module_calls={nm} bad={bad} time={time.time() - t0:.1f}s")
     return 1 if bad else 0
 
 
