@@ -22,6 +22,7 @@ import asyncio
 import concurrent.futures
 import gc
 import logging
+import threading
 import time
 from typing import Any, Dict, List, Optional
 
@@ -45,19 +46,22 @@ class _gc_paused:
     restored when the last pause ends, and it then sees the wave's objects once."""
     _depth = 0
     _was_enabled = False
+    _lock = threading.Lock()        # (managers on several event-loop threads share the process-wide collector switch)
 
     def __enter__(self):
         cls = _gc_paused
-        if cls._depth == 0:
-            cls._was_enabled = gc.isenabled()
-            gc.disable()
-        cls._depth += 1
+        with cls._lock:
+            if cls._depth == 0:
+                cls._was_enabled = gc.isenabled()
+                gc.disable()
+            cls._depth += 1
 
     def __exit__(self, *exc):
         cls = _gc_paused
-        cls._depth -= 1
-        if cls._depth == 0 and cls._was_enabled:
-            gc.enable()
+        with cls._lock:
+            cls._depth -= 1
+            if cls._depth == 0 and cls._was_enabled:
+                gc.enable()
         return False
 
 
@@ -106,7 +110,8 @@ class BatchedPluginManager(PluginManager):
         self._pending: Dict[str, list] = {}
         self._scheduled: Dict[str, bool] = {}
         self._busy: Dict[str, bool] = {}
-        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="cfgpu-chain")
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="cfgpu-chain")   # ONE launch at a time: the waves of every loop share the device batch
+        self._chain_lock = threading.Lock()
         self._ctx: Optional[engine.Context] = None
         self._batch: Optional[engine.Batch] = None
         self.waves = 0
@@ -119,7 +124,11 @@ class BatchedPluginManager(PluginManager):
 
     # ---- chain plans
     def _chain_for(self, hook: str) -> Optional[_Chain]:
-        if hook not in self._chains:
+        if hook in self._chains:
+            return self._chains[hook]
+        with self._chain_lock:                          # (first use from two event-loop threads at once: one builds and compiles the chain)
+            if hook in self._chains:
+                return self._chains[hook]
             refs = [h for h in self._registry.get_hook_refs_for_hook(hook) if h.plugin_ref.mode != PluginMode.DISABLED]
             ch = _Chain(hook, refs) if refs else None
             if ch is not None and not ch.usable:
@@ -129,7 +138,7 @@ class BatchedPluginManager(PluginManager):
                 if ch.has_patterns:
                     ch.prog.compile(self._ctx)
             self._chains[hook] = ch
-        return self._chains[hook]
+            return ch
 
     async def shutdown(self) -> None:
         await super().shutdown()
@@ -143,13 +152,14 @@ class BatchedPluginManager(PluginManager):
             return await super().invoke_hook(hook_type, payload, global_context, local_contexts, violations_as_exceptions)
         loop = asyncio.get_running_loop()
         fut: asyncio.Future = loop.create_future()
-        self._pending.setdefault(hook, []).append((payload, global_context, local_contexts, violations_as_exceptions, fut))
-        if not self._scheduled.get(hook):
-            self._scheduled[hook] = True
+        key = (id(loop), hook)          # waves are per event loop (a process may run one per thread): a future is only ever resolved on the loop that made it
+        self._pending.setdefault(key, []).append((payload, global_context, local_contexts, violations_as_exceptions, fut))
+        if not self._scheduled.get(key):
+            self._scheduled[key] = True
             if self.window_us > 0:
-                loop.call_later(self.window_us / 1e6, lambda: loop.create_task(self._flush(hook)))
+                loop.call_later(self.window_us / 1e6, lambda: loop.create_task(self._flush(key)))
             else:
-                loop.call_soon(lambda: loop.create_task(self._flush(hook)))
+                loop.call_soon(lambda: loop.create_task(self._flush(key)))
         return await fut
 
     async def invoke_hook_batch(self, hook_type: Any, payloads: List[Any], global_contexts: List[GlobalContext], violations_as_exceptions: bool = False) -> list:
@@ -158,25 +168,35 @@ class BatchedPluginManager(PluginManager):
         return await asyncio.gather(*[self.invoke_hook(hook_type, p, g, None, violations_as_exceptions) for p, g in zip(payloads, global_contexts)],
                                     return_exceptions=True)
 
-    async def _flush(self, hook: str) -> None:
-        """One wave at a time per hook: requests that arrive while a wave is on the GPU park and form the next wave the moment it
-        returns (the batch size adapts to the load by itself; `window_us` only adds a floor)."""
-        self._scheduled[hook] = False
-        if self._busy.get(hook):
+    async def _flush(self, key: tuple) -> None:
+        """One wave at a time per (event loop, hook): requests that arrive while a wave is on the GPU park and form the next wave the moment
+        it returns (the batch size adapts to the load by itself; `window_us` only adds a floor)."""
+        hook = key[1]
+        self._scheduled[key] = False
+        if self._busy.get(key):
             return
-        self._busy[hook] = True
+        self._busy[key] = True
         try:
-            while self._pending.get(hook):
-                waiting = self._pending[hook]
-                wave, self._pending[hook] = waiting[: self.max_wave], waiting[self.max_wave:]
+            while self._pending.get(key):
+                waiting = self._pending[key]
+                wave, self._pending[key] = waiting[: self.max_wave], waiting[self.max_wave:]
                 try:
                     await self._run_wave(hook, wave)
-                except BaseException as exc:  # noqa: BLE001 - a failed launch fails every parked request loudly (no CPU fallback)
+                except Exception as exc:  # noqa: BLE001 - a failed launch fails every parked request loudly (no CPU fallback)
                     for *_, fut in wave:
                         if not fut.done():
                             fut.set_exception(exc)
+                except BaseException as exc:  # the flush task itself is being cancelled: the parked requests learn it, the cancellation goes on
+                    for *_, fut in wave:
+                        if not fut.done():
+                            fut.set_exception(RuntimeError(f"BatchedPluginManager: wave aborted ({type(exc).__name__})"))
+                    raise
         finally:
-            self._busy[hook] = False
+            self._busy.pop(key, None)
+            if not self._pending.get(key):              # (loops come and go: no entry outlives its last request)
+                self._pending.pop(key, None)
+                if not self._scheduled.get(key):
+                    self._scheduled.pop(key, None)
 
     # ---- one wave
     def _speculate(self, chain: _Chain, wave: list):

@@ -125,3 +125,57 @@ def test_batched_manager_equals_sequential_manager(sim):
                     assert not bad, (hook, vae, bad[:2])
             if regex_prio == 50:
                 assert bat.slow_path_calls > 0
+
+
+def test_batched_manager_serves_two_event_loops(sim):
+    """One BatchedPluginManager, two threads with an event loop each (a process may run one loop per thread): waves are per loop — every future is
+    resolved on the loop that made it — and the launches of both are serialised; results equal the sequential manager's."""
+    import threading
+
+    import test_manager_gpu as tm
+    from mcp_context_forge_b200.manager import BatchedPluginManager
+
+    with tempfile.TemporaryDirectory() as td:
+        cfg = os.path.join(td, "plugins.yaml")
+        with open(cfg, "w") as f:
+            f.write(tm.YAML % {"harm_mode": "sequential", "regex_prio": 150})
+        seq, bat = fw.PluginManager(cfg, timeout=120, hook_policies=tm.POL), BatchedPluginManager(cfg, timeout=120, hook_policies=tm.POL)
+        run(seq.initialize())
+        run(bat.initialize())
+        sets = [tm.payloads(40, 21), tm.payloads(40, 22)]
+        out, errs = {}, []
+
+        def worker(k):
+            try:
+                loop = asyncio.new_event_loop()
+                pre, tpre, post = sets[k]
+                gcs = [fw.GlobalContext(request_id=f"w{k}r{i}") for i in range(len(pre))]
+                res = []
+                for _ in range(3):
+                    for hook, pls in (("prompt_pre_fetch", pre), ("tool_pre_invoke", tpre), ("tool_post_invoke", post)):
+                        async def wave():
+                            return await asyncio.gather(*[bat.invoke_hook(hook, p, g) for p, g in zip(pls, gcs)], return_exceptions=True)
+                        res.append(loop.run_until_complete(wave()))
+                out[k] = res
+                loop.close()
+            except BaseException as exc:  # noqa: BLE001
+                errs.append(exc)
+
+        ts = [threading.Thread(target=worker, args=(k,)) for k in (0, 1)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(300)
+        assert not errs, errs
+        for k in (0, 1):
+            pre, tpre, post = sets[k]
+            gcs = [fw.GlobalContext(request_id=f"w{k}r{i}") for i in range(len(pre))]
+            exp = []
+            for hook, pls in (("prompt_pre_fetch", pre), ("tool_pre_invoke", tpre), ("tool_post_invoke", post)):
+                async def wave():
+                    return await asyncio.gather(*[seq.invoke_hook(hook, p, g) for p, g in zip(pls, gcs)], return_exceptions=True)
+                exp.append(run(wave()))
+            for r in range(3):
+                for h in range(3):
+                    assert [tm.norm(x) for x in out[k][r * 3 + h]] == [tm.norm(x) for x in exp[h]], (k, r, h)
+        assert not bat._pending and not bat._busy
