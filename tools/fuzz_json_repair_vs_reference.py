@@ -2,7 +2,6 @@
 substitution routines for the trailing-comma rule) against the REFERENCE'S OWN plugins/json_repair/json_repair.py, imported unmodified from
 /root/reference (orjson stood in for by the strict stdlib parser; texts that would expose an orjson / json delta are skipped).
 usage: python tools/fuzz_json_repair_vs_reference.py [seed] [cases]"""
-import json
 import os
 import random
 import re
