@@ -21,21 +21,24 @@ def parses(s: str) -> bool:
         return False
 
 
-def repair(s: str) -> Optional[str]:
+def candidates(s: str):
+    """The texts `_repair` (:53-78) would try, in its order; a candidate that does not differ from its predecessor is not a candidate."""
     t = s.strip()
     base = t
-    if _BRACKETS.match(t) and ("'" in t and '"' not in t):
+    quoted = bool(_BRACKETS.match(t)) and "'" in t and '"' not in t
+    if quoted:
         base = t.replace("'", '"')
-        if parses(base):
-            return base
-    cand = _TRAILING_COMMA.sub(r"\1", base)
-    if cand != base and parses(cand):
-        return cand
-    if not t.startswith("{") and ":" in t and t.count("{") == 0 and t.count("}") == 0:
-        cand = "{" + t + "}"
-        if parses(cand):
-            return cand
-    return None
+        yield base
+    without_commas = _TRAILING_COMMA.sub(r"\1", base)
+    if without_commas != base:
+        yield without_commas
+    bare = not t.startswith("{") and ":" in t and "{" not in t and "}" not in t
+    if bare:
+        yield "{" + t + "}"
+
+
+def repair(s: str) -> Optional[str]:
+    return next((c for c in candidates(s) if parses(c)), None)
 
 
 def hook(result: Any) -> Dict[str, Any]:
