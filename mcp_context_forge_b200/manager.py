@@ -103,6 +103,12 @@ class BatchedPluginManager(PluginManager):
 
     def __init__(self, *args: Any, window_us: int = 0, max_wave: int = 8192, device: int = 0, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
+        # built on the executor's internals as the in-tree restatement has them (registry of hook refs, config, timeout).  Under an installed
+        # cpex whose manager is shaped differently this must fail at construction, loudly — not at the first request.
+        reg = getattr(self, "_registry", None)
+        if not callable(getattr(reg, "get_hook_refs_for_hook", None)) or not hasattr(self, "_config") or not hasattr(self, "_timeout"):
+            raise RuntimeError("BatchedPluginManager: the installed cpex PluginManager does not expose the registry / config internals the chain replay "
+                               "reads; run the drop-in plugins under cpex's own manager (per-plugin coalescing, batching.GpuBatcher) instead")
         self.window_us = window_us
         self.max_wave = max_wave
         self._device = device
