@@ -1081,6 +1081,7 @@ CF_HD void toon_emit(Ctx& c, uint32_t root) {
       newline(c, pre + (i == 0 ? ind : fi));
       if (i == 0) { c.out.put('-'); c.out.put(' '); }
       emit_key(c, N[k], pre);
+      if (c.err) break;                                         // the key is encoded first (toon.py:396): its ValueError precedes the .keys() crash below
       uint32_t vt = N[v].t & J_TYPE;
       if (vt == J_ARR && N[v].len) {
         if (i == 0) {

@@ -143,3 +143,19 @@ def test_duplicate_keys_last_wins_small_and_huge_objects():
     text = '{"a\\u0062c": 1, "x": 2, "abc": 3}'
     st, got = hs.toon_host(text, unlimited=True)
     assert st == 0 and got == toon_ref.encode(toon_ref.loads_strict(text)) == "abc: 3\nx: 2"
+
+
+def test_error_precedence_key_before_columnar_crash():
+    """A list item whose FIRST key cannot be encoded (control character -> ValueError, toon.py:396) and whose value is a list that would crash the
+    unchecked `.keys()` (AttributeError, toon.py:400-404): the reference encodes the key first, so ValueError (status 3) wins — found by
+    tools/fuzz_vs_reference.py against the reference's own toon.py (the sequential encoder used to report 4)."""
+    for t in ['[2,{"A.b":"null"},{"A\\b":[0,"trail ",true,"Z1",null]}]', '[{"k\\u0001":[1,2]}]', '{"x":[{"\\u0007":[0]},3]}']:
+        assert hs.toon_host(t, unlimited=True) == (3, None), t
+        st, _ = hs.toon_tp(t, unlimited=True)
+        assert st in (3, 7), t
+        try:
+            toon_ref.encode(toon_ref.loads_strict(t))
+            raise AssertionError("the oracle should raise ValueError")
+        except ValueError:
+            pass
+    assert hs.toon_host('[{"k":[1,2]}]', unlimited=True)[0] == 4           # the crash alone is still an AttributeError
