@@ -9,7 +9,9 @@ host logic identical to the reference (:221-235, :260-275, :305-326, :328-363).
 """
 from __future__ import annotations
 
+import json
 import logging
+import re
 import time
 from typing import Any, Dict, List, Optional
 
@@ -19,6 +21,93 @@ from ..cpex_compat.framework import fast_construct
 from ..framework import Plugin, PluginConfig, PluginContext, ToolPostInvokePayload, ToolPostInvokeResult
 
 logger = logging.getLogger(__name__)
+
+
+_KEY_RAW = re.compile(r"^[A-Za-z_][A-Za-z0-9_.]*$")             # toon.py `_VALID_KEY_RE`: such a key is written as it is, any other is quoted
+_RESERVED = ("null", "true", "false")
+
+
+def _first_error(v: Any) -> Optional[BaseException]:
+    """The exception `toon.encode(v)` raises first, found by walking `v` in the encoder's own order (toon.py:82-565): the `ValueError` of the
+    first quoted string that holds a control character other than \\n \\r \\t (:264-279; keys of a columnar table are never quoted, its
+    values are visited row by row in the first row's key order), or the `AttributeError` of the unchecked `.keys()` when the FIRST field of
+    an object inside a list is a non-empty list that is not made of objects (:400-404 -> :479-497).  Only called on the error path of
+    `skip_on_error: false`, to word the exception like the reference does — the kernel's status already says WHICH kind it is."""
+    def string(s: str) -> None:
+        for ch in s:
+            if ord(ch) < 32 and ch not in "\n\r\t":
+                raise ValueError(f"Cannot encode control character U+{ord(ch):04X} in TOON")
+
+    def key(k: str) -> None:
+        if not (k and _KEY_RAW.match(k) and k not in _RESERVED):
+            string(k)
+
+    def simple(x: Any) -> bool:
+        return x is None or isinstance(x, (bool, int, float, str))
+
+    def columnar(arr: list) -> bool:                            # _try_columnar_encoding up to its decision; visits the rows when it says yes
+        first = list(arr[0].keys())                             # AttributeError of a non-dict, worded by Python itself
+        if not first:
+            return False
+        for obj in arr[1:]:
+            if set(obj.keys()) != set(first):
+                return False
+        for obj in arr:
+            if not all(simple(x) for x in obj.values()):
+                return False
+        for obj in arr:
+            for k in first:
+                value(obj[k])
+        return True
+
+    def array(arr: list) -> None:
+        if not arr:
+            return
+        if all(isinstance(x, dict) for x in arr) and columnar(arr):
+            return
+        for x in arr:                                           # primitives in order; an object is a list item; a list is an array of its own
+            if isinstance(x, dict):
+                list_item(x)
+            else:
+                value(x)
+
+    def list_item(obj: dict) -> None:
+        for i, (k, x) in enumerate(obj.items()):
+            key(k)
+            if isinstance(x, list) and x:
+                if i == 0 and columnar(x):
+                    continue
+                array(x)
+            else:
+                value(x)
+
+    def value(x: Any) -> None:
+        if isinstance(x, str):
+            string(x)
+        elif isinstance(x, list):
+            array(x)
+        elif isinstance(x, dict):
+            for k, y in x.items():
+                key(k)
+                value(y)
+
+    try:
+        value(v)
+    except (ValueError, AttributeError) as exc:
+        return exc
+    return None
+
+
+def _encode_error(status: int, text: str) -> BaseException:
+    """The exception of a unit the kernel reported as TOON_VALUE_ERROR / TOON_ATTR_ERROR, with the reference's wording."""
+    kind = ValueError if status == engine.TOON_VALUE_ERROR else AttributeError
+    try:
+        exc = _first_error(json.loads(text))
+    except (ValueError, RecursionError):
+        exc = None
+    if isinstance(exc, kind):
+        return exc
+    return kind("Cannot encode control character in TOON" if kind is ValueError else "object has no attribute 'keys'")
 
 
 class ToonEncoderPlugin(Plugin):
@@ -169,9 +258,7 @@ class ToonEncoderPlugin(Plugin):
                 total_new += len(toon_bytes)
             elif status in (engine.TOON_VALUE_ERROR, engine.TOON_ATTR_ERROR):
                 if not self._skip_on_error:
-                    if status == engine.TOON_VALUE_ERROR:
-                        raise ValueError("Cannot encode control character in TOON")
-                    raise AttributeError("object has no attribute 'keys'")
+                    raise _encode_error(status, raws[i])
                 logger.warning(f"ToonEncoder: Failed to encode '{tool_name}' to TOON")
                 new_content.append(item)
             elif status == engine.TOON_NOT_SMALLER:

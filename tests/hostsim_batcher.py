@@ -86,6 +86,17 @@ def _text(u) -> str:
     return u if isinstance(u, str) else bytes(u).decode("utf-8", "surrogatepass")
 
 
+def _toon(t: str, report_errors: bool):
+    """cf_toon's contract per unit.  With CF_TOON_REPORT_ERRORS the encoder runs to the end even when the output has outgrown the input, so a
+    ValueError / AttributeError anywhere in the document is reported; the text is kept only when strictly smaller (include/cfgpu.h)."""
+    if not report_errors:
+        return hs.toon_host(t)
+    st, txt = hs.toon_host(t, unlimited=True)
+    if st == 0 and len(txt.encode("utf-8", "surrogatepass")) >= len(t.encode("utf-8", "surrogatepass")):
+        return 1, None                                          # CF_TOON_NOT_SMALLER
+    return st, txt
+
+
 class SimBatcher(batching.GpuBatcher):
     """GpuBatcher whose synchronous cores run on the simulator (the asyncio coalescing above them is the product's)."""
 
@@ -131,7 +142,7 @@ class SimBatcher(batching.GpuBatcher):
         for g in groups:
             row = []
             for u in g:
-                st, txt = hs.toon_host(_text(u))
+                st, txt = _toon(_text(u), report_errors)
                 row.append((st, txt.encode("utf-8") if st == 0 else None))
             res.append(row)
         return res
@@ -148,7 +159,7 @@ def sim_launch(self, chain, units, stages):
             rew = sp.sub(u)
         tstat, ttxt = 8, None                                   # CF_TOON_SKIPPED
         if st & 8 and rew is None:
-            tstat, t = hs.toon_host(u)
+            tstat, t = _toon(u, bool(chain.toon_flags & 1))
             ttxt = t.encode("utf-8") if tstat == 0 else None
         out.append(mgr.UnitResult(bm, rew, tstat, ttxt))
     return out

@@ -179,3 +179,29 @@ def test_batched_manager_serves_two_event_loops(sim):
                 for h in range(3):
                     assert [tm.norm(x) for x in out[k][r * 3 + h]] == [tm.norm(x) for x in exp[h]], (k, r, h)
         assert not bat._pending and not bat._busy
+
+
+def test_toon_encoder_raises_with_the_reference_wording(sim):
+    """`skip_on_error: false`: the kernel's status says WHICH error (ValueError / AttributeError, in the encoder's order); the exception's wording —
+    the code point of the first control character a quoted string holds, the type that has no `.keys()` — is the reference's (toon.py:279, :480),
+    checked against the reference itself by tools/fuzz_vs_reference.py and fuzz_plugins_vs_reference.py."""
+    from mcp_context_forge_b200.plugins.toon_encoder import ToonEncoderPlugin, _first_error
+
+    plug = ToonEncoderPlugin(fw.PluginConfig(name="te", kind="x", hooks=["tool_post_invoke"], config={"min_size_bytes": 5, "skip_on_error": False}))
+
+    def call(doc):
+        res = {"content": [{"type": "text", "text": json.dumps(doc)}]}
+        return run(plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result=res), CTX))
+
+    for doc, exc, msg in [({"k": "ctrl\x01"}, ValueError, "Cannot encode control character U+0001 in TOON"),
+                          ([{"c": "ok"}, {"c": "tab\tbell\x07 and \x02"}], ValueError, "Cannot encode control character U+0007 in TOON"),
+                          ({"a\x1fb": 1, "z": "\x00"}, ValueError, "Cannot encode control character U+001F in TOON"),
+                          ([{"x": [1, 2]}, 5], AttributeError, "'int' object has no attribute 'keys'"),
+                          ({"m": [{"x": ["s"], "y": "\x01"}, 5]}, AttributeError, "'str' object has no attribute 'keys'"),
+                          ([2, {"A.b": "null"}, {"A\b": [0, "trail ", True]}], ValueError, "Cannot encode control character U+0008 in TOON")]:
+        with pytest.raises(exc) as ei:
+            call(doc)
+        assert str(ei.value) == msg, doc
+    # the keys of a columnar table are never quoted: no error, the table is written
+    assert _first_error([{"a\x01": 1, "b": 2}, {"a\x01": 3, "b": 4}]) is None
+    assert call([{"a\x01": 1, "bbbbbbbb": 2}, {"a\x01": 3, "bbbbbbbb": 4}]).modified_payload is not None

@@ -27,7 +27,7 @@ REFS = {"harm": "plugins.harmful_content_detector.harmful_content_detector.Harmf
         "code": "plugins.code_safety_linter.code_safety_linter.CodeSafetyLinterPlugin", "repair": "plugins.json_repair.json_repair.JSONRepairPlugin",
         "toon": "plugins.toon_encoder.toon_encoder.ToonEncoderPlugin"}
 WORDS = ["hello", "crap", "crud", "innovative", "kill him", "suicide", "normal text", "Kill her", "revolutionary idea", "I want to die", "racial slur", "fine", "DROP table t -- crap",
-         "select 1 /* c */", "delete from t", "eval(x)", "rm -rf /", "é", "ſuicide", "日本語", "user@example.com", "12", "update t set a=1", "groundbreaking", "x", ""]
+         "select 1 /* c */", "delete from t", "eval(x)", "rm -rf /", "é", "ſuicide", "日本語", "user@example.com", "12", "update t set a=1", "groundbreaking", "x", "", "bell\x07"]
 
 
 def config(rng):
@@ -43,7 +43,7 @@ def config(rng):
         {"k": "sql", "hooks": ["prompt_pre_fetch", "tool_pre_invoke"], "mode": mode(), "priority": 45, "config": rng.choice([{"block_on_violation": False}, {}, {"strip_comments": False}])},
         {"k": "code", "hooks": ["tool_post_invoke"], "mode": mode(), "priority": rng.choice([120, 30]), "config": {}},
         {"k": "repair", "hooks": ["tool_post_invoke"], "mode": mode(), "priority": 145, "config": {}},
-        {"k": "toon", "hooks": ["tool_post_invoke"], "mode": "sequential", "priority": 900, "config": rng.choice([{"min_size_bytes": 10}, {}, {"min_size_bytes": 10, "add_format_marker": False}]),
+        {"k": "toon", "hooks": ["tool_post_invoke"], "mode": mode(), "priority": 900, "config": rng.choice([{"min_size_bytes": 10}, {}, {"min_size_bytes": 10, "add_format_marker": False}, {"min_size_bytes": 10, "skip_on_error": False}]),
          "conditions": rng.choice([None, [{"tools": ["t", "u"]}]])},
     ]
     return [p for p in plugs if rng.random() < 0.8]

@@ -21,7 +21,7 @@ WORDS = ["kill", "myself", "suicide", "self-harm", "want", "to", "die", "him", "
          "crud", "innovative", "groundbreaking", "revolutionary", "the", "a", "of", "x", "Kill", "KILL", "ſuicide", "Kill", "é", "ß", "naïve", "日本語", "\U0001f600", "12", "_", "-", ".",
          ",", "\n", "DROP", "drop table t", "DELETE FROM t", "delete from t where x=1", "UPDATE t SET a=1", "update t set a=1 where b=2", "-- comment", "/* c */", "select * from t",
          "eval(", "exec (", "os.system('x')", "subprocess.run([", "rm -rf /", "'; --", "\"%s\" % x", "f\"{x}\"", "{} + {}", "buy now", "free", "xxy", "user@example.com", "555-1234", "a b",
-         "zzz", "TRUNCATE", "alter", "GRANT all", "where", "#", "/*", "*/", "--", ";"]
+         "zzz", "TRUNCATE", "alter", "GRANT all", "where", "#", "/*", "*/", "--", ";", "bell\x07", "\x01"]
 SEPS = [" ", " ", " ", "", "  ", "\n", "-", "_", ".", "é", "1", "\t", ", "]
 RULES = [("crap", "crud"), ("crud", "yikes"), (r"\bkill\b", "[k]"), ("(unclosed", "x"), (r"\d+", "#"), (r"cr[au]p+", "X"), (r"a|ab|abc", "<>"), ("a*", "-"), (r"(a)|b", r"[\1]"), (r"x*", "."),
          (r"(\w+)@(\w+)\.com", r"\2 at \1"), (r"\s+", " "), (r"(?i)kill", "K"), (r"é", "e"), (r"(?P<n>\d)(\d)", r"\g<n>-\2"), (r"^", ">"), (r"$", "<"), (r"\b", "|"), (r"[^\W\d_]+", "w"),
@@ -32,7 +32,8 @@ HARM_CFG = [None, {"block_on": ["violence"]}, {"categories": {"spam": ["buy now"
 SQL_CFG = [None, {"block_on_violation": False}, {"block_on_violation": False, "require_parameterization": True, "fields": ["sql", "query"]}, {"strip_comments": False},
            {"fields": ["q"], "blocked_statements": [r"\bDROP\b", r"(?i)truncate\s+table"]}, {"require_parameterization": True}, {"block_delete_without_where": False, "block_update_without_where": False}]
 CODE_CFG = [None, {"blocked_patterns": [r"curl\s+\S+\s*\|\s*sh", r"(?i)\bdrop\b", r"import\s+os"]}, {"blocked_patterns": []}, {"blocked_patterns": [r"rm\s+-rf", r"é+"]}]
-TOON_CFG = [{"min_size_bytes": 10}, {"min_size_bytes": 10, "max_size_bytes": 300}, {"min_size_bytes": 10, "add_format_marker": False}, {"min_size_bytes": 40, "exclude_tools": ["other"]}]
+TOON_CFG = [{"min_size_bytes": 10}, {"min_size_bytes": 10, "max_size_bytes": 300}, {"min_size_bytes": 10, "add_format_marker": False}, {"min_size_bytes": 40, "exclude_tools": ["other"]}, {"min_size_bytes": 10, "skip_on_error": False},
+            {"min_size_bytes": 10, "skip_on_error": False, "add_format_marker": False}]
 
 
 def text(rng, n=None):
@@ -88,7 +89,7 @@ def main() -> int:
     rng = random.Random(seed)
     loop = asyncio.new_event_loop()
     t0 = time.time()
-    n = bad = rejected = 0
+    n = bad = rejected = raised = 0
 
     def payloads(kind):
         out = []
@@ -133,18 +134,19 @@ def main() -> int:
                     try:
                         exp = norm(loop.run_until_complete(getattr(ref, hook)(pa, ctx)))
                     except Exception as exc:  # noqa: BLE001 - the reference raises: so must the drop-in
-                        exp = {"raises": type(exc).__name__}
+                        exp = {"raises": type(exc).__name__, "message": str(exc)}
                     try:
                         got = norm(loop.run_until_complete(getattr(ours, hook)(pb, ctx)))
                     except Exception as exc:  # noqa: BLE001
-                        got = {"raises": type(exc).__name__}
+                        got = {"raises": type(exc).__name__, "message": str(exc)}
                     n += 1
+                    raised += "raises" in exp
                     if exp != got:
                         bad += 1
                         if bad <= 6:
                             print("BAD", name, hook, json.dumps(cfg, ensure_ascii=False)[:300], "\n  payload  ", repr(p)[:400], "\n  reference", json.dumps(exp, ensure_ascii=False)[:500],
                                   "\n  drop-in  ", json.dumps(got, ensure_ascii=False)[:500])
-    print(f"seed={seed} rounds={rounds} hook_calls={n} configs_rejected_loudly={rejected} bad={bad} time={time.time() - t0:.1f}s")
+    print(f"seed={seed} rounds={rounds} hook_calls={n} configs_rejected_loudly={rejected} reference_raised={raised} bad={bad} time={time.time() - t0:.1f}s")
     return 1 if bad else 0
 
 

@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import hostsim_util as hs  # noqa: E402
 from fuzz_toon_tp import make_gen  # noqa: E402
+from mcp_context_forge_b200.plugins.toon_encoder import _encode_error  # noqa: E402
 from oracle import toon_ref  # noqa: E402
 
 
@@ -59,9 +60,11 @@ def expected(toon, t: str):
         return None
     try:
         return (0, toon.encode(doc))
-    except ValueError:
+    except ValueError as exc:
+        expected.message = str(exc)
         return (3, None)
-    except AttributeError:
+    except AttributeError as exc:
+        expected.message = str(exc)
         return (4, None)
 
 
@@ -75,7 +78,7 @@ def main() -> int:
     rng = random.Random(seed)
     case = make_gen(rng)
     t0 = time.time()
-    done = skipped = handed = bad = 0
+    done = skipped = handed = bad = worded = 0
     for it in range(n):
         t = case()
         exp = expected(toon, t)
@@ -94,11 +97,18 @@ def main() -> int:
             orc = (2 if exp[0] == 2 else 3, None)
         except toon_ref.ToonCrash:
             orc = (4, None)
+        if exp[0] in (3, 4):                                    # the wording the drop-in gives the exception (skip_on_error: false) == the reference's
+            worded += 1
+            msg = str(_encode_error(exp[0], t))
+            if msg != expected.message:
+                bad += 1
+                if bad <= 8:
+                    print("BAD MESSAGE", repr(t)[:400], "\n   reference", expected.message, "\n   drop-in  ", msg)
         if not (seq == exp and tp == exp and orc == exp):
             bad += 1
             if bad <= 8:
                 print("BAD", repr(t)[:400], "\n   reference", repr(exp)[:300], "\n   seq      ", repr(seq)[:300], "\n   tp       ", repr(tp)[:300], "\n   oracle   ", repr(orc)[:300])
-    print(f"seed={seed} cases={n} compared={done} skipped={skipped} handed_over={handed} bad={bad} time={time.time() - t0:.1f}s")
+    print(f"seed={seed} cases={n} compared={done} skipped={skipped} handed_over={handed} error_messages_compared={worded} bad={bad} time={time.time() - t0:.1f}s")
     return 1 if bad else 0
 
 
