@@ -33,7 +33,7 @@ WORDS = ["hello", "crap", "crud", "innovative", "kill him", "suicide", "normal t
 def config(rng):
     """One random chain: which plugins, their modes / priorities / configs (the same dict rendered with either set of `kind`s)."""
     rules = [["crap", "crud"], ["crud", "yikes"], ["(?i)(kill) (him|her)", r"\2 <\1>"], [r"\d+", "#"], ["a*", "-"], [r"(\w+)@(\w+)\.com", r"\2 at \1"], [r"\s+", " "], ["é", "e"]]
-    mode = lambda: rng.choice(["sequential", "sequential", "transform", "audit"])      # noqa: E731
+    mode = lambda: rng.choice(["sequential", "sequential", "transform", "audit", "enforce", "enforce_ignore_error", "permissive", "fire_and_forget", "concurrent", "disabled"])   # noqa: E731
     plugs = [
         {"k": "harm", "hooks": ["prompt_pre_fetch", "tool_post_invoke"], "mode": mode(), "priority": rng.choice([96, 40, 500]),
          "config": rng.choice([{}, {"block_on": ["violence"]}, {"categories": {"spam": ["buy now", r"\bfine\b"]}, "block_on": ["spam", "self_harm"]}])},
@@ -46,19 +46,25 @@ def config(rng):
         {"k": "toon", "hooks": ["tool_post_invoke"], "mode": mode(), "priority": 900, "config": rng.choice([{"min_size_bytes": 10}, {}, {"min_size_bytes": 10, "add_format_marker": False}, {"min_size_bytes": 10, "skip_on_error": False}]),
          "conditions": rng.choice([None, [{"tools": ["t", "u"]}]])},
     ]
+    conds = [None, None, None, [{"tools": ["t", "u"]}], [{"server_ids": ["s1"]}], [{"tenant_ids": ["acme"]}], [{"user_patterns": ["ali"]}], [{"prompts": ["p"]}, {"tools": ["other"]}],
+             [{"server_ids": ["s2"], "tools": ["t"]}], [{"user_patterns": ["bob*", "zed"]}]]
+    for p in plugs:
+        p["on_error"] = rng.choice(["fail", "fail", "ignore", "disable"])
+        if "conditions" not in p:
+            p["conditions"] = rng.choice(conds)
     return [p for p in plugs if rng.random() < 0.8]
 
 
-def render(plugs, kinds):
+def render(plugs, kinds, fail_all=False):
     import yaml
 
     out = []
     for p in plugs:
-        d = {"name": p["k"], "kind": kinds[p["k"]], "hooks": p["hooks"], "mode": p["mode"], "priority": p["priority"], "config": p["config"]}
+        d = {"name": p["k"], "kind": kinds[p["k"]], "hooks": p["hooks"], "mode": p["mode"], "priority": p["priority"], "config": p["config"], "on_error": p["on_error"]}
         if p.get("conditions"):
             d["conditions"] = p["conditions"]
         out.append(d)
-    return yaml.safe_dump({"plugins": out, "plugin_settings": {"plugin_timeout": 120}})
+    return yaml.safe_dump({"plugins": out, "plugin_settings": {"plugin_timeout": 120, "fail_on_plugin_error": fail_all}})
 
 
 def main() -> int:
@@ -89,8 +95,9 @@ def main() -> int:
         plugs = config(rng)
         with tempfile.TemporaryDirectory() as td:
             a, b = os.path.join(td, "ref.yaml"), os.path.join(td, "ours.yaml")
-            open(a, "w").write(render(plugs, REFS))
-            open(b, "w").write(render(plugs, OURS))
+            fail_all = rng.random() < 0.2
+            open(a, "w").write(render(plugs, REFS, fail_all))
+            open(b, "w").write(render(plugs, OURS, fail_all))
             seq = fw.PluginManager(a, timeout=120, hook_policies=tm.POL)
             bat = BatchedPluginManager(b, timeout=120, hook_policies=tm.POL)
             loop.run_until_complete(seq.initialize())
@@ -119,7 +126,8 @@ def main() -> int:
                 else:
                     result = rng.choice([{"text": rng.choice(WORDS), "other": rng.choice(WORDS)}, None, 5, [rng.choice(WORDS)], {"a": {"b": rng.choice(WORDS)}, "c": [rng.choice(WORDS), 3]}])
                 post.append(fw.ToolPostInvokePayload(name=rng.choice(["t", "u", "other"]), result=result))
-            gcs = [fw.GlobalContext(request_id=f"r{i}") for i in range(nreq)]
+            gcs = [fw.GlobalContext(request_id=f"r{i}", server_id=rng.choice([None, "s1", "s2"]), tenant_id=rng.choice([None, "acme", "other"]), user=rng.choice([None, "alice", "bob7", "zed"]))
+                   for i in range(nreq)]
             for hook, pls in (("prompt_pre_fetch", pre), ("tool_pre_invoke", tpre), ("tool_post_invoke", post)):
                 for vae in (False, True):
                     async def wave(m):
