@@ -66,9 +66,26 @@ def main() -> int:
                 print("KEY", repr(k), "reference", exp, "kernel", got, "oracle", orc)
     keys = sorted(seen)
 
+    import math
+    import struct
+
+    def rand_prim():
+        k = rng.random()
+        if k < 0.35:                                            # any finite double: ryu's shortest digits and serde_json's layout (oracle: repr() digits)
+            x = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
+            return x if math.isfinite(x) else 0.5
+        if k < 0.55:
+            return rng.randint(-2 ** 63, 2 ** 64 - 1) >> rng.randint(0, 63)
+        if k < 0.9:                                             # strings over controls, quotes, separators, BMP and astral code points: serde_json's escapes
+            lo, hi = rng.choice([(0x00, 0x7F), (0x00, 0x1F), (0x7F, 0xFF), (0x2000, 0x2070), (0x3040, 0x30FF), (0x1F600, 0x1F64F), (0xFFF0, 0xFFFD)])
+            return "".join(chr(rng.randint(lo, hi)) for _ in range(rng.choice([0, 1, 2, 5, 17, 40])))
+        return round(rng.uniform(-1e9, 1e9), rng.randint(0, 12))
+
     def rand_obj(depth):
         r = rng.random()
         if depth <= 0 or r < 0.3:
+            if rng.random() < 0.5:
+                return rand_prim()
             return rng.choice(["v", 1, 2.5, True, None, "secret-value", -7, 1e16, 0.1, 10 ** 15, "é", "q\"\\\n\t\x01/", 1.0, 100.0, 1e-7, 123456789012, "", 0, -0.0, 5e-324, 1.7976931348623157e308])
         if r < 0.55:
             return [rand_obj(depth - 1) for _ in range(rng.randint(0, 4))]

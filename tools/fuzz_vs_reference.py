@@ -3,7 +3,7 @@ body csrc/json_tp.h on the 32-fibre warp emulator) against the REFERENCE'S OWN `
 /root/reference — no restatement in between (the oracle is compared too, so a gap in it shows).  Random JSON documents from the generator of
 tools/fuzz_toon_tp.py (adversarial keys / strings / numbers, tables, byte-level mutations).  orjson is not installable here: the strict stdlib
 parser stands in, and documents that would expose an orjson / json delta (integers beyond 64 bits, lone surrogates, non-finite floats) are skipped.
-usage: python tools/fuzz_vs_reference.py [seed] [cases]"""
+usage: python tools/fuzz_vs_reference.py [seed] [cases] [gen2]"""
 import importlib.util
 import json
 import math
@@ -68,6 +68,75 @@ def expected(toon, t: str):
         return (4, None)
 
 
+def make_gen2(rng):
+    """A second generator: strings over the whole BMP + astral planes (controls, quotes, separators, RTL, combining marks), numbers of every
+    magnitude orjson and json agree on, deeper nesting, wide tables with missing / reordered / nested cells."""
+    import struct
+
+    pools = [(0x20, 0x7E), (0x00, 0x1F), (0x7F, 0xA0), (0xA0, 0x17F), (0x300, 0x36F), (0x590, 0x6FF), (0x2000, 0x206F), (0x3040, 0x30FF), (0xE000, 0xE010), (0xFFF0, 0xFFFD), (0x1F600, 0x1F64F)]
+
+    def rstr():
+        k = rng.random()
+        if k < 0.3:
+            return rng.choice(["", "null", "true", "false", "-", "- x", "1e5", "0x10", "007", "1.", ".5", "+3", "-0", "1_000", "NaN", "Infinity", " a", "a ", "a,b", "a:b", "a\"b", "[1]", "{}", "a\\b", "#", "x\ny", "\t"])
+        n = rng.choice([1, 1, 2, 3, 5, 8, 20, 64])
+        lo, hi = rng.choice(pools)
+        return "".join(chr(rng.randint(*rng.choice([(lo, hi), (0x61, 0x7A)]))) for _ in range(n))
+
+    def rnum():
+        k = rng.random()
+        if k < 0.3:
+            return rng.randint(-2 ** 63, 2 ** 63 - 1) >> rng.randint(0, 62)
+        if k < 0.4:
+            return rng.choice([0, -0.0, 2 ** 53, 2 ** 53 + 1, -2 ** 63, 2 ** 64 - 1, 1e15, 1e16, 1e21, 1e22, 123456789012345.6, 0.1, 1 / 3, 5e-324, 1.7976931348623157e308, 2.2250738585072014e-308])
+        if k < 0.7:
+            x = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
+            return x if math.isfinite(x) else 1.5
+        return round(rng.uniform(-1e6, 1e6), rng.randint(0, 10))
+
+    def rprim():
+        k = rng.random()
+        return rstr() if k < 0.45 else rnum() if k < 0.8 else rng.choice([None, True, False])
+
+    def rkey():
+        return rstr() if rng.random() < 0.5 else rng.choice(["id", "name", "a", "b", "value", "x.y", "_p", "k1", "A", "items", "é"])
+
+    def rval(d):
+        k = rng.random()
+        if d <= 0 or k < 0.25:
+            return rprim()
+        if k < 0.4:
+            return [rprim() for _ in range(rng.randint(0, 6))]
+        if k < 0.6:
+            keys = [rkey() for _ in range(rng.randint(1, 5))]
+            rows = []
+            for _ in range(rng.randint(1, 6)):
+                ks = list(keys)
+                q = rng.random()
+                if q < 0.1:
+                    rng.shuffle(ks)
+                elif q < 0.15:
+                    ks = ks[1:]
+                rows.append({kk: (rprim() if rng.random() < 0.93 else rval(d - 1)) for kk in ks})
+            if rng.random() < 0.1:
+                rows.insert(rng.randint(0, len(rows)), rval(d - 1))
+            return rows
+        if k < 0.85:
+            return {rkey(): rval(d - 1) for _ in range(rng.randint(0, 5))}
+        return [rval(d - 1) for _ in range(rng.randint(0, 4))]
+
+    def case():
+        v = rval(rng.randint(0, 9))
+        k = rng.random()
+        if k < 0.5:
+            return json.dumps(v, separators=(",", ":"), ensure_ascii=False)
+        if k < 0.75:
+            return json.dumps(v, ensure_ascii=True)
+        return json.dumps(v, indent=rng.choice([None, 1, 3]), ensure_ascii=False)
+
+    return case
+
+
 def main() -> int:
     if not os.path.isdir(REF):
         print("fuzz_vs_reference: /root/reference is not here (container-only tool)")
@@ -76,7 +145,7 @@ def main() -> int:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
     toon = load_reference_toon()
     rng = random.Random(seed)
-    case = make_gen(rng)
+    case = make_gen2(rng) if len(sys.argv) > 3 and sys.argv[3] == "gen2" else make_gen(rng)
     t0 = time.time()
     done = skipped = handed = bad = worded = 0
     for it in range(n):
