@@ -99,7 +99,7 @@ def main() -> int:
             open(a, "w").write(render(plugs, REFS, fail_all))
             open(b, "w").write(render(plugs, OURS, fail_all))
             seq = fw.PluginManager(a, timeout=120, hook_policies=tm.POL)
-            bat = BatchedPluginManager(b, timeout=120, hook_policies=tm.POL)
+            bat = BatchedPluginManager(b, timeout=120, hook_policies=tm.POL, max_wave=rng.choice([8192, 8192, 7, 1, 33]), window_us=rng.choice([0, 0, 50, 400]))
             loop.run_until_complete(seq.initialize())
             try:
                 loop.run_until_complete(bat.initialize())

@@ -3,7 +3,7 @@ body csrc/json_tp.h on the 32-fibre warp emulator) against the REFERENCE'S OWN `
 /root/reference — no restatement in between (the oracle is compared too, so a gap in it shows).  Random JSON documents from the generator of
 tools/fuzz_toon_tp.py (adversarial keys / strings / numbers, tables, byte-level mutations).  orjson is not installable here: the strict stdlib
 parser stands in, and documents that would expose an orjson / json delta (integers beyond 64 bits, lone surrogates, non-finite floats) are skipped.
-usage: python tools/fuzz_vs_reference.py [seed] [cases] [gen2]"""
+usage: python tools/fuzz_vs_reference.py [seed] [cases] [gen1|gen2|synth]"""
 import importlib.util
 import json
 import math
@@ -145,7 +145,16 @@ def main() -> int:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
     toon = load_reference_toon()
     rng = random.Random(seed)
-    case = make_gen2(rng) if len(sys.argv) > 3 and sys.argv[3] == "gen2" else make_gen(rng)
+    which = sys.argv[3] if len(sys.argv) > 3 else "gen1"
+    if which == "synth":                                        # the bench's payload shapes (tabular / nested config / prose in JSON), 200 B .. 70 KB
+        from mcp_context_forge_b200 import synth
+
+        def case():
+            shape = rng.choice("AABBC")
+            p = synth.payload(shape, rng.choice([200, 600, 2000, 5000, 16384, 16384, 40000, 70000]), seed=rng.randrange(1 << 30), hit_rate=rng.choice([0, 1e-4, 1e-2]))
+            return p if shape != "C" else json.dumps({"title": "d", "body": p}, ensure_ascii=rng.random() < 0.3)
+    else:
+        case = make_gen2(rng) if which == "gen2" else make_gen(rng)
     t0 = time.time()
     done = skipped = handed = bad = worded = 0
     for it in range(n):
@@ -173,6 +182,15 @@ def main() -> int:
                 bad += 1
                 if bad <= 8:
                     print("BAD MESSAGE", repr(t)[:400], "\n   reference", expected.message, "\n   drop-in  ", msg)
+        # the product's rule on top (include/cfgpu.h): the text is kept only when strictly smaller than the JSON it came from
+        small = exp if (exp[0] != 0 or len(exp[1].encode("utf-8")) < len(t.encode("utf-8"))) else (1, None)
+        seq2, tp2 = hs.toon_host(t), hs.toon_tp(t, report_errors=True)
+        if tp2[0] == 7:
+            tp2 = small
+        if not (seq2 == small and tp2 == small):
+            bad += 1
+            if bad <= 8:
+                print("BAD (size rule)", repr(t)[:300], "\n   expected", repr(small)[:200], "\n   seq", repr(seq2)[:200], "\n   tp ", repr(tp2)[:200])
         if not (seq == exp and tp == exp and orc == exp):
             bad += 1
             if bad <= 8:
