@@ -224,3 +224,21 @@ def test_copy_on_write_dict_is_a_dict_that_never_writes_through():
     del d["edits"]
     assert src == {"path": "sql.txt", "edits": [{"new": "DROP table tab1;"}]} and d == {"path": "other"} and d.modified == {"path", "edits"} and d.original is src
     assert fw.ToolPreInvokePayload(name="echo", args=CopyOnWriteDict({"message": "x"})).args == {"message": "x"}
+
+
+def test_manager_internals_the_gateway_itself_reads():
+    """The gateway reads two protected attributes of the manager (mcpgateway/services/tool_service.py:4142-4160: `_registry.get_hook_refs_for_hook(
+    hook_type=...)`, then `hook_ref.plugin_ref.mode / .conditions / .name / .plugin.config.config`; mcpgateway/services/plugin_service.py:84-130:
+    `_registry.get_all_plugins()`, `_config.plugins`, `plugin_ref.name / .mode / .priority / .hooks / .tags / .plugin.config.{description,author,
+    version,kind,namespace,config}`) — the same ones BatchedPluginManager's replay is built on."""
+    m = _manager(MessageFilter, blocked_words=["spam"])
+    refs = m._registry.get_hook_refs_for_hook(hook_type=fw.AgentHookType.AGENT_PRE_INVOKE)
+    assert len(refs) == 1
+    pr = refs[0].plugin_ref
+    assert (pr.name, pr.mode, pr.priority, list(pr.conditions), pr.plugin.config.config) == ("P", fw.PluginMode.SEQUENTIAL, 50, [], {"blocked_words": ["spam"]})
+    (only,) = m._registry.get_all_plugins()
+    assert only is pr and pr.hooks == ["agent_pre_invoke", "agent_post_invoke"] and pr.tags == []
+    c = pr.plugin.config
+    assert (c.description, c.author, c.version, c.namespace, c.kind) == (None, None, None, None, f"{__name__}.MessageFilter")
+    assert [p.name for p in m._config.plugins] == ["P"] and m.plugin_count == 1 and m.has_hooks_for(fw.AgentHookType.AGENT_POST_INVOKE)
+    assert not m.has_hooks_for(fw.ToolHookType.TOOL_POST_INVOKE)
