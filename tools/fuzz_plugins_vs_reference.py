@@ -55,7 +55,10 @@ def norm(r):
     v = r.violation.model_dump(include={"reason", "description", "code", "details"}) if r.violation is not None else None
     mp = r.modified_payload
     md = {k: x for k, x in (r.metadata or {}).items() if k != "conversion_time_ms"}
-    return json.loads(json.dumps({"cont": r.continue_processing, "violation": v, "args": getattr(mp, "args", None) if mp is not None else "-", "result": getattr(mp, "result", None) if mp is not None else "-",
+    res = getattr(mp, "result", None) if mp is not None else "-"
+    if hasattr(res, "model_dump"):
+        res = res.model_dump()
+    return json.loads(json.dumps({"cont": r.continue_processing, "violation": v, "args": getattr(mp, "args", None) if mp is not None else "-", "result": res,
                                   "metadata": md}, default=str, sort_keys=True))
 
 
@@ -67,7 +70,7 @@ def main() -> int:
     rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     gen_golden.install_shims()
     import pytest
-    from cpex.framework import GlobalContext, PluginConfig, PluginContext, PromptPrehookPayload, ToolPostInvokePayload, ToolPreInvokePayload
+    from cpex.framework import GlobalContext, PluginConfig, PluginContext, PromptPosthookPayload, PromptPrehookPayload, ToolPostInvokePayload, ToolPreInvokePayload
     from plugins.code_safety_linter.code_safety_linter import CodeSafetyLinterPlugin as RCode
     from plugins.deny_filter.deny import DenyListPlugin as RDeny
     from plugins.harmful_content_detector.harmful_content_detector import HarmfulContentDetectorPlugin as RHarm
@@ -104,7 +107,7 @@ def main() -> int:
 
     for rd in range(rounds):
         plan = [
-            ("regex_filter", RRegex, SearchReplacePlugin, {"words": [{"search": s, "replace": r} for s, r in rng.sample(RULES, rng.randint(0, 4))]}, ["prompt_pre_fetch", "tool_pre_invoke", "tool_post_invoke"]),
+            ("regex_filter", RRegex, SearchReplacePlugin, {"words": [{"search": s, "replace": r} for s, r in rng.sample(RULES, rng.randint(0, 4))]}, ["prompt_pre_fetch", "tool_pre_invoke", "tool_post_invoke", "prompt_post_fetch"]),
             ("deny_filter", RDeny, DenyListPlugin, {"words": rng.sample(DENY, rng.randint(0, 4))}, ["prompt_pre_fetch"]),
             ("harmful", RHarm, HarmfulContentDetectorPlugin, rng.choice(HARM_CFG), ["prompt_pre_fetch", "tool_post_invoke"]),
             ("sql_sanitizer", RSql, SQLSanitizerPlugin, rng.choice(SQL_CFG), ["prompt_pre_fetch", "tool_pre_invoke"]),
@@ -120,8 +123,11 @@ def main() -> int:
                 rejected += 1
                 continue
             for hook in hooks:
-                for p in payloads("args" if hook != "tool_post_invoke" else "result"):
-                    if hook == "prompt_pre_fetch":
+                for p in payloads("args" if hook in ("prompt_pre_fetch", "tool_pre_invoke") else "result"):
+                    if hook == "prompt_post_fetch":                                       # a rendered prompt: messages with text content
+                        msgs = {"messages": [{"role": rng.choice(["user", "assistant"]), "content": {"type": "text", "text": text(rng)}} for _ in range(rng.randint(0, 4))]}
+                        mk = lambda: PromptPosthookPayload(prompt_id="p", result=json.loads(json.dumps(msgs)))   # noqa: E731
+                    elif hook == "prompt_pre_fetch":
                         mk = lambda: PromptPrehookPayload(prompt_id="p", args=p)          # noqa: E731
                     elif hook == "tool_pre_invoke":
                         mk = lambda: ToolPreInvokePayload(name="t", args=p)              # noqa: E731
