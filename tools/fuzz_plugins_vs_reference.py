@@ -152,6 +152,12 @@ def main() -> int:
                         if bad <= 6:
                             print("BAD", name, hook, json.dumps(cfg, ensure_ascii=False)[:300], "\n  payload  ", repr(p)[:400], "\n  reference", json.dumps(exp, ensure_ascii=False)[:500],
                                   "\n  drop-in  ", json.dumps(got, ensure_ascii=False)[:500])
+            if callable(getattr(ref, "get_stats", None)) and callable(getattr(ours, "get_stats", None)):      # toon_encoder's counters after the same calls
+                n += 1
+                if ref.get_stats() != ours.get_stats():
+                    bad += 1
+                    if bad <= 6:
+                        print("BAD stats", name, json.dumps(cfg), ref.get_stats(), ours.get_stats())
     print(f"seed={seed} rounds={rounds} hook_calls={n} configs_rejected_loudly={rejected} reference_raised={raised} bad={bad} time={time.time() - t0:.1f}s")
     return 1 if bad else 0
 
