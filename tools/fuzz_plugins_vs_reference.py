@@ -29,6 +29,10 @@ RULES = [("crap", "crud"), ("crud", "yikes"), (r"\bkill\b", "[k]"), ("(unclosed"
 DENY = ["innovative", "groundbreaking", "revolutionary", "a b", "é", "x", "", "zzz", "kill", "Kill", "日本", "\n", "free", "--"]
 HARM_CFG = [None, {"block_on": ["violence"]}, {"categories": {"spam": ["buy now", r"\bfree\b"], "x": ["x+y"]}, "block_on": ["spam"]}, {"block_on": []}, {"block_on": ["self_harm", "hate"]},
             {"categories": {"k": [r"k\w+l", "é+"], "w": [r"\bwhere\b"]}, "block_on": ["k", "w", "violence"]}]
+import re as _re  # noqa: E402
+
+HARM_CFG += [{"categories": {"c": [_re.compile("Kill"), _re.compile("him", _re.I), "Her"], "d": [_re.compile(r"k.ll\s+h", _re.S | _re.I), _re.compile(r"^die", _re.M)]}, "block_on": ["c", "d"]},
+             {"categories": {"e": [_re.compile(r"\bé\w*", _re.I), _re.compile(r"ſ", _re.I), _re.compile(r"(?i)K")]}, "block_on": ["e"]}]
 SQL_CFG = [None, {"block_on_violation": False}, {"block_on_violation": False, "require_parameterization": True, "fields": ["sql", "query"]}, {"strip_comments": False},
            {"fields": ["q"], "blocked_statements": [r"\bDROP\b", r"(?i)truncate\s+table"]}, {"require_parameterization": True}, {"block_delete_without_where": False, "block_update_without_where": False}]
 CODE_CFG = [None, {"blocked_patterns": [r"curl\s+\S+\s*\|\s*sh", r"(?i)\bdrop\b", r"import\s+os"]}, {"blocked_patterns": []}, {"blocked_patterns": [r"rm\s+-rf", r"é+"]}]
@@ -150,14 +154,14 @@ def main() -> int:
                     if exp != got:
                         bad += 1
                         if bad <= 6:
-                            print("BAD", name, hook, json.dumps(cfg, ensure_ascii=False)[:300], "\n  payload  ", repr(p)[:400], "\n  reference", json.dumps(exp, ensure_ascii=False)[:500],
+                            print("BAD", name, hook, repr(cfg)[:300], "\n  payload  ", repr(p)[:400], "\n  reference", json.dumps(exp, ensure_ascii=False)[:500],
                                   "\n  drop-in  ", json.dumps(got, ensure_ascii=False)[:500])
             if callable(getattr(ref, "get_stats", None)) and callable(getattr(ours, "get_stats", None)):      # toon_encoder's counters after the same calls
                 n += 1
                 if ref.get_stats() != ours.get_stats():
                     bad += 1
                     if bad <= 6:
-                        print("BAD stats", name, json.dumps(cfg), ref.get_stats(), ours.get_stats())
+                        print("BAD stats", name, repr(cfg), ref.get_stats(), ours.get_stats())
     print(f"seed={seed} rounds={rounds} hook_calls={n} configs_rejected_loudly={rejected} reference_raised={raised} bad={bad} time={time.time() - t0:.1f}s")
     return 1 if bad else 0
 
