@@ -78,11 +78,12 @@ def test_toon_encoder_plugin_golden(sim):
 
     n = 0
     for block in load("toon.json")["plugin"]:
-        if block["config"] and block["config"].get("skip_on_error") is False:
-            continue                                       # error reporting past the size cut-off is exercised on the GPU path
         plug = ToonEncoderPlugin(fw.PluginConfig(name="te", kind="x", hooks=["tool_post_invoke"], config=block["config"]))
         for c in block["cases"]:
-            if "raises" in c:
+            if "raises" in c:                                   # skip_on_error: false — the reference's exception type (the simulator honours CF_TOON_REPORT_ERRORS)
+                with pytest.raises((ValueError, AttributeError)) as ei:
+                    run(plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result=c["result"]), CTX))
+                assert (type(ei.value).__name__, str(ei.value)) == (c["raises"], c["message"]), c["result"]
                 continue
             r = run(plug.tool_post_invoke(fw.ToolPostInvokePayload(name="t", result=c["result"]), CTX))
             if c["modified"] is None:

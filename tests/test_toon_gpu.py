@@ -53,6 +53,7 @@ def test_plugin_matches_reference_golden(gold):
                 with pytest.raises(Exception) as ei:
                     run(plug.tool_post_invoke(payload, CTX))
                 assert type(ei.value).__name__ == c["raises"]
+                assert str(ei.value) == c["message"]          # worded on the host from the document, in the encoder's order (plugins/toon_encoder.py::_first_error)
                 continue
             r = run(plug.tool_post_invoke(payload, CTX))
             if c["modified"] is None:

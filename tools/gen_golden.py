@@ -303,7 +303,7 @@ def gen_toon():
                 md.pop("conversion_time_ms", None)
                 cases.append({"result": result, "modified": r.modified_payload.result if r.modified_payload else None, "metadata": md})
             except Exception as exc:
-                cases.append({"result": result, "raises": type(exc).__name__})
+                cases.append({"result": result, "raises": type(exc).__name__, "message": str(exc)})
         non_dict = run(plug.tool_post_invoke(ToolPostInvokePayload(name="t", result="str result"), ctx))
         plug_cases.append({"config": cfg, "cases": cases, "stats": plug.get_stats(), "non_dict_modified": non_dict.modified_payload is not None})
     dump("toon.json", {"n_harvested_from_reference_tests": n_harvested, "encode": enc_cases, "helpers": helper, "plugin": plug_cases})
